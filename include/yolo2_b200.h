@@ -1,0 +1,156 @@
+/*
+ * yolo2_b200.h -- C ABI of libyolo2_b200.so: the B200 (sm_100a) kernels behind the detection
+ * hot path of wenxichen/tensorflow_yolo2 (Darknet19 forward, grid/region decode, NMS, YOLO loss).
+ *
+ * The reference has NO native interface (it is pure Python over TensorFlow 1.x); the "FFI" a
+ * maintainer binds is therefore the set of TF-op call sites on the path.  Each entry point below
+ * names the reference call site (file:line under the reference repo's src/) it replaces.  The
+ * Python stub that binds these (ctypes) is shown in INTEGRATION.md and lives in
+ * tensorflow_yolo2_b200/_lib.py.
+ *
+ * Conventions
+ *   - extern "C"; plain pointers and sizes; no torch / C++ types in any signature.
+ *   - All data pointers are DEVICE pointers owned by the caller unless the name says `host`.
+ *   - Every function returns int: 0 = OK, <0 = bad argument (Y2_ERR_*), >0 = cudaError_t.
+ *     y2_last_error() returns a thread-local message for the last failure.
+ *   - No allocation and no host synchronisation inside (exception: y2_*_host helpers, which say
+ *     so).  Work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - Tensors are NHWC; "rows" M = N*H*W pixels.  bf16 = __nv_bfloat16 bits.
+ */
+#ifndef YOLO2_B200_H_
+#define YOLO2_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Y2_OK 0
+#define Y2_ERR_BAD_ARG (-1)
+#define Y2_ERR_UNSUPPORTED (-2)
+#define Y2_ERR_WORKSPACE (-3)
+#define Y2_ERR_DRIVER (-4)
+
+typedef void* y2_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int y2_version(void);
+const char* y2_last_error(void);
+/* Number of kernels this library has launched from the calling process since load (all threads).
+ * bench.py reports the delta over the timed region as "gpu_launches". */
+unsigned long long y2_launch_count(void);
+
+/* ---- a10: input preprocessing ------------------------------------------------------------
+ * pascal_detect_darknet.py:36-37, img_dataset/pascal_voc.py:62-64:  x = (u8 / 255.0) * 2.0 - 1.0
+ * on an already-resized BGR image.  out_dtype 0: float32 [N,H,W,3];  1: bf16 [N,H,W,8] with
+ * channels 3..7 zero (the layout the first tensor-core conv consumes). */
+int y2_preprocess_u8(const uint8_t* img, void* out, int N, int H, int W, int out_dtype, y2_stream_t stream);
+/* float32 [N,H,W,3] (already normalised, what the reference feeds sess.run) -> bf16 [N,H,W,8] */
+int y2_pad_cast_f32_to_bf16c8(const float* x, void* out, int N, int H, int W, y2_stream_t stream);
+
+/* ---- a1: convolution, exact float32 path ---------------------------------------------------
+ * yolo2_nets/darknet.py:20-21 (tf.nn.conv2d SAME stride 1) + :35 (+ bias).
+ * x [N,H,W,Cin] f32, w HWIO [k,k,Cin,Cout] f32 (the TF variable layout), y [N,H,W,Cout] f32.
+ * FFMA kernel, fp32 accumulate: the "1e-5" path of the spec and the GPU cross-check of the
+ * tensor-core kernel.  ksize in {1,3}. */
+int y2_conv_fwd_f32(const float* x, const float* w_hwio, const float* bias, float* y,
+                    int N, int H, int W, int Cin, int Cout, int ksize, y2_stream_t stream);
+
+/* ---- a1+a2+a3 fused: convolution on tcgen05 tensor cores ----------------------------------
+ * Same call sites as above plus darknet.py:42-45 (BN as per-channel scale/shift, leaky ReLU) and
+ * :24-25 (2x2 max-pool) in the epilogue.  Implicit GEMM: A = activations via TMA (im2col or
+ * tiled box mode) into swizzled smem, B = packed weights via TMA, D in TMEM, bf16 x bf16 -> fp32.
+ *
+ *   x        bf16 [N,H,W,Cin_p]    Cin_p = y2_conv_cin_padded(Cin)  (3 -> 8, else Cin)
+ *   w_packed bf16 [Cout_p][k*k][Cin_p]  from y2_pack_weights_bf16  (Cout_p = Cout rounded up to 16,
+ *            K padded with zero columns as y2_conv_packed_weight_elems says)
+ *   epilogue v = acc * scale[c] + shift[c];  if LEAKY: v = max(v, alpha*v);  if POOL2: 2x2 max
+ *   y        bf16 [N,Ho,Wo,Cout] (ldy = Cout)   or, with OUT_F32, float32 rows of stride ldy
+ */
+#define Y2_CONV_LEAKY 1
+#define Y2_CONV_POOL2 2
+#define Y2_CONV_OUT_F32 4
+typedef struct y2_conv_params {
+  const void* x;
+  const void* w_packed;
+  const float* scale; /* [Cout] or NULL (=1) */
+  const float* shift; /* [Cout] or NULL (=0) */
+  void* y;
+  int N, H, W, Cin, Cout, ksize;
+  int flags;
+  float alpha;
+  int ldy;      /* output row stride in elements; 0 -> Cout */
+  int reserved; /* must be 0 */
+} y2_conv_params;
+int y2_conv_cin_padded(int Cin);
+size_t y2_conv_packed_weight_elems(int ksize, int Cin, int Cout);
+int y2_pack_weights_bf16(const float* w_hwio, void* w_packed, int ksize, int Cin, int Cout, y2_stream_t stream);
+int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream);
+
+/* ---- a2: batch normalisation pieces (darknet.py:42-44, tf.layers.batch_normalization) -------
+ * y2_bn_stats: per-channel mean and BIASED variance over the M rows of x [M, ld] (float32),
+ * accumulated in float64 (activations reach 1e9+ with the reference's initialiser; see DESIGN).
+ * workspace: y2_bn_stats_workspace_bytes(M, C) bytes. */
+size_t y2_bn_stats_workspace_bytes(int M, int C);
+int y2_bn_stats(const float* x, int M, int C, int ld, float* mean, float* var,
+                void* workspace, size_t workspace_bytes, y2_stream_t stream);
+/* scale = gamma * rsqrt(var + eps); shift = beta + (bias_or_0 - mean) * scale.
+ * Pass conv_bias when the scale/shift is applied to a bias-free accumulator (fused epilogue),
+ * NULL when it is applied to h = conv + b. */
+int y2_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+               const float* conv_bias, float eps, float* scale, float* shift, int C, y2_stream_t stream);
+/* moving = moving * momentum + batch * (1 - momentum)   (UPDATE_OPS, pascal_train_darknet.py:49-50) */
+int y2_bn_update_moving(float* moving_mean, float* moving_var, const float* mean, const float* var,
+                        float momentum, int C, y2_stream_t stream);
+/* y = leaky((x - sub) * scale + shift) with optional 2x2 max-pool (darknet.py:45, :24-25); sub,
+ * scale, shift are per-channel [C] and may each be NULL (0, 1, 0).  Batch-stat BN passes sub = mean,
+ * scale = gamma*rsqrt(var+eps), shift = beta so that the subtraction happens before the scaling.
+ * x float32 [N,H,W,C] rows of stride ldx; out_dtype 0: float32, 1: bf16; output [N,Ho,Wo,C] dense. */
+int y2_affine_leaky_pool(const float* x, int ldx, const float* sub, const float* scale, const float* shift, float alpha,
+                         int leaky, int pool, void* out, int out_dtype, int N, int H, int W, int C,
+                         y2_stream_t stream);
+
+/* ---- a8: grid decode of show_yolo_detection (yolo2_nets/net_utils.py:393-407,418) -----------
+ * net [N,S,S,C+5B] f32.  boxes [N,S,S,B,4] = ((x+j)/S, (y+i)/S, w^2, h^2); conf [N,S,S,B];
+ * keep [N,S,S,B] u8 = conf > thresh; cls [N,S,S] int32 = argmax of the cell's class vector. */
+int y2_decode_ref_v1(const float* net, int N, int S, int B, int C, float thresh,
+                     float* boxes, float* conf, uint8_t* keep, int32_t* cls, y2_stream_t stream);
+
+/* ---- a': region decode (YOLOv2; absent from the reference) ---------------
+ * net [N,S,S,A*(5+C)] f32; anchors [A,2] (cell units).  boxes [N,S*S*A,4] (cx,cy,w,h normalised),
+ * scores [N,S*S*A,C] = sigmoid(to)*softmax(c) where > thresh else 0.  One warp per cell. */
+int y2_decode_region(const float* net, const float* anchors, int N, int S, int A, int C, float thresh,
+                     float* boxes, float* scores, y2_stream_t stream);
+
+/* ---- a': per-class greedy NMS (absent from the reference; IoU arithmetic = net_utils.py:222-260)
+ * boxes [N,nbox,4], scores [N,nbox,C].  Candidates of class k: score > score_thresh, visited by
+ * (score desc, box index asc); suppressed iff an earlier kept candidate has IoU > iou_thresh.
+ * keep_idx [N,C,max_keep] int32 (visiting order; only the first keep_count entries are written),
+ * keep_count [N,C] int32 (may exceed max_keep: then only max_keep were stored). */
+size_t y2_nms_workspace_bytes(int N, int nbox, int C);
+int y2_nms(const float* boxes, const float* scores, int N, int nbox, int C, float score_thresh,
+           float iou_thresh, int32_t* keep_idx, int32_t* keep_count, int max_keep,
+           void* workspace, size_t workspace_bytes, y2_stream_t stream);
+
+/* ---- a6+a7: YOLO loss forward + backward, one kernel (net_utils.py:263-372 + TF autodiff) ----
+ * net [N,S,S,C+5B], labels [N,S,S,5+C] float32.  terms[5] = class, coord, object, noobject, total
+ * (each already the batch mean, lambda applied).  ious/object_mask [N,S,S,B]; dnet like net
+ * (d total / d net).  Any of ious, object_mask, dnet may be NULL.  No pre-zeroing needed: block
+ * partials are folded in a fixed order by a trailing 1-block launch (deterministic). */
+size_t y2_loss_v1_workspace_bytes(int N, int S);
+int y2_loss_v1_fwd_bwd(const float* net, const float* labels, int N, int S, int B, int C,
+                       float image_size, float lambda_coord, float lambda_noobj, float* terms,
+                       float* ious, float* object_mask, float* dnet,
+                       void* workspace, size_t workspace_bytes, y2_stream_t stream);
+
+/* ---- a11: Adam (tf.train.AdamOptimizer defaults, pascal_train_darknet.py:51) -----------------
+ * p -= lr_t * m / (sqrt(v) + eps), lr_t = lr * sqrt(1-b2^t)/(1-b1^t) computed by the caller. */
+int y2_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1,
+                 float beta2, float eps, y2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO2_B200_H_ */

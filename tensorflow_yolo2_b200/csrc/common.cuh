@@ -1,0 +1,45 @@
+// common.cuh -- error plumbing and small device helpers shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/yolo2_b200.h"
+
+namespace y2 {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define Y2_ARG(cond)                                                              \
+  do {                                                                            \
+    if (!(cond)) {                                                                \
+      y2::set_error("%s: bad argument: %s", __func__, #cond);                     \
+      return Y2_ERR_BAD_ARG;                                                      \
+    }                                                                             \
+  } while (0)
+
+#define Y2_CUDA(expr)                                                             \
+  do {                                                                            \
+    cudaError_t e__ = (expr);                                                     \
+    if (e__ != cudaSuccess) {                                                     \
+      y2::set_error("%s: %s -> %s", __func__, #expr, cudaGetErrorString(e__));    \
+      return (int)e__;                                                            \
+    }                                                                             \
+  } while (0)
+
+// after a <<<>>> launch: count it and surface launch-configuration errors
+#define Y2_LAUNCHED()                                                             \
+  do {                                                                            \
+    y2::count_launch();                                                           \
+    Y2_CUDA(cudaPeekAtLastError());                                               \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+__device__ __forceinline__ float leaky(float v, float alpha) { return fmaxf(v, alpha * v); }
+
+}  // namespace y2

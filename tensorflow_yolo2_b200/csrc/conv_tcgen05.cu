@@ -1,0 +1,656 @@
+// conv_tcgen05.cu -- a1+a2+a3: convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+// Replaces, per layer, the reference's tf.nn.conv2d (yolo2_nets/darknet.py:20-21) + bias (:35) +
+// tf.layers.batch_normalization (:42-44, folded to per-channel scale/shift) + leaky (:45) +
+// tf.nn.max_pool 2x2 (:24-25) with ONE kernel:
+//
+//   D[M = pixels, N = Cout] = A[M, K = taps*Cin] * B[N, K]^T      bf16 x bf16 -> fp32 in TMEM
+//
+//   warp 0      TMA producer.  A tile (128 pixels x KCHUNK channels of one filter tap) straight from
+//               the NHWC activation tensor: either im2col-mode TMA (128 consecutive output pixels,
+//               halo/padding zero-filled by the TMA unit) or tiled-mode TMA (an NB x TH x TW pixel
+//               box, used by the pooled layers so that every 2x2 window sits inside one tile).
+//               B tile (BLOCK_N filters x KCHUNK) from the packed K-major weights.  Both land in
+//               128B/64B-swizzled (or, for the Cin=3->8 first layer, un-swizzled) K-major smem.
+//   warp 1      allocates TMEM, then one lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16) per
+//               16-channel slice and commits to the stage's "empty" barrier; the accumulator is
+//               double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 2..5  epilogue: tcgen05.ld 32 columns at a time, v = acc*scale[c]+shift[c], leaky,
+//               optional 2x2 max-pool across lanes (warp shuffles; the tiled box guarantees the
+//               window partners are lanes r^1 and r^TW), convert, 16-byte global stores.
+//   Persistent grid (<= #SMs CTAs), static round-robin over (m_tile, n_tile) with n fastest so
+//   CTAs running concurrently share the same A rows in L2.
+//
+// Every mbarrier wait has a clock-based timeout that traps instead of hanging the GPU.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstring>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace y2 {
+
+constexpr int TC_THREADS = 192;
+constexpr int TILE_M = 128;
+
+struct ConvArgs {
+  const float* scale;
+  const float* shift;
+  void* y;
+  long long M;            // N*H*W
+  int N, H, W, Cout;
+  int ldy;
+  int flags;
+  float alpha;
+  int ksize, pad;
+  int cin_p;              // padded input channels
+  int kchunk;             // channels per smem row (8 / 32 / 64)
+  int row_bytes;          // kchunk * 2
+  int kblocks;            // pipeline stages per tile: taps * cin_p/kchunk   (first layer: 1)
+  int cchunks;            // cin_p / kchunk
+  int ksteps;             // MMAs per stage (K=16 each)
+  int a_mode;             // 0 im2col, 1 tiled box
+  int tw_log2, th_log2, nb_log2;
+  int tiles_w, tiles_h, tiles_nb;
+  int m_tiles, n_tiles;
+  int stages;
+  uint32_t a_stage_bytes, b_stage_bytes;
+  uint32_t a_sbo, a_lbo, b_sbo, b_lbo, layout_type, kstep_bytes;   // UMMA smem-descriptor fields (bytes)
+  int first_layer;        // Cin_p == 8 special case (all taps in one stage, no swizzle)
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if ((++spins & 0xfff) == 0) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 6000000000ll) {   // ~3 s at 2 GHz: a protocol bug, not a slow tile
+        printf("y2 conv_tc: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h,
+                                                   int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base_offset | [61,64) layout
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// tile -> coordinates
+// ------------------------------------------------------------------------------------------
+struct TileCoord {
+  int n_tile;
+  int n0, h0, w0;        // first pixel of the tile (im2col: flattened start; tiled: box origin)
+  long long m0;          // im2col: first flattened pixel index
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
+  TileCoord t;
+  t.n_tile = tile % a.n_tiles;
+  int mt = tile / a.n_tiles;
+  if (a.a_mode == 0) {
+    t.m0 = (long long)mt * TILE_M;
+    t.w0 = (int)(t.m0 % a.W);
+    t.h0 = (int)((t.m0 / a.W) % a.H);
+    t.n0 = (int)(t.m0 / ((long long)a.W * a.H));
+  } else {
+    int tw_i = mt % a.tiles_w;
+    int th_i = (mt / a.tiles_w) % a.tiles_h;
+    int tn_i = mt / (a.tiles_w * a.tiles_h);
+    t.w0 = tw_i << a.tw_log2;
+    t.h0 = th_i << a.th_log2;
+    t.n0 = tn_i << a.nb_log2;
+    t.m0 = 0;
+  }
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int MAX_STAGES = 12;
+  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // dynamic smem base rounded up to 1024 B (swizzle-128B atoms)
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a.a_stage_bytes + a.b_stage_bytes;
+  const int total_tiles = a.m_tiles * a.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile);
+        const int nrow0 = t.n_tile * BLOCK_N;
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const uint32_t sA = smem_base + stage * stage_bytes;
+          const uint32_t sB = sA + a.a_stage_bytes;
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          if (a.first_layer) {
+            // all 9 taps (+ tap 0 again against zero weights) of 8 padded channels: 10 x [128 px][16 B]
+            for (int g = 0; g < 10; ++g) {
+              int tap = g < 9 ? g : 0;
+              int kh = tap / 3, kw = tap - kh * 3;
+              if (a.a_mode == 0)
+                tma_load_im2col_4d(sA + g * (TILE_M * 16), &tmA, bar, 0, t.w0 - a.pad, t.h0 - a.pad, t.n0, (uint16_t)kw,
+                                   (uint16_t)kh);
+              else
+                tma_load_4d(sA + g * (TILE_M * 16), &tmA, bar, 0, t.w0 + kw - a.pad, t.h0 + kh - a.pad, t.n0);
+            }
+            tma_load_3d(sB, &tmB, bar, 0, nrow0, 0);
+          } else {
+            const int tap = kb / a.cchunks;
+            const int c0 = (kb - tap * a.cchunks) * a.kchunk;
+            const int kh = tap / a.ksize, kw = tap - kh * a.ksize;
+            if (a.a_mode == 0)
+              tma_load_im2col_4d(sA, &tmA, bar, c0, t.w0 - a.pad, t.h0 - a.pad, t.n0, (uint16_t)kw, (uint16_t)kh);
+            else
+              tma_load_4d(sA, &tmA, bar, c0, t.w0 + kw - a.pad, t.h0 + kh - a.pad, t.n0);
+            tma_load_2d(sB, &tmB, bar, tap * a.cin_p + c0, nrow0);
+          }
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BLOCK_N);
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_base + stage * stage_bytes;
+          const uint32_t sB = sA + a.a_stage_bytes;
+          for (int ks = 0; ks < a.ksteps; ++ks) {
+            const uint64_t ad = make_smem_desc(sA + ks * a.kstep_bytes * (a.first_layer ? TILE_M : 1), a.a_lbo, a.a_sbo, a.layout_type);
+            const uint64_t bd = make_smem_desc(sB + ks * a.kstep_bytes * (a.first_layer ? BLOCK_N : 1), a.b_lbo, a.b_sbo, a.layout_type);
+            umma_bf16(tmem_d, ad, bd, idesc, (kb | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);           // frees the smem stage when these MMAs retire
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full_bar[buf]);           // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                    // accumulator row = pixel slot within the tile
+    const bool pool = (a.flags & Y2_CONV_POOL2) != 0;
+    const bool leaky_on = (a.flags & Y2_CONV_LEAKY) != 0;
+    const bool out_f32 = (a.flags & Y2_CONV_OUT_F32) != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const TileCoord t = decode_tile(a, tile);
+      // ---- where does my row go? ----
+      bool valid;
+      long long orow;     // output pixel row index
+      int tw = 0, th = 0;
+      if (a.a_mode == 0) {
+        long long m = t.m0 + r;
+        valid = m < a.M;
+        orow = m;
+      } else {
+        tw = r & ((1 << a.tw_log2) - 1);
+        th = (r >> a.tw_log2) & ((1 << a.th_log2) - 1);
+        int nb = r >> (a.tw_log2 + a.th_log2);
+        int n = t.n0 + nb, h = t.h0 + th, w = t.w0 + tw;
+        valid = n < a.N && h < a.H && w < a.W;
+        if (pool) {
+          valid = valid && ((tw | th) & 1) == 0;
+          orow = ((long long)n * (a.H >> 1) + (h >> 1)) * (a.W >> 1) + (w >> 1);
+        } else {
+          orow = ((long long)n * a.H + h) * a.W + w;
+        }
+      }
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N);
+      const int nbase = t.n_tile * BLOCK_N;
+#pragma unroll 1
+      for (int cc = 0; cc < BLOCK_N; cc += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr0 + (uint32_t)cc, v);
+        tmem_ld_wait();
+        if (cc + 32 >= BLOCK_N) {
+          // last chunk is in registers: hand the accumulator buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        const int c0 = nbase + cc;
+        if (c0 < a.ldy) {                           // (warp-uniform) chunk has columns that are stored
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            int c = c0 + i;
+            float sc = 1.0f, sh = 0.0f;
+            if (c < a.Cout) {
+              if (a.scale) sc = __ldg(a.scale + c);
+              if (a.shift) sh = __ldg(a.shift + c);
+            }
+            float x = fmaf(__uint_as_float(v[i]), sc, sh);
+            if (leaky_on) x = fmaxf(x, a.alpha * x);
+            f[i] = x;
+          }
+          if (pool) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
+              f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1 << a.tw_log2));
+            }
+          }
+          const int ncols = min(32, a.ldy - c0);    // columns of this chunk that exist in the output row
+          if (valid) {
+            if (out_f32) {
+              float* dst = reinterpret_cast<float*>(a.y) + (size_t)orow * a.ldy + c0;
+              if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+              } else {
+                for (int i = 0; i < ncols; ++i) dst[i] = f[i];
+              }
+            } else {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)orow * a.ldy + c0;
+              if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  uint4 pk;
+                  __nv_bfloat162 p0 = __floats2bfloat162_rn(f[i + 0], f[i + 1]);
+                  __nv_bfloat162 p1 = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
+                  __nv_bfloat162 p2 = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
+                  __nv_bfloat162 p3 = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&p0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&p2);
+                  pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                  *reinterpret_cast<uint4*>(dst + i) = pk;
+                }
+              } else {
+                for (int i = 0; i < ncols; ++i) dst[i] = __float2bfloat16_rn(f[i]);
+              }
+            }
+          }
+        }
+        __syncwarp();                               // reconverge before the next .sync.aligned TMEM load
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps (driver entry points fetched at run time -> no libcuda link dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encodeTiled = nullptr;
+static PFN_encodeIm2col g_encodeIm2col = nullptr;
+static int g_num_sms = 0;
+static int g_driver_version = 0;
+static std::mutex g_mu;
+
+static int load_driver_entry_points() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_encodeTiled && g_encodeIm2col) return Y2_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+    return Y2_ERR_DRIVER;
+  }
+  g_encodeTiled = (PFN_encodeTiled)fn;
+  fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn) {
+    set_error("cuTensorMapEncodeIm2col not available: %s", cudaGetErrorString(e));
+    return Y2_ERR_DRIVER;
+  }
+  g_encodeIm2col = (PFN_encodeIm2col)fn;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDriverGetVersion(&g_driver_version);
+  return Y2_OK;
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                          : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// choose the pixel box (NB x TH x TW = 128, powers of two) with the least padding waste
+static void choose_box(int N, int H, int W, bool pool, int* tw, int* th, int* nb) {
+  double best = 1e30;
+  int btw = 16, bth = 8, bnb = 1;
+  for (int TW = (pool ? 2 : 1); TW <= (pool ? 16 : 128); TW <<= 1)
+    for (int TH = (pool ? 2 : 1); TH * TW <= 128; TH <<= 1) {
+      int NB = 128 / (TW * TH);
+      double cover = (double)((W + TW - 1) / TW * TW) * ((H + TH - 1) / TH * TH) * ((N + NB - 1) / NB * NB);
+      double waste = cover / ((double)W * H * N);
+      // prefer wide boxes (longer contiguous runs for the TMA) when the waste ties
+      double score = waste - 1e-6 * TW;
+      if (score < best) { best = score; btw = TW; bth = TH; bnb = NB; }
+    }
+  *tw = btw; *th = bth; *nb = bnb;
+}
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, size_t smem, cudaStream_t st) {
+  Y2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int total = a.m_tiles * a.n_tiles;
+  int grid = total < g_num_sms ? total : g_num_sms;
+  conv_tc_kernel<BLOCK_N><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+}  // namespace y2
+
+using namespace y2;
+
+extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
+  Y2_ARG(p != nullptr);
+  Y2_ARG(p->x && p->w_packed && p->y && p->reserved == 0);
+  Y2_ARG(p->N > 0 && p->H > 0 && p->W > 0 && p->Cin > 0 && p->Cout > 0 && (p->ksize == 1 || p->ksize == 3));
+  const bool pool = (p->flags & Y2_CONV_POOL2) != 0;
+  const bool out_f32 = (p->flags & Y2_CONV_OUT_F32) != 0;
+  if (pool) Y2_ARG(p->H % 2 == 0 && p->W % 2 == 0);
+  int rc = load_driver_entry_points();
+  if (rc != Y2_OK) return rc;
+
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.scale = p->scale;
+  a.shift = p->shift;
+  a.y = p->y;
+  a.N = p->N; a.H = p->H; a.W = p->W; a.Cout = p->Cout;
+  a.M = (long long)p->N * p->H * p->W;
+  a.ldy = p->ldy > 0 ? p->ldy : p->Cout;
+  Y2_ARG(a.ldy >= p->Cout);
+  a.flags = p->flags;
+  a.alpha = p->alpha;
+  a.ksize = p->ksize;
+  a.pad = p->ksize / 2;
+  a.cin_p = y2_conv_cin_padded(p->Cin);
+  Y2_ARG(a.cin_p == p->Cin || p->Cin < 8);
+  const int cout_p = (p->Cout + 15) / 16 * 16;
+  const int taps = p->ksize * p->ksize;
+  a.first_layer = a.cin_p == 8;
+  if (a.first_layer) {
+    Y2_ARG(p->ksize == 3);
+    a.kchunk = 8; a.row_bytes = 16; a.kblocks = 1; a.cchunks = 1; a.ksteps = 5;
+    a.layout_type = 0;                    // no swizzle: core matrices of 8 rows x 16 B
+    a.kstep_bytes = 2 * 16;               // x rows -> two 16-byte K groups per MMA (scaled by rows in-kernel)
+  } else if (a.cin_p % 64 == 0) {
+    a.kchunk = 64; a.row_bytes = 128; a.layout_type = 2; a.ksteps = 4; a.kstep_bytes = 32;
+    a.cchunks = a.cin_p / 64; a.kblocks = taps * a.cchunks;
+  } else if (a.cin_p % 32 == 0) {
+    a.kchunk = 32; a.row_bytes = 64; a.layout_type = 4; a.ksteps = 2; a.kstep_bytes = 32;
+    a.cchunks = a.cin_p / 32; a.kblocks = taps * a.cchunks;
+  } else {
+    set_error("y2_conv_fwd_bf16: Cin=%d unsupported (need 3, or a multiple of 32)", p->Cin);
+    return Y2_ERR_UNSUPPORTED;
+  }
+  int block_n = cout_p >= 128 ? 128 : (cout_p > 32 ? 64 : 32);
+  a.n_tiles = (cout_p + block_n - 1) / block_n;
+  a.a_mode = pool ? 1 : 0;
+  if (getenv("Y2_CONV_FORCE_TILED")) a.a_mode = 1;
+  int TW = 1, TH = 1, NB = 128;
+  if (a.a_mode == 1) {
+    choose_box(p->N, p->H, p->W, pool, &TW, &TH, &NB);
+    a.tw_log2 = ilog2(TW); a.th_log2 = ilog2(TH); a.nb_log2 = ilog2(NB);
+    a.tiles_w = (p->W + TW - 1) / TW; a.tiles_h = (p->H + TH - 1) / TH; a.tiles_nb = (p->N + NB - 1) / NB;
+    a.m_tiles = a.tiles_w * a.tiles_h * a.tiles_nb;
+  } else {
+    a.m_tiles = (int)((a.M + TILE_M - 1) / TILE_M);
+  }
+  if (a.first_layer) {
+    a.a_stage_bytes = 10 * TILE_M * 16;
+    a.b_stage_bytes = 10 * block_n * 16;
+    a.a_sbo = 128; a.a_lbo = TILE_M * 16;
+    a.b_sbo = 128; a.b_lbo = block_n * 16;
+  } else {
+    a.a_stage_bytes = TILE_M * a.row_bytes;
+    a.b_stage_bytes = block_n * a.row_bytes;
+    a.a_sbo = 8 * a.row_bytes; a.b_sbo = 8 * a.row_bytes;
+    a.a_lbo = 16; a.b_lbo = 16;           // ignored for swizzled K-major layouts (CUTLASS writes 1)
+  }
+  // stages: B-stage must stay 1024-byte aligned for the 128B swizzle atoms
+  uint32_t stage_bytes = a.a_stage_bytes + a.b_stage_bytes;
+  Y2_ARG(a.first_layer || (a.a_stage_bytes % 1024 == 0 && a.b_stage_bytes % 1024 == 0));
+  int stages = (int)((196 * 1024) / stage_bytes);
+  if (stages > 12) stages = 12;
+  if (stages > a.kblocks * 4) stages = a.kblocks * 4 > 2 ? a.kblocks * 4 : 2;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes + 1024;
+
+  // ---- tensor maps ----
+  CUtensorMap tmA, tmB;
+  const CUtensorMapSwizzle sw = swizzle_for(a.row_bytes);
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a.cin_p, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t strides[3] = {(cuuint64_t)a.cin_p * 2, (cuuint64_t)p->W * a.cin_p * 2, (cuuint64_t)p->H * p->W * a.cin_p * 2};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r;
+    if (a.a_mode == 0) {
+      int lower[2] = {-a.pad, -a.pad};
+      int upper[2] = {a.pad - (p->ksize - 1), a.pad - (p->ksize - 1)};
+      r = g_encodeIm2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), dims, strides, lower, upper,
+                         (cuuint32_t)a.kchunk, (cuuint32_t)TILE_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      // same small-tensor fix-up CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp) for drivers <= 13.1
+      if (r == CUDA_SUCCESS && g_driver_version <= 13010 && (size_t)a.M * a.cin_p * 2 < 131072)
+        reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
+    } else {
+      cuuint32_t box[4] = {(cuuint32_t)a.kchunk, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB};
+      r = g_encodeTiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+      set_error("y2_conv_fwd_bf16: tensor map A encode failed (CUresult %d, mode %d)", (int)r, a.a_mode);
+      return Y2_ERR_DRIVER;
+    }
+  }
+  {
+    CUresult r;
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (a.first_layer) {
+      // packed as [kgroup=10][Cout_p][8]
+      cuuint64_t dims[3] = {8, (cuuint64_t)cout_p, 10};
+      cuuint64_t strides[2] = {16, (cuuint64_t)cout_p * 16};
+      cuuint32_t box[3] = {8, (cuuint32_t)block_n, 10};
+      r = g_encodeTiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->w_packed), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      const int Kp = taps * a.cin_p;
+      cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)cout_p};
+      cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+      cuuint32_t box[2] = {(cuuint32_t)a.kchunk, (cuuint32_t)block_n};
+      r = g_encodeTiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->w_packed), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+      set_error("y2_conv_fwd_bf16: tensor map B encode failed (CUresult %d)", (int)r);
+      return Y2_ERR_DRIVER;
+    }
+  }
+  (void)out_f32;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (block_n) {
+    case 32: return launch_conv<32>(tmA, tmB, a, smem, st);
+    case 64: return launch_conv<64>(tmA, tmB, a, smem, st);
+    default: return launch_conv<128>(tmA, tmB, a, smem, st);
+  }
+}

@@ -1,0 +1,375 @@
+// elementwise.cu -- HBM-bound helpers around the convolutions: input preprocessing (a10),
+// weight packing, batch-norm statistics / folding / apply (+leaky, +2x2 pool) (a2, a3), Adam (a11).
+// Reference call sites are cited per kernel; the ABI is documented in include/yolo2_b200.h.
+#include "common.cuh"
+
+namespace y2 {
+
+// ---------------------------------------------------------------------------------------------
+// a10  pascal_detect_darknet.py:36-37 / pascal_voc.py:62-64:  (u8 / 255.0) * 2.0 - 1.0
+// Division and multiply kept as separate IEEE ops so the f32 output is bit-identical to NumPy's.
+// ---------------------------------------------------------------------------------------------
+__global__ void preprocess_u8_f32_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = (float)img[i];
+    out[i] = __fsub_rn(__fmul_rn(__fdiv_rn(v, 255.0f), 2.0f), 1.0f);
+  }
+}
+
+// one thread per pixel: 3 bytes in, 8 bf16 (16 B) out; channels 3..7 are zero padding so the
+// first conv can run on the tensor cores with 16-byte TMA rows.
+__global__ void preprocess_u8_bf16c8_kernel(const uint8_t* __restrict__ img, uint4* __restrict__ out, size_t npix) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < npix; i += stride) {
+    float v0 = (float)img[3 * i + 0], v1 = (float)img[3 * i + 1], v2 = (float)img[3 * i + 2];
+    v0 = __fsub_rn(__fmul_rn(__fdiv_rn(v0, 255.0f), 2.0f), 1.0f);
+    v1 = __fsub_rn(__fmul_rn(__fdiv_rn(v1, 255.0f), 2.0f), 1.0f);
+    v2 = __fsub_rn(__fmul_rn(__fdiv_rn(v2, 255.0f), 2.0f), 1.0f);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v2, 0.0f);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    o.z = 0u;
+    o.w = 0u;
+    out[i] = o;
+  }
+}
+
+__global__ void pad_cast_f32_bf16c8_kernel(const float* __restrict__ x, uint4* __restrict__ out, size_t npix) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < npix; i += stride) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(x[3 * i + 0], x[3 * i + 1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(x[3 * i + 2], 0.0f);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    o.z = 0u;
+    o.w = 0u;
+    out[i] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: TF HWIO [k,k,Cin,Cout] f32  ->  [Cout_p][Kp] bf16, K index = tap*Cin_p + c
+// (K-major rows, the B operand of the implicit GEMM).  Padding rows/columns are zero.
+// First layer (Cin 3 -> 8): [10 k-groups][Cout_p][8] instead, k-group 9 all zero.
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps, int Cin,
+                                    int Cout, int Cin_p, int Cout_p, int Kp) {
+  size_t total = (size_t)Cout_p * Kp;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int n = (int)(i / Kp);
+    int kk = (int)(i % Kp);
+    int tap = kk / Cin_p, c = kk % Cin_p;
+    float v = 0.0f;
+    if (n < Cout && tap < taps && c < Cin) v = w[((size_t)tap * Cin + c) * Cout + n];
+    // first layer (Cin_p == 8): smem-ready order [k-group = tap][Cout_p][8] (un-swizzled core matrices)
+    size_t o = (Cin_p == 8) ? ((size_t)tap * Cout_p + n) * 8 + c : i;
+    out[o] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2  batch statistics (tf.layers.batch_normalization training=True, darknet.py:42-44):
+// per-channel mean and biased variance over M rows.  Shifted sums in float64: with the
+// reference's initialiser activations reach 1e9..1e12 and |mean| >> std, where a float32
+// E[x^2]-E[x]^2 cancels catastrophically.
+// stage 1: grid (ceil(C/32), splits), block (32, 8): partial sum(d), sum(d^2), d = x - x[0][c]
+// stage 2: one thread per channel folds the splits in a fixed order (deterministic).
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_stats_partial_kernel(const float* __restrict__ x, int M, int C, int ld, int rows_per_split,
+                                        double* __restrict__ part) {
+  __shared__ double s1[8][33], s2[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int split = blockIdx.y;
+  int r0 = split * rows_per_split;
+  int r1 = min(M, r0 + rows_per_split);
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C) {
+    float k = x[c];
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      double d = (double)(x[(size_t)r * ld + c] - k);
+      a1 += d;
+      a2 += d * d;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a1;
+  s2[threadIdx.y][threadIdx.x] = a2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int y = 1; y < 8; ++y) {
+      a1 += s1[y][threadIdx.x];
+      a2 += s2[y][threadIdx.x];
+    }
+    part[((size_t)split * C + c) * 2 + 0] = a1;
+    part[((size_t)split * C + c) * 2 + 1] = a2;
+  }
+}
+
+__global__ void bn_stats_final_kernel(const float* __restrict__ x, const double* __restrict__ part, int splits, int M,
+                                      int C, float* __restrict__ mean, float* __restrict__ var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a1 = 0.0, a2 = 0.0;
+  for (int s = 0; s < splits; ++s) {
+    a1 += part[((size_t)s * C + c) * 2 + 0];
+    a2 += part[((size_t)s * C + c) * 2 + 1];
+  }
+  double md = a1 / (double)M;
+  double v = a2 / (double)M - md * md;
+  if (v < 0.0) v = 0.0;
+  mean[c] = (float)((double)x[c] + md);
+  var[c] = (float)v;
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var,
+                               const float* __restrict__ bias, float eps, float* __restrict__ scale,
+                               float* __restrict__ shift, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = gamma[c] * rsqrtf(var[c] + eps);
+  float b = bias ? bias[c] : 0.0f;
+  scale[c] = s;
+  shift[c] = beta[c] + (b - mean[c]) * s;
+}
+
+__global__ void bn_update_moving_kernel(float* __restrict__ mm, float* __restrict__ mv, const float* __restrict__ mean,
+                                        const float* __restrict__ var, float momentum, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mm[c] = mm[c] * momentum + mean[c] * (1.0f - momentum);
+  mv[c] = mv[c] * momentum + var[c] * (1.0f - momentum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2/a3  y = leaky((x - sub)*scale + shift), optional 2x2/2 max-pool (order conv->BN->leaky->pool,
+// darknet.py:150-151), f32 or bf16 output.  One thread per output element group of VEC channels.
+// ---------------------------------------------------------------------------------------------
+template <int VEC, bool BF16OUT>
+__global__ void affine_leaky_pool_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ sub,
+                                         const float* __restrict__ scale, const float* __restrict__ shift, float alpha, int leaky_on, int pool,
+                                         void* __restrict__ out, int N, int H, int W, int C) {
+  int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  int CV = C / VEC;
+  size_t total = (size_t)N * Ho * Wo * CV;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int cv = (int)(i % CV);
+    size_t pix = i / CV;
+    int wo = (int)(pix % Wo);
+    int ho = (int)((pix / Wo) % Ho);
+    int n = (int)(pix / ((size_t)Wo * Ho));
+    int c0 = cv * VEC;
+    float r[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r[v] = -INFINITY;
+    int np = pool ? 2 : 1;
+    for (int dy = 0; dy < np; ++dy)
+      for (int dx = 0; dx < np; ++dx) {
+        int h = pool ? ho * 2 + dy : ho, w = pool ? wo * 2 + dx : wo;
+        const float* px = x + ((size_t)(n * H + h) * W + w) * ldx + c0;
+        float t[VEC];
+        if (VEC == 4) {
+          float4 q = *reinterpret_cast<const float4*>(px);
+          t[0] = q.x; t[1 % VEC] = q.y; t[2 % VEC] = q.z; t[3 % VEC] = q.w;
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) t[v] = px[v];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          float sc = scale ? scale[c0 + v] : 1.0f, sh = shift ? shift[c0 + v] : 0.0f;
+          float sb = sub ? sub[c0 + v] : 0.0f;
+          float y = (t[v] - sb) * sc + sh;   // (x - mean) first: exact cancellation when |mean| >> std
+          if (leaky_on) y = leaky(y, alpha);
+          r[v] = fmaxf(r[v], y);
+        }
+      }
+    size_t o = pix * C + c0;
+    if (BF16OUT) {
+      __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out) + o;
+      if (VEC == 4) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1 % VEC]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(r[2 % VEC], r[3 % VEC]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(ob) = pk;
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) ob[v] = __float2bfloat16_rn(r[v]);
+      }
+    } else {
+      float* of = reinterpret_cast<float*>(out) + o;
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(of) = make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) of[v] = r[v];
+      }
+    }
+  }
+}
+
+// a11  tf.train.AdamOptimizer (pascal_train_darknet.py:51): TF1 update form, lr_t from the host.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr_t, float b1, float b2, float eps) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float gi = g[i];
+    float mi = b1 * m[i] + (1.0f - b1) * gi;
+    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+static int grid_for(size_t n, int block) {
+  size_t g = (n + block - 1) / block;
+  size_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace y2
+
+using namespace y2;
+
+extern "C" {
+
+int y2_preprocess_u8(const uint8_t* img, void* out, int N, int H, int W, int out_dtype, y2_stream_t stream) {
+  Y2_ARG(img && out && N > 0 && H > 0 && W > 0 && (out_dtype == 0 || out_dtype == 1));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t npix = (size_t)N * H * W;
+  if (out_dtype == 0) {
+    preprocess_u8_f32_kernel<<<grid_for(npix * 3, 256), 256, 0, st>>>(img, (float*)out, npix * 3);
+  } else {
+    preprocess_u8_bf16c8_kernel<<<grid_for(npix, 256), 256, 0, st>>>(img, (uint4*)out, npix);
+  }
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_pad_cast_f32_to_bf16c8(const float* x, void* out, int N, int H, int W, y2_stream_t stream) {
+  Y2_ARG(x && out && N > 0 && H > 0 && W > 0);
+  size_t npix = (size_t)N * H * W;
+  pad_cast_f32_bf16c8_kernel<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint4*)out, npix);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_conv_cin_padded(int Cin) { return Cin < 8 ? 8 : Cin; }
+
+static int conv_kp(int ksize, int Cin) {
+  int cin_p = y2_conv_cin_padded(Cin);
+  int K = ksize * ksize * cin_p;
+  if (cin_p == 8) return (K + 15) / 16 * 16;   // first layer: 9 taps x 8 -> 72 -> 80 (whole MMA K steps)
+  return K;
+}
+
+size_t y2_conv_packed_weight_elems(int ksize, int Cin, int Cout) {
+  int cout_p = (Cout + 15) / 16 * 16;
+  return (size_t)cout_p * conv_kp(ksize, Cin);
+}
+
+int y2_pack_weights_bf16(const float* w_hwio, void* w_packed, int ksize, int Cin, int Cout, y2_stream_t stream) {
+  Y2_ARG(w_hwio && w_packed && (ksize == 1 || ksize == 3) && Cin > 0 && Cout > 0);
+  int cin_p = y2_conv_cin_padded(Cin);
+  Y2_ARG(cin_p == 8 || cin_p % 32 == 0);
+  int cout_p = (Cout + 15) / 16 * 16;
+  int Kp = conv_kp(ksize, Cin);
+  size_t total = (size_t)cout_p * Kp;
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      w_hwio, (__nv_bfloat16*)w_packed, ksize * ksize, Cin, Cout, cin_p, cout_p, Kp);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+static int bn_splits(int M) {
+  int s = (M + 255) / 256;
+  return s > 512 ? 512 : (s < 1 ? 1 : s);
+}
+
+size_t y2_bn_stats_workspace_bytes(int M, int C) { return (size_t)bn_splits(M) * C * 2 * sizeof(double); }
+
+int y2_bn_stats(const float* x, int M, int C, int ld, float* mean, float* var, void* workspace, size_t workspace_bytes,
+                y2_stream_t stream) {
+  Y2_ARG(x && mean && var && M > 0 && C > 0 && ld >= C);
+  if (!workspace || workspace_bytes < y2_bn_stats_workspace_bytes(M, C)) {
+    set_error("y2_bn_stats: workspace too small (%zu < %zu)", workspace_bytes, y2_bn_stats_workspace_bytes(M, C));
+    return Y2_ERR_WORKSPACE;
+  }
+  Y2_ARG(((uintptr_t)workspace & 7) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  int splits = bn_splits(M);
+  int rows = (M + splits - 1) / splits;
+  splits = (M + rows - 1) / rows;
+  dim3 grid((C + 31) / 32, splits), block(32, 8);
+  bn_stats_partial_kernel<<<grid, block, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
+  Y2_LAUNCHED();
+  bn_stats_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(x, (const double*)workspace, splits, M, C, mean, var);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias,
+               float eps, float* scale, float* shift, int C, y2_stream_t stream) {
+  Y2_ARG(gamma && beta && mean && var && scale && shift && C > 0);
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, conv_bias, eps, scale,
+                                                                     shift, C);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_bn_update_moving(float* moving_mean, float* moving_var, const float* mean, const float* var, float momentum,
+                        int C, y2_stream_t stream) {
+  Y2_ARG(moving_mean && moving_var && mean && var && C > 0);
+  bn_update_moving_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(moving_mean, moving_var, mean, var,
+                                                                              momentum, C);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_affine_leaky_pool(const float* x, int ldx, const float* sub, const float* scale, const float* shift, float alpha, int leaky_on,
+                         int pool, void* out, int out_dtype, int N, int H, int W, int C, y2_stream_t stream) {
+  Y2_ARG(x && out && N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && (out_dtype == 0 || out_dtype == 1));
+  if (pool) Y2_ARG(H % 2 == 0 && W % 2 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  bool vec4 = (C % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  size_t total = (size_t)N * Ho * Wo * (vec4 ? C / 4 : C);
+  int g = grid_for(total, 256);
+  if (vec4) {
+    if (out_dtype == 1)
+      affine_leaky_pool_kernel<4, true><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C);
+    else
+      affine_leaky_pool_kernel<4, false><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C);
+  } else {
+    if (out_dtype == 1)
+      affine_leaky_pool_kernel<1, true><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C);
+    else
+      affine_leaky_pool_kernel<1, false><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C);
+  }
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
+                 float eps, y2_stream_t stream) {
+  Y2_ARG(p && g && m && v && n > 0);
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_t, beta1, beta2, eps);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+}  // extern "C"

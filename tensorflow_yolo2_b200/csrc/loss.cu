@@ -1,0 +1,208 @@
+// loss.cu -- a6 + a7: the YOLO (v1-style) sum-squared loss of yolo2_nets/net_utils.py:263-372 and
+// its gradient (what TF autodiff produces for that graph), fused in ONE kernel pass over the grid:
+// one thread per cell, cells staged through shared memory with coalesced loads/stores, the
+// gradient written in place of the staged predictions.  Loss terms: block partials + a fixed-order
+// fold (deterministic).
+//   net    [N,S,S,C+5B] : [0:C] class (per cell) | [C:C+B] confidence | B x (x, y, sqrt w, sqrt h)
+//   labels [N,S,S,5+C]  : [0] responsible | [1:5] GT (cx,cy,w,h) pixels of the resized image | one-hot
+// Tie rules of the backward pass follow TF (maximum: first arg wins on >=, minimum: on <=).
+#include "common.cuh"
+
+namespace y2 {
+
+constexpr int LOSS_THREADS = 128;
+constexpr int LOSS_MAXB = 8;
+
+struct IouOut { float iou, gx, gy, gw, gh; };   // iou and d iou / d (cx, cy, w, h) of box 1
+
+// net_utils.py:231-260 forward, then the reverse sweep.
+__device__ __forceinline__ IouOut iou_fwd_bwd(float cx, float cy, float w, float h, float gcx, float gcy, float gw_,
+                                              float gh_) {
+  float x1a = cx - w / 2.0f, y1a = cy - h / 2.0f, x2a = cx + w / 2.0f, y2a = cy + h / 2.0f;
+  float x1b = gcx - gw_ / 2.0f, y1b = gcy - gh_ / 2.0f, x2b = gcx + gw_ / 2.0f, y2b = gcy + gh_ / 2.0f;
+  float lux = fmaxf(x1a, x1b), luy = fmaxf(y1a, y1b);
+  float rdx = fminf(x2a, x2b), rdy = fminf(y2a, y2b);
+  float dw = rdx - lux, dh = rdy - luy;
+  float iw = fmaxf(0.0f, dw), ih = fmaxf(0.0f, dh);
+  float inter = iw * ih;
+  float sq1 = (x2a - x1a) * (y2a - y1a);
+  float sq2 = (x2b - x1b) * (y2b - y1b);
+  float uraw = sq1 + sq2 - inter;
+  float uni = fmaxf(uraw, 1e-10f);
+  float q = inter / uni;
+  IouOut o;
+  o.iou = fminf(fmaxf(q, 0.0f), 1.0f);
+  // reverse, seeded with d iou = 1
+  float g_q = (q >= 0.0f && q <= 1.0f) ? 1.0f : 0.0f;
+  float g_inter = g_q / uni;
+  float g_uni = -g_q * inter / (uni * uni);
+  float g_uraw = (uraw >= 1e-10f) ? g_uni : 0.0f;
+  float g_sq1 = g_uraw;
+  g_inter -= g_uraw;
+  float g_dw = (dw > 0.0f) ? g_inter * ih : 0.0f;
+  float g_dh = (dh > 0.0f) ? g_inter * iw : 0.0f;
+  float g_x1a = (x1a >= x1b) ? -g_dw : 0.0f;
+  float g_y1a = (y1a >= y1b) ? -g_dh : 0.0f;
+  float g_x2a = (x2a <= x2b) ? g_dw : 0.0f;
+  float g_y2a = (y2a <= y2b) ? g_dh : 0.0f;
+  float hh = y2a - y1a, ww = x2a - x1a;
+  g_x2a += g_sq1 * hh;
+  g_x1a -= g_sq1 * hh;
+  g_y2a += g_sq1 * ww;
+  g_y1a -= g_sq1 * ww;
+  o.gx = g_x1a + g_x2a;
+  o.gy = g_y1a + g_y2a;
+  o.gw = (g_x2a - g_x1a) * 0.5f;
+  o.gh = (g_y2a - g_y1a) * 0.5f;
+  return o;
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS) loss_v1_kernel(
+    const float* __restrict__ net, const float* __restrict__ labels, int ncell_total, int N, int S, int B, int C,
+    float image_size, float lambda_coord, float lambda_noobj, float* __restrict__ ious_out,
+    float* __restrict__ mask_out, float* __restrict__ dnet, double* __restrict__ partials) {
+  extern __shared__ __align__(16) float smem[];
+  const int ch = C + 5 * B, lab = 5 + C;
+  float* s_net = smem;
+  float* s_lab = smem + LOSS_THREADS * ch;
+  __shared__ float s_red[4][LOSS_THREADS / 32];
+  const int tid = threadIdx.x;
+  const int cell0 = blockIdx.x * LOSS_THREADS;
+  const int ncell = min(LOSS_THREADS, ncell_total - cell0);
+  for (int e = tid; e < ncell * ch; e += LOSS_THREADS) s_net[e] = net[(size_t)cell0 * ch + e];
+  for (int e = tid; e < ncell * lab; e += LOSS_THREADS) s_lab[e] = labels[(size_t)cell0 * lab + e];
+  __syncthreads();
+
+  float l_class = 0.0f, l_coord = 0.0f, l_obj = 0.0f, l_noobj = 0.0f;
+  if (tid < ncell) {
+    const int cell = cell0 + tid;
+    const int j = cell % S, i = (cell / S) % S;
+    float* p = s_net + tid * ch;
+    const float* lb = s_lab + tid * lab;
+    const float invN = 1.0f / (float)N;
+    const float resp = lb[0];
+    // class term (:290-297)
+    for (int k = 0; k < C; ++k) {
+      float d = resp * (p[k] - lb[5 + k]);
+      l_class += d * d;
+      p[k] = 2.0f * resp * d * invN;
+    }
+    // boxes (:302-334)
+    const float fS = (float)S;
+    const float gcx = lb[1] / image_size, gcy = lb[2] / image_size, gw = lb[3] / image_size, gh = lb[4] / image_size;
+    float conf[LOSS_MAXB], bx[LOSS_MAXB], by[LOSS_MAXB], bw[LOSS_MAXB], bh[LOSS_MAXB];
+    IouOut io[LOSS_MAXB];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int b = 0; b < LOSS_MAXB; ++b) {
+      if (b < B) {
+        conf[b] = p[C + b];
+        bx[b] = p[C + B + 4 * b + 0];
+        by[b] = p[C + B + 4 * b + 1];
+        bw[b] = p[C + B + 4 * b + 2];
+        bh[b] = p[C + B + 4 * b + 3];
+        float px = (bx[b] + (float)j) / fS, py = (by[b] + (float)i) / fS;
+        io[b] = iou_fwd_bwd(px, py, bw[b] * bw[b], bh[b] * bh[b], gcx, gcy, gw, gh);
+        mx = fmaxf(mx, io[b].iou);
+      }
+    }
+    const float grx = gcx * fS - (float)j, gry = gcy * fS - (float)i;
+    const float grw = sqrtf(gw), grh = sqrtf(gh);
+#pragma unroll
+    for (int b = 0; b < LOSS_MAXB; ++b) {
+      if (b < B) {
+        float m = (io[b].iou >= mx ? 1.0f : 0.0f) * resp;     // :323-324 (ties mark every predictor)
+        float nm = 1.0f - m;                                   // :325-326
+        float dx = bx[b] - grx, dy = by[b] - gry, dw = bw[b] - grw, dh = bh[b] - grh;
+        float m2 = m * m;
+        l_coord += m2 * (dx * dx + dy * dy + dw * dw + dh * dh);
+        float od = m * (conf[b] - io[b].iou);
+        l_obj += od * od;
+        float nd = nm * conf[b];
+        l_noobj += nd * nd;
+        // gradients
+        float g_conf = (2.0f * m2 * (conf[b] - io[b].iou) + 2.0f * lambda_noobj * nm * nm * conf[b]) * invN;
+        float g_iou = -2.0f * m2 * (conf[b] - io[b].iou) * invN;
+        float cs = 2.0f * lambda_coord * invN * m2;
+        p[C + b] = g_conf;
+        p[C + B + 4 * b + 0] = cs * dx + g_iou * io[b].gx / fS;
+        p[C + B + 4 * b + 1] = cs * dy + g_iou * io[b].gy / fS;
+        p[C + B + 4 * b + 2] = cs * dw + g_iou * io[b].gw * 2.0f * bw[b];
+        p[C + B + 4 * b + 3] = cs * dh + g_iou * io[b].gh * 2.0f * bh[b];
+        if (ious_out) ious_out[(size_t)cell * B + b] = io[b].iou;
+        if (mask_out) mask_out[(size_t)cell * B + b] = m;
+      }
+    }
+  }
+  // block reduction of the four terms
+  float v[4] = {l_class, l_coord, l_obj, l_noobj};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+    if ((tid & 31) == 0) s_red[q][tid >> 5] = v[q];
+  }
+  __syncthreads();
+  if (tid < 4) {
+    double acc = 0.0;
+    for (int wv = 0; wv < LOSS_THREADS / 32; ++wv) acc += (double)s_red[tid][wv];
+    partials[(size_t)blockIdx.x * 4 + tid] = acc;
+  }
+  if (dnet)
+    for (int e = tid; e < ncell * ch; e += LOSS_THREADS) dnet[(size_t)cell0 * ch + e] = s_net[e];
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ partials, int nblocks, int N, float lambda_coord,
+                                     float lambda_noobj, float* __restrict__ terms) {
+  int q = threadIdx.x;
+  __shared__ double s[4];
+  if (q < 4) {
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; ++b) acc += partials[(size_t)b * 4 + q];
+    acc /= (double)N;
+    if (q == 1) acc *= (double)lambda_coord;
+    if (q == 3) acc *= (double)lambda_noobj;
+    s[q] = acc;
+    terms[q] = (float)acc;
+  }
+  __syncthreads();
+  if (q == 0) terms[4] = (float)(s[0] + s[2] + s[3] + s[1]);   // :372 class + object + noobject + coord
+}
+
+}  // namespace y2
+
+using namespace y2;
+
+extern "C" {
+
+size_t y2_loss_v1_workspace_bytes(int N, int S) {
+  int ncell = N * S * S;
+  return (size_t)ceil_div(ncell, LOSS_THREADS) * 4 * sizeof(double);
+}
+
+int y2_loss_v1_fwd_bwd(const float* net, const float* labels, int N, int S, int B, int C, float image_size,
+                       float lambda_coord, float lambda_noobj, float* terms, float* ious, float* object_mask,
+                       float* dnet, void* workspace, size_t workspace_bytes, y2_stream_t stream) {
+  Y2_ARG(net && labels && terms && N > 0 && S > 0 && B > 0 && B <= LOSS_MAXB && C > 0 && image_size > 0.0f);
+  if (!workspace || workspace_bytes < y2_loss_v1_workspace_bytes(N, S)) {
+    set_error("y2_loss_v1_fwd_bwd: workspace too small");
+    return Y2_ERR_WORKSPACE;
+  }
+  Y2_ARG((((uintptr_t)workspace) & 7) == 0);
+  size_t smem = (size_t)LOSS_THREADS * (C + 5 * B + 5 + C) * sizeof(float);
+  if (smem > 48 * 1024) {
+    set_error("y2_loss_v1_fwd_bwd: C=%d B=%d needs %zu B smem", C, B, smem);
+    return Y2_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int ncell = N * S * S;
+  int nblocks = ceil_div(ncell, LOSS_THREADS);
+  loss_v1_kernel<<<nblocks, LOSS_THREADS, smem, st>>>(net, labels, ncell, N, S, B, C, image_size, lambda_coord,
+                                                      lambda_noobj, ious, object_mask, dnet, (double*)workspace);
+  Y2_LAUNCHED();
+  loss_finalize_kernel<<<1, 32, 0, st>>>((const double*)workspace, nblocks, N, lambda_coord, lambda_noobj, terms);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+}  // extern "C"

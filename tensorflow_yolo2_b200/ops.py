@@ -1,0 +1,233 @@
+"""Thin torch-tensor front end over the C ABI (include/yolo2_b200.h).
+
+torch is plumbing here: device memory, streams.  Every function enqueues on the current torch
+CUDA stream and raises (never falls back) if a tensor is not a contiguous CUDA tensor of the
+expected dtype or if the library call fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvParams, Y2_CONV_LEAKY, Y2_CONV_POOL2, Y2_CONV_OUT_F32, check
+
+ALPHA = 0.1        # yolo2_nets/darknet.py:5
+BN_EPS = 1e-3      # tf.layers.batch_normalization default
+BN_MOMENTUM = 0.99
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=None):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.Y2Error('expected a CUDA tensor (no CPU fallback exists)')
+    if not t.is_contiguous():
+        raise _lib.Y2Error('expected a contiguous tensor')
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.Y2Error('expected dtype %s, got %s' % (dtype, t.dtype))
+    return C.c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(_lib.load().y2_launch_count())
+
+
+# ---- a10 -----------------------------------------------------------------------------------
+def preprocess_u8(img_u8, bf16c8=True, out=None):
+    """[N,H,W,3] uint8 BGR (already resized) -> (x/255)*2-1 as bf16 [N,H,W,8] or f32 [N,H,W,3]."""
+    N, H, W, c = img_u8.shape
+    assert c == 3
+    if out is None:
+        out = torch.empty((N, H, W, 8), dtype=torch.bfloat16, device=img_u8.device) if bf16c8 else \
+            torch.empty((N, H, W, 3), dtype=torch.float32, device=img_u8.device)
+    check(_lib.load().y2_preprocess_u8(_p(img_u8, torch.uint8), _p(out), N, H, W, 1 if bf16c8 else 0, _stream()),
+          'y2_preprocess_u8')
+    return out
+
+
+def pad_cast_f32_to_bf16c8(x, out=None):
+    N, H, W, c = x.shape
+    assert c == 3
+    if out is None:
+        out = torch.empty((N, H, W, 8), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().y2_pad_cast_f32_to_bf16c8(_p(x, torch.float32), _p(out, torch.bfloat16), N, H, W, _stream()),
+          'y2_pad_cast_f32_to_bf16c8')
+    return out
+
+
+# ---- a1 ------------------------------------------------------------------------------------
+def conv_fwd_f32(x, w_hwio, bias, out=None):
+    N, H, W, Cin = x.shape
+    k, k2, cin2, Cout = w_hwio.shape
+    assert k == k2 and cin2 == Cin
+    if out is None:
+        out = torch.empty((N, H, W, Cout), dtype=torch.float32, device=x.device)
+    check(_lib.load().y2_conv_fwd_f32(_p(x, torch.float32), _p(w_hwio, torch.float32), _p(bias, torch.float32),
+                                      _p(out, torch.float32), N, H, W, Cin, Cout, k, _stream()), 'y2_conv_fwd_f32')
+    return out
+
+
+def conv_cin_padded(cin):
+    return int(_lib.load().y2_conv_cin_padded(cin))
+
+
+def pack_weights_bf16(w_hwio):
+    k, _, Cin, Cout = w_hwio.shape
+    n = int(_lib.load().y2_conv_packed_weight_elems(k, Cin, Cout))
+    out = torch.empty((n,), dtype=torch.bfloat16, device=w_hwio.device)
+    check(_lib.load().y2_pack_weights_bf16(_p(w_hwio, torch.float32), _p(out), k, Cin, Cout, _stream()),
+          'y2_pack_weights_bf16')
+    return out
+
+
+def conv_fwd_bf16(x, w_packed, ksize, cin, cout, scale=None, shift=None, leaky=True, pool=False, out_f32=False,
+                  ldy=None, out=None, alpha=ALPHA):
+    """x bf16 [N,H,W,Cin_p]; returns bf16 [N,Ho,Wo,Cout] or (out_f32) f32 [N*H*W, ldy]."""
+    N, H, W, cin_p = x.shape
+    assert cin_p == conv_cin_padded(cin), (cin_p, cin)
+    flags = (Y2_CONV_LEAKY if leaky else 0) | (Y2_CONV_POOL2 if pool else 0) | (Y2_CONV_OUT_F32 if out_f32 else 0)
+    ld = int(ldy) if ldy else cout
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    if out is None:
+        if out_f32:
+            out = torch.empty((N * Ho * Wo, ld), dtype=torch.float32, device=x.device)
+        else:
+            assert ld == cout
+            out = torch.empty((N, Ho, Wo, cout), dtype=torch.bfloat16, device=x.device)
+    prm = ConvParams(x=_p(x, torch.bfloat16), w_packed=_p(w_packed, torch.bfloat16), scale=_p(scale, torch.float32),
+                     shift=_p(shift, torch.float32), y=_p(out), N=N, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize,
+                     flags=flags, alpha=alpha, ldy=ld, reserved=0)
+    check(_lib.load().y2_conv_fwd_bf16(C.byref(prm), _stream()), 'y2_conv_fwd_bf16')
+    return out
+
+
+# ---- a2 / a3 -------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty((max(int(nbytes), 1 << 16),), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def bn_stats(x2d, C_, ld=None, workspace=None):
+    """x2d f32 [M, ld]; returns (mean[C], biased var[C])."""
+    M = x2d.shape[0]
+    ld = ld or x2d.shape[1]
+    lib = _lib.load()
+    need = int(lib.y2_bn_stats_workspace_bytes(M, C_))
+    ws = workspace if workspace is not None else _workspace(need, x2d.device)
+    mean = torch.empty((C_,), dtype=torch.float32, device=x2d.device)
+    var = torch.empty((C_,), dtype=torch.float32, device=x2d.device)
+    check(lib.y2_bn_stats(_p(x2d, torch.float32), M, C_, ld, _p(mean), _p(var), _p(ws), ws.numel(), _stream()),
+          'y2_bn_stats')
+    return mean, var
+
+
+def bn_fold(gamma, beta, mean, var, conv_bias=None, eps=BN_EPS, scale=None, shift=None):
+    C_ = gamma.numel()
+    if scale is None:
+        scale = torch.empty((C_,), dtype=torch.float32, device=gamma.device)
+    if shift is None:
+        shift = torch.empty((C_,), dtype=torch.float32, device=gamma.device)
+    check(_lib.load().y2_bn_fold(_p(gamma, torch.float32), _p(beta, torch.float32), _p(mean, torch.float32),
+                                 _p(var, torch.float32), _p(conv_bias, torch.float32), eps, _p(scale), _p(shift),
+                                 C_, _stream()), 'y2_bn_fold')
+    return scale, shift
+
+
+def bn_update_moving(mm, mv, mean, var, momentum=BN_MOMENTUM):
+    check(_lib.load().y2_bn_update_moving(_p(mm, torch.float32), _p(mv, torch.float32), _p(mean, torch.float32),
+                                          _p(var, torch.float32), momentum, mm.numel(), _stream()),
+          'y2_bn_update_moving')
+
+
+def affine_leaky_pool(x, N, H, W, C_, ldx=None, sub=None, scale=None, shift=None, leaky=True, pool=False,
+                      out_bf16=False, alpha=ALPHA, out=None):
+    """x f32 rows [N*H*W, ldx] (or [N,H,W,C]); y = leaky((x-sub)*scale+shift), optional 2x2 pool."""
+    ldx = ldx or C_
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    if out is None:
+        out = torch.empty((N, Ho, Wo, C_), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    check(_lib.load().y2_affine_leaky_pool(_p(x, torch.float32), ldx, _p(sub, torch.float32), _p(scale, torch.float32),
+                                           _p(shift, torch.float32), alpha, 1 if leaky else 0, 1 if pool else 0,
+                                           _p(out), 1 if out_bf16 else 0, N, H, W, C_, _stream()),
+          'y2_affine_leaky_pool')
+    return out
+
+
+# ---- a8 / a' -------------------------------------------------------------------------------
+def decode_ref_v1(net, S, B, C_, thresh=0.5):
+    N = net.shape[0]
+    assert net.numel() == N * S * S * (C_ + 5 * B)
+    dev = net.device
+    boxes = torch.empty((N, S, S, B, 4), dtype=torch.float32, device=dev)
+    conf = torch.empty((N, S, S, B), dtype=torch.float32, device=dev)
+    keep = torch.empty((N, S, S, B), dtype=torch.uint8, device=dev)
+    cls = torch.empty((N, S, S), dtype=torch.int32, device=dev)
+    check(_lib.load().y2_decode_ref_v1(_p(net, torch.float32), N, S, B, C_, thresh, _p(boxes), _p(conf), _p(keep),
+                                       _p(cls), _stream()), 'y2_decode_ref_v1')
+    return boxes, conf, keep, cls
+
+
+def decode_region(net, anchors, C_=20, thresh=0.3, boxes=None, scores=None):
+    N, S = net.shape[0], net.shape[1]
+    A = anchors.shape[0]
+    assert net.numel() == N * S * S * A * (5 + C_)
+    dev = net.device
+    if boxes is None:
+        boxes = torch.empty((N, S * S * A, 4), dtype=torch.float32, device=dev)
+    if scores is None:
+        scores = torch.empty((N, S * S * A, C_), dtype=torch.float32, device=dev)
+    check(_lib.load().y2_decode_region(_p(net, torch.float32), _p(anchors, torch.float32), N, S, A, C_, thresh,
+                                       _p(boxes), _p(scores), _stream()), 'y2_decode_region')
+    return boxes, scores
+
+
+def nms(boxes, scores, score_thresh=0.3, iou_thresh=0.45, max_keep=None, keep_idx=None, keep_count=None):
+    N, nbox, _ = boxes.shape
+    C_ = scores.shape[2]
+    max_keep = max_keep or nbox
+    dev = boxes.device
+    if keep_idx is None:
+        keep_idx = torch.full((N, C_, max_keep), -1, dtype=torch.int32, device=dev)
+    if keep_count is None:
+        keep_count = torch.empty((N, C_), dtype=torch.int32, device=dev)
+    check(_lib.load().y2_nms(_p(boxes, torch.float32), _p(scores, torch.float32), N, nbox, C_, score_thresh,
+                             iou_thresh, _p(keep_idx), _p(keep_count), max_keep, None, 0, _stream()), 'y2_nms')
+    return keep_idx, keep_count
+
+
+# ---- a6 / a7 -------------------------------------------------------------------------------
+def loss_v1(net, labels, S, B, C_, image_size, lambda_coord=5.0, lambda_noobj=0.5, want_grad=True):
+    """Returns (terms[5] = class, coord, object, noobject, total; ious; object_mask; dnet)."""
+    N = net.shape[0]
+    dev = net.device
+    lib = _lib.load()
+    terms = torch.empty((5,), dtype=torch.float32, device=dev)
+    ious = torch.empty((N, S, S, B), dtype=torch.float32, device=dev)
+    mask = torch.empty((N, S, S, B), dtype=torch.float32, device=dev)
+    dnet = torch.empty_like(net) if want_grad else None
+    need = int(lib.y2_loss_v1_workspace_bytes(N, S))
+    ws = _workspace(need, dev)
+    check(lib.y2_loss_v1_fwd_bwd(_p(net, torch.float32), _p(labels, torch.float32), N, S, B, C_, float(image_size),
+                                 lambda_coord, lambda_noobj, _p(terms), _p(ious), _p(mask), _p(dnet), _p(ws),
+                                 ws.numel(), _stream()), 'y2_loss_v1_fwd_bwd')
+    return terms, ious, mask, dnet
+
+
+# ---- a11 -----------------------------------------------------------------------------------
+def adam_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    lr_t = lr * (1.0 - b2 ** step) ** 0.5 / (1.0 - b1 ** step)
+    check(_lib.load().y2_adam_step(_p(p, torch.float32), _p(g, torch.float32), _p(m, torch.float32),
+                                   _p(v, torch.float32), p.numel(), lr_t, b1, b2, eps, _stream()), 'y2_adam_step')

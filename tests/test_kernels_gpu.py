@@ -1,0 +1,224 @@
+"""GPU parity tests: every CUDA kernel called through the C ABI (tensorflow_yolo2_b200.ops ->
+ctypes -> libyolo2_b200.so) against the CPU oracle on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import yolo2_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from tensorflow_yolo2_b200 import ops as _ops
+    from tensorflow_yolo2_b200 import _lib
+    _lib.load()
+    return _ops
+
+
+def cu(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+# ---------------------------------------------------------------------------------- a10
+def test_preprocess_u8_bit_exact(ops, golden_dir):
+    import cv2
+    im = cv2.resize(cv2.imread(os.path.join(golden_dir, 'testImg1.jpg')), (416, 416))
+    want = O.preprocess_u8(im)
+    got = ops.preprocess_u8(cu(im[None]), bf16c8=False).cpu().numpy()[0]
+    np.testing.assert_array_equal(got, want)                 # integer/byte work: bit-exact
+    got8 = ops.preprocess_u8(cu(im[None]), bf16c8=True).float().cpu().numpy()[0]
+    want8 = torch.tensor(want).to(torch.bfloat16).float().numpy()
+    np.testing.assert_array_equal(got8[..., :3], want8)
+    assert np.all(got8[..., 3:] == 0)
+
+
+# ---------------------------------------------------------------------------------- a1 (fp32 path)
+@pytest.mark.parametrize('N,H,W,Cin,Cout,k', [(2, 13, 13, 64, 48, 3), (1, 16, 20, 3, 32, 3), (2, 7, 7, 128, 30, 1),
+                                              (1, 26, 26, 32, 125, 3)])
+def test_conv_f32_vs_oracle(ops, N, H, W, Cin, Cout, k):
+    rs = np.random.RandomState(1)
+    x = rs.randn(N, H, W, Cin).astype(np.float32)
+    w = (rs.randn(k, k, Cin, Cout) * 0.1).astype(np.float32)
+    b = rs.randn(Cout).astype(np.float32)
+    want = (O.conv2d_same(torch.tensor(x), torch.tensor(w), torch.float64) + torch.tensor(b).double()).numpy()
+    got = ops.conv_fwd_f32(cu(x), cu(w), cu(b)).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())   # fp32 path: 1e-5
+
+
+# ---------------------------------------------------------------------------------- a2 / a3
+def test_bn_stats_large_mean(ops):
+    rs = np.random.RandomState(2)
+    M, C = 3 * 13 * 13, 70
+    x = (rs.randn(M, C) * rs.uniform(0.5, 3, C) * 1e6 + rs.randn(C) * 1e9).astype(np.float32)   # |mean| >> std
+    mean, var = ops.bn_stats(cu(x), C)
+    np.testing.assert_allclose(mean.cpu().numpy(), x.astype(np.float64).mean(0), rtol=1e-6)
+    np.testing.assert_allclose(var.cpu().numpy(), x.astype(np.float64).var(0), rtol=1e-5)
+
+
+@pytest.mark.parametrize('C,pool,bf16', [(64, True, False), (125, False, False), (32, True, True), (30, False, False)])
+def test_affine_leaky_pool(ops, C, pool, bf16):
+    rs = np.random.RandomState(3)
+    N, H, W = 2, 8, 6
+    ld = (C + 31) // 32 * 32
+    x = rs.randn(N * H * W, ld).astype(np.float32)
+    sub, scale, shift = [rs.randn(C).astype(np.float32) for _ in range(3)]
+    y = (torch.tensor(x[:, :C]).double().reshape(N, H, W, C) - torch.tensor(sub).double()) * torch.tensor(scale).double() \
+        + torch.tensor(shift).double()
+    y = torch.maximum(O.ALPHA * y, y)
+    if pool:
+        y = O.max_pool_2x2(y)
+    got = ops.affine_leaky_pool(cu(x), N, H, W, C, ldx=ld, sub=cu(sub), scale=cu(scale), shift=cu(shift), leaky=True,
+                                pool=pool, out_bf16=bf16).float().cpu().numpy()
+    np.testing.assert_allclose(got, y.numpy(), rtol=1e-2 if bf16 else 1e-5, atol=1e-2 if bf16 else 1e-5)
+
+
+def test_bn_fold_and_moving(ops):
+    rs = np.random.RandomState(4)
+    C = 50
+    g, b, m, bias = [rs.randn(C).astype(np.float32) for _ in range(4)]
+    v = rs.uniform(0.1, 2, C).astype(np.float32)
+    scale, shift = ops.bn_fold(cu(g), cu(b), cu(m), cu(v), cu(bias))
+    s = g / np.sqrt(v + 1e-3)
+    np.testing.assert_allclose(scale.cpu().numpy(), s, rtol=1e-5)
+    np.testing.assert_allclose(shift.cpu().numpy(), b + (bias - m) * s, rtol=1e-4, atol=1e-5)
+    mm, mv = cu(np.zeros(C, np.float32)), cu(np.ones(C, np.float32))
+    ops.bn_update_moving(mm, mv, cu(m), cu(v))
+    np.testing.assert_allclose(mm.cpu().numpy(), m * 0.01, rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(mv.cpu().numpy(), 0.99 + v * 0.01, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------- a8
+@pytest.mark.parametrize('name,S,B', [('s7', 7, 2), ('s13', 13, 5)])
+def test_decode_ref_v1_golden(ops, golden_dir, name, S, B):
+    g = np.load(os.path.join(golden_dir, 'ref_decode.npz'))
+    pred = g[name + '_pred']
+    boxes, conf, keep, cls = [t.cpu().numpy() for t in ops.decode_ref_v1(cu(pred), S, B, 20, 0.5)]
+    dec = O.decode_ref_v1(pred[0], S, B, 20, 0.5)
+    np.testing.assert_array_equal(boxes[0, ..., 0], dec['xs'])        # same fp32 op order: bit-exact
+    np.testing.assert_array_equal(boxes[0, ..., 1], dec['ys'])
+    np.testing.assert_array_equal(boxes[0, ..., 2], dec['ws'])
+    np.testing.assert_array_equal(boxes[0, ..., 3], dec['hs'])
+    np.testing.assert_array_equal(keep[0].astype(bool), dec['keep'])
+    np.testing.assert_array_equal(cls[0], dec['cls'])
+    # and the reference's own draw list (golden produced by the reference source)
+    im_w, im_h = [int(v) for v in g['im_wh']]
+    d = dict(xs=boxes[0, ..., 0], ys=boxes[0, ..., 1], ws=boxes[0, ..., 2], hs=boxes[0, ..., 3], conf=conf[0],
+             keep=keep[0].astype(bool), cls=cls[0])
+    rects = np.array([r[:4] for r in O.draw_list_ref_v1(d, im_w, im_h)], dtype=np.int64).reshape(-1, 4)
+    np.testing.assert_array_equal(rects, g[name + '_rects'])
+
+
+# ---------------------------------------------------------------------------------- a' region decode
+@pytest.mark.parametrize('N,S', [(3, 13), (2, 19), (1, 7)])
+def test_decode_region_vs_oracle(ops, N, S):
+    net = (2.0 * np.random.RandomState(1234).randn(N, S, S, 125)).astype(np.float32)
+    boxes, scores = ops.decode_region(cu(net), cu(O.VOC_ANCHORS), 20, 0.3)
+    wb, ws_thr, ws = O.region_decode_v2(net, O.VOC_ANCHORS, 20, 0.3)
+    np.testing.assert_allclose(boxes.cpu().numpy(), wb, rtol=1e-5, atol=1e-7)
+    got = scores.cpu().numpy()
+    # threshold flips are allowed only for scores within 1e-5 relative of the threshold
+    near = np.abs(ws - 0.3) < 1e-5
+    np.testing.assert_allclose(got[~near], ws_thr[~near], rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------- a' NMS (bit-exact)
+def _nms_check(ops, boxes, scores, score_thr, iou_thr):
+    ki, kc = ops.nms(cu(boxes), cu(scores), score_thr, iou_thr)
+    ki, kc = ki.cpu().numpy(), kc.cpu().numpy()
+    for n in range(boxes.shape[0]):
+        want = O.nms_per_class(boxes[n], scores[n], iou_thr, score_thr)
+        for k in range(scores.shape[2]):
+            assert kc[n, k] == len(want[k]), (n, k, kc[n, k], len(want[k]))
+            np.testing.assert_array_equal(ki[n, k, :kc[n, k]], want[k])
+
+
+def test_nms_bit_exact_decoded(ops):
+    net = (2.0 * np.random.RandomState(1234).randn(4, 13, 13, 125)).astype(np.float32)
+    boxes, scores = ops.decode_region(cu(net), cu(O.VOC_ANCHORS), 20, 0.3)
+    _nms_check(ops, boxes.cpu().numpy(), scores.cpu().numpy(), 0.3, 0.45)
+
+
+def test_nms_bit_exact_dense_overlaps(ops):
+    rs = np.random.RandomState(7)
+    N, nbox, C = 2, 845, 20
+    boxes = np.concatenate([rs.uniform(0.3, 0.7, (N, nbox, 2)), rs.uniform(0.05, 0.5, (N, nbox, 2))], -1).astype(np.float32)
+    scores = rs.uniform(0, 1, (N, nbox, C)).astype(np.float32)
+    scores[scores < 0.6] = 0                         # ~40% candidates per class, heavy overlap
+    scores[0, 5:40, 3] = 0.75                        # score ties -> index order
+    boxes[0, 100] = boxes[0, 101]                    # identical boxes -> IoU 1
+    _nms_check(ops, boxes, scores, 0.3, 0.45)
+
+
+def test_nms_worst_case_all_candidates_and_empty(ops):
+    rs = np.random.RandomState(8)
+    N, nbox, C = 1, 845, 3
+    boxes = np.concatenate([rs.uniform(0, 1, (N, nbox, 2)), rs.uniform(0.01, 0.3, (N, nbox, 2))], -1).astype(np.float32)
+    scores = rs.uniform(0.01, 1, (N, nbox, C)).astype(np.float32)
+    scores[:, :, 2] = 0                              # an empty class
+    _nms_check(ops, boxes, scores, 0.0, 0.45)        # thresh 0: every box of classes 0,1 is a candidate
+
+
+def test_nms_fallback_path_1805_boxes(ops):
+    rs = np.random.RandomState(9)
+    N, nbox, C = 1, 1805, 2
+    boxes = np.concatenate([rs.uniform(0, 1, (N, nbox, 2)), rs.uniform(0.01, 0.2, (N, nbox, 2))], -1).astype(np.float32)
+    scores = rs.uniform(0.01, 1, (N, nbox, C)).astype(np.float32)
+    _nms_check(ops, boxes, scores, 0.0, 0.45)        # n > 1024 -> on-the-fly sweep
+
+
+# ---------------------------------------------------------------------------------- a6 / a7 loss
+@pytest.mark.parametrize('name', ['katA', 'katB', 'katC', 'rand7', 'rand13', 'rand19'])
+def test_loss_v1_golden(ops, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, 'ref_loss.npz'))
+    IS, S, B = [int(v) for v in g[name + '_cfg']]
+    net, lab = g[name + '_net'], g[name + '_labels']
+    terms, ious, mask, dnet = ops.loss_v1(cu(net, torch.float32), cu(lab, torch.float32), S, B, 20, IS)
+    r = O.get_loss(net, lab, 20, net.shape[0], IS, S, B, with_grad=True)
+    want_terms = [r['class_loss'], r['coord_loss'], r['object_loss'], r['noobject_loss'], r['loss']]
+    np.testing.assert_allclose(terms.cpu().numpy(), want_terms, rtol=1e-3, atol=1e-6)      # spec: 1e-3 relative
+    assert float(terms[4]) == pytest.approx(float(g[name + '_loss']), rel=1e-3)            # the reference's own graph
+    np.testing.assert_allclose(ious.cpu().numpy(), r['ious'], atol=2e-6)
+    np.testing.assert_array_equal(mask.cpu().numpy(), r['object_mask'])
+    gmax = np.abs(r['dnet']).max()
+    np.testing.assert_allclose(dnet.cpu().numpy(), r['dnet'], rtol=1e-3, atol=1e-5 * gmax)
+    if name not in ('katA', 'katB'):
+        np.testing.assert_allclose(dnet.cpu().numpy(), g[name + '_dnet'], rtol=1e-3, atol=1e-5 * gmax)
+
+
+def test_loss_v1_batch64(ops):
+    rs = np.random.RandomState(0)
+    N, S, B, IS = 64, 13, 5, 416
+    net = rs.uniform(-0.3, 1.0, (N, S, S, 45)).astype(np.float32)
+    lab = np.zeros((N, S, S, 25), np.float32)
+    for n in range(N):
+        for _ in range(rs.randint(1, 4)):
+            cx, cy = rs.uniform(0, IS, 2)
+            j, i = int(cx * S / IS), int(cy * S / IS)
+            if lab[n, i, j, 0] == 1:
+                continue
+            lab[n, i, j, :5] = [1, cx, cy, rs.uniform(20, 300), rs.uniform(20, 300)]
+            lab[n, i, j, 5 + rs.randint(20)] = 1
+    terms, ious, mask, dnet = ops.loss_v1(cu(net), cu(lab), S, B, 20, IS)
+    r = O.get_loss(net, lab, 20, N, IS, S, B, with_grad=True)
+    assert float(terms[4]) == pytest.approx(r['loss'], rel=1e-4)
+    np.testing.assert_array_equal(mask.cpu().numpy(), r['object_mask'])
+    np.testing.assert_allclose(dnet.cpu().numpy(), r['dnet'], rtol=1e-3, atol=1e-5 * np.abs(r['dnet']).max())
+
+
+# ---------------------------------------------------------------------------------- a11 Adam
+def test_adam_step(ops):
+    rs = np.random.RandomState(5)
+    n = 10007
+    p, g, m, v = rs.randn(n).astype(np.float32), rs.randn(n).astype(np.float32), \
+        rs.randn(n).astype(np.float32) * 0.1, rs.uniform(0, 1, n).astype(np.float32)
+    pt, mt, vt = cu(p), cu(m), cu(v)
+    ops.adam_step(pt, cu(g), mt, vt, step=3)
+    wp, wm, wv = O.adam_step(p.astype(np.float64), g.astype(np.float64), m.astype(np.float64), v.astype(np.float64), 3)
+    np.testing.assert_allclose(pt.cpu().numpy(), wp, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(mt.cpu().numpy(), wm, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(vt.cpu().numpy(), wv, rtol=1e-5, atol=1e-7)
