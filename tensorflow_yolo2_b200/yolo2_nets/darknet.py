@@ -1,0 +1,234 @@
+"""Darknet19 network builders with the reference's interface (src/yolo2_nets/darknet.py), running on
+the B200 kernels of libyolo2_b200.so.
+
+Same names, positional/keyword arguments and defaults as the reference:
+    alpha, weight_variable, bias_variable, conv2d, max_pool, conv_layer, conv_bn_layer,
+    darknet19_core, darknet19_detection
+Tensors are CUDA torch tensors in NHWC (float32 in, bf16 between layers on the tensor-core path,
+float32 out of the detection head).  Where the reference builds a TF graph, these functions execute
+eagerly; variables live in a VariableStore that reproduces TF's auto-generated names
+(`darknet19/Variable_3`, `darknet19/batch_normalization_1/gamma`, ...), created on first use and
+found again under `reuse=True`.
+
+Compute path (config.COMPUTE): 'bf16' -> tcgen05 implicit-GEMM conv with BN/leaky/pool fused in the
+epilogue; 'fp32' -> exact FFMA conv + separate BN/leaky/pool kernels.  No CPU / cuDNN fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import config as cfg
+from .. import ops
+from ..variables import default_store
+
+alpha = 0.1                       # darknet.py:5
+
+# The reference's UPDATE_OPS only run as a dependency of train_op (pascal_train_darknet.py:49-50);
+# a plain sess.run(grid_net) with is_training=True normalises with batch statistics but leaves the
+# moving averages untouched.  The training harness flips this flag.
+UPDATE_MOVING_AVERAGES = False
+
+# (ksize, cin, cout, pool_after): darknet.py:150-177
+CORE_PLAN = [
+    (3, 3, 32, True), (3, 32, 64, True),
+    (3, 64, 128, False), (3, 128, 64, False), (3, 64, 128, True),
+    (3, 128, 256, False), (1, 256, 128, False), (3, 128, 256, True),
+    (3, 256, 512, False), (1, 512, 256, False), (3, 256, 512, False), (1, 512, 256, False), (3, 256, 512, True),
+    (3, 512, 1024, False), (1, 1024, 512, False), (3, 512, 1024, False), (1, 1024, 512, False),
+    (3, 512, 1024, False),
+]
+
+
+def _device():
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _as_param(store, name):
+    """Variables are created as numpy arrays by the store; move them to the GPU on first touch."""
+    v = store[name]
+    if isinstance(v, np.ndarray):
+        v = torch.from_numpy(v).to(_device())
+        store.vars[name] = v
+    return v
+
+
+# ---------------------------------------------------------------------------------------------
+# packed-weight / folded-BN caches (invalidated when the store changes)
+# ---------------------------------------------------------------------------------------------
+_pack_cache = {}
+
+
+def _packed(store, wname):
+    key = (id(store), wname)
+    hit = _pack_cache.get(key)
+    w = _as_param(store, wname)
+    if hit is None or hit[0] != store.version or hit[1] != w.data_ptr():
+        hit = (store.version, w.data_ptr(), ops.pack_weights_bf16(w))
+        _pack_cache[key] = hit
+    return hit[2]
+
+
+_zeros_cache = {}
+
+
+def _zeros(c):
+    key = (c, torch.cuda.current_device())
+    z = _zeros_cache.get(key)
+    if z is None:
+        z = torch.zeros((c,), dtype=torch.float32, device=_device())
+        _zeros_cache[key] = z
+    return z
+
+
+# ---------------------------------------------------------------------------------------------
+# building blocks (darknet.py:10-46)
+# ---------------------------------------------------------------------------------------------
+def weight_variable(shape):
+    """darknet.py:10-12 -- truncated normal, stddev 0.1."""
+    store = default_store()
+    name, _ = store.weight_variable(list(shape))
+    return _as_param(store, name)
+
+
+def bias_variable(shape):
+    """darknet.py:15-17 -- constant 0.1."""
+    store = default_store()
+    name, _ = store.bias_variable(list(shape))
+    return _as_param(store, name)
+
+
+def conv2d(x, W, stride):
+    """darknet.py:20-21: SAME, stride 1 cross-correlation (exact fp32 kernel, no bias)."""
+    assert stride == 1
+    return ops.conv_fwd_f32(x.float().contiguous(), W, None)
+
+
+def max_pool(x, pool_size, stride):
+    """darknet.py:24-25: 2x2/2 max-pool."""
+    assert pool_size == 2 and stride == 2
+    N, H, W, C = x.shape
+    out_bf16 = x.dtype == torch.bfloat16
+    xf = x if x.dtype == torch.float32 else x.float()
+    return ops.affine_leaky_pool(xf.contiguous(), N, H, W, C, leaky=False, pool=True, out_bf16=out_bf16)
+
+
+def conv_layer(x, filter_size, input_chl, output_chl, stride):
+    """darknet.py:32-36: conv + bias (fp32)."""
+    assert stride == 1
+    W_conv = weight_variable([filter_size, filter_size, input_chl, output_chl])
+    b_conv = bias_variable([output_chl])
+    return ops.conv_fwd_f32(x.float().contiguous(), W_conv, b_conv)
+
+
+def conv_bn_layer(x, filter_size, input_chl, output_chl, stride, is_training, _pool=False, _out_f32=None):
+    """darknet.py:39-46: conv + bias -> batch norm -> leaky(0.1).
+
+    `_pool` fuses the 2x2 max-pool that follows the layer in the builders (darknet.py:151,154,...);
+    `_out_f32` forces a float32 result (the detection output).  Both are extensions with defaults
+    that reproduce the reference call."""
+    assert stride == 1
+    store = default_store()
+    wname, _ = store.weight_variable([filter_size, filter_size, input_chl, output_chl])
+    bname, _ = store.bias_variable([output_chl])
+    bn = store.batch_norm_variables(output_chl)
+    W, b = _as_param(store, wname), _as_param(store, bname)
+    gamma, beta = _as_param(store, bn['gamma']), _as_param(store, bn['beta'])
+    mm, mv = _as_param(store, bn['moving_mean']), _as_param(store, bn['moving_variance'])
+    training = bool(is_training)
+    N, H, Wd, _ = x.shape
+    mode = cfg.COMPUTE
+    if mode == 'fp32':
+        h = ops.conv_fwd_f32(x.float().contiguous(), W, b)
+        if training:
+            mean, var = ops.bn_stats(h.view(-1, output_chl), output_chl)
+            if UPDATE_MOVING_AVERAGES:
+                ops.bn_update_moving(mm, mv, mean, var)
+        else:
+            mean, var = mm, mv
+        scale, shift = ops.bn_fold(gamma, beta, _zeros(output_chl), var, None)      # shift == beta
+        return ops.affine_leaky_pool(h, N, H, Wd, output_chl, sub=mean, scale=scale, shift=shift, leaky=True,
+                                     pool=_pool, out_bf16=False)
+    if mode != 'bf16':
+        raise ValueError('config.COMPUTE must be "bf16" or "fp32"')
+    # ---- tensor-core path ----
+    if x.dtype == torch.float32:
+        if input_chl == 3:
+            xb = ops.pad_cast_f32_to_bf16c8(x.contiguous())
+        else:
+            xb = x.to(torch.bfloat16).contiguous()
+    else:
+        xb = x
+    wp = _packed(store, wname)
+    out_f32 = bool(_out_f32)
+    if not training:
+        scale, shift = ops.bn_fold(gamma, beta, mm, mv, b)          # bias folded: acc has no bias
+        if out_f32:
+            ld = (output_chl + 31) // 32 * 32
+            raw = ops.conv_fwd_bf16(xb, wp, filter_size, input_chl, output_chl, scale=scale, shift=shift, leaky=True,
+                                    pool=_pool, out_f32=True, ldy=ld)
+            Ho, Wo = (H // 2, Wd // 2) if _pool else (H, Wd)
+            return raw.view(N, Ho, Wo, ld)[..., :output_chl].contiguous() if ld != output_chl else raw.view(N, Ho, Wo, ld)
+        return ops.conv_fwd_bf16(xb, wp, filter_size, input_chl, output_chl, scale=scale, shift=shift, leaky=True,
+                                 pool=_pool)
+    # batch statistics: raw fp32 conv+bias, stats, then normalise + leaky (+ pool)
+    ld = (output_chl + 31) // 32 * 32
+    raw = ops.conv_fwd_bf16(xb, wp, filter_size, input_chl, output_chl, scale=None, shift=b, leaky=False, pool=False,
+                            out_f32=True, ldy=ld)
+    mean, var = ops.bn_stats(raw, output_chl, ld=ld)
+    if UPDATE_MOVING_AVERAGES:
+        ops.bn_update_moving(mm, mv, mean, var)
+    scale, shift = ops.bn_fold(gamma, beta, _zeros(output_chl), var, None)
+    return ops.affine_leaky_pool(raw, N, H, Wd, output_chl, ldx=ld, sub=mean, scale=scale, shift=shift, leaky=True,
+                                 pool=_pool, out_bf16=not out_f32)
+
+
+# ---------------------------------------------------------------------------------------------
+# builders (darknet.py:126-201)
+# ---------------------------------------------------------------------------------------------
+class _variable_scope:
+    """tf.variable_scope(scope, default, [inputs], reuse=reuse): reuse=True replays the same
+    auto-generated names so the existing variables are found."""
+
+    def __init__(self, name, reuse=None):
+        self.name, self.reuse = name, reuse
+        self.store = default_store()
+
+    def __enter__(self):
+        self.ctx = self.store.scope(self.name)
+        self.ctx.__enter__()
+        if self.reuse:
+            prefix = self.store._prefix()
+            for key in [k for k in self.store._counters if k[0] == prefix or k[0].startswith(prefix + '/')]:
+                del self.store._counters[key]
+        return self
+
+    def __exit__(self, *exc):
+        return self.ctx.__exit__(*exc)
+
+
+def darknet19_core(inputs, num_classes=None, is_training=True, global_pool=True, output_stride=None, reuse=None,
+                   scope='darknet19'):
+    """darknet.py:126-179.  `num_classes`, `global_pool`, `output_stride` are accepted and ignored,
+    exactly like the reference.  Fully convolutional: 224 -> 7x7, 416 -> 13x13, 608 -> 19x19."""
+    net = inputs
+    with _variable_scope(scope, reuse=reuse):
+        for (k, cin, cout, pool) in CORE_PLAN:
+            net = conv_bn_layer(net, k, cin, cout, 1, is_training, _pool=pool)
+    return net
+
+
+def darknet19_detection(net, output_filter, is_training=True, scope='darknet19_detection', reuse=None):
+    """darknet.py:182-201: conv1..conv3 (3x3, 1024->1024) + output (1x1 -> output_filter), every
+    layer conv+BN+leaky, `is_training` defaulting to True (so the head normalises with batch
+    statistics unless the caller says otherwise -- the reference's scripts never do)."""
+    with _variable_scope(scope, reuse=reuse):
+        with _variable_scope('conv1'):
+            net = conv_bn_layer(net, 3, 1024, 1024, 1, is_training)
+        with _variable_scope('conv2'):
+            net = conv_bn_layer(net, 3, 1024, 1024, 1, is_training)
+        with _variable_scope('conv3'):
+            net = conv_bn_layer(net, 3, 1024, 1024, 1, is_training)
+        with _variable_scope('output'):
+            output = conv_bn_layer(net, 1, 1024, output_filter, 1, is_training, _out_f32=True)
+    return output
