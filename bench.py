@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of Darknet19-YOLO2 416x416 inference (forward + region decode + per-class
+NMS), the metric BASELINE.json names, on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]        # CPU restatement of the reference
+    torchrun ... bench.py --gpus N ...                               # N > 1: one rank per GPU
+
+One "step" = one pass of the hot path over one synthetic batch (64 images of 416x416x3 uint8 per
+GPU, random-init weights of the reference's initialiser, core BN in inference mode, head BN in
+batch-statistics mode -- the reference detect script's graph).  Prints ONE JSON line (rank 0).
+
+value      device-timed throughput with the batch already resident in HBM (CUDA events per step on
+           the launching stream, L2 flushed between steps, max over ranks).
+e2e        same metric through Yolo2Engine.infer(): pinned host uint8 batch -> H2D -> step -> D2H of
+           the detections, copies inside the timed region.
+roofline   tensor-core bound: algorithmic conv FLOPs of one step / summed conv-kernel time per step,
+           measured live with CUDA events around each conv launch, vs MEASURED_PEAKS.json.
+cpu_baseline  the oracle (CPU restatement of the reference, PyTorch-CPU fp32) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 64
+IMAGE_SIZE = 416
+OUTPUT_FILTER = 125
+SCORE_THRESH, IOU_THRESH = 0.3, 0.45
+METRIC = 'images/sec Darknet19-YOLO2 416x416 (fwd+decode+NMS)'
+
+# (k, cin, cout, out_hw) at 416^2 -> algorithmic FLOPs = 2*k*k*cin*cout*hw*hw   
+def conv_flops_per_image(image_size, output_filter):
+    from tensorflow_yolo2_b200.yolo2_nets.darknet import CORE_PLAN
+    h = image_size
+    total, per = 0.0, []
+    plan = list(CORE_PLAN) + [(3, 1024, 1024, False)] * 3 + [(1, 1024, output_filter, False)]
+    for (k, cin, cout, pool) in plan:
+        f = 2.0 * k * k * cin * cout * h * h
+        per.append(f)
+        total += f
+        if pool:
+            h //= 2
+    return total, per
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=d.get('bf16_tflops', 1590.0), sustained=d.get('bf16_tflops_sustained', 1400.0),
+                    hbm=d.get('hbm_gbs', 6650.0), which='measured')
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, which='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return None
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return None
+        # under-load samples: the top half of the observed clocks
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU restatement of the reference (oracle) -- used ONLY for cpu_baseline / --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(batch, threads=None, reps=1, seed=0):
+    import numpy as np
+    import torch
+    from oracle import yolo2_oracle as O
+    from tests.helpers import make_store, oracle_params
+    if threads:
+        torch.set_num_threads(threads)
+    st, layers = make_store(OUTPUT_FILTER, seed=seed)
+    core_p, head_p = oracle_params(st, layers)
+    img = np.random.RandomState(seed).randint(0, 256, (batch, IMAGE_SIZE, IMAGE_SIZE, 3)).astype(np.uint8)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        x = torch.tensor(O.preprocess_u8(img))
+        with torch.no_grad():
+            net = O.darknet19_forward(x, core_p, head_p, core_training=False, head_training=True,
+                                      dtype=torch.float32).numpy()
+        boxes, sthr, _ = O.region_decode_v2(net, O.VOC_ANCHORS, 20, SCORE_THRESH)
+        for n in range(batch):
+            O.nms_per_class(boxes[n], sthr[n], IOU_THRESH, SCORE_THRESH)
+        times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_batch = 8
+    t_all, threads = cpu_reference_step(sample_batch, threads=cores, reps=args.warmup + args.steps)
+    timed = t_all[args.warmup:]
+    total = sum(timed)
+    value = sample_batch * len(timed) / total
+    sample = 'batch %d of 416x416 per step (bounded sample of the batch-64 workload), torch-CPU fp32' % sample_batch
+    line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total / len(timed), higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload='Darknet19-YOLO2 416x416 inference, fwd + region decode + NMS, batch 64/GPU '
+                                     '(reference arm: CPU restatement of the reference, sample batch %d)' % sample_batch),
+                cpu_baseline=dict(value=value, unit='images/s', cores=threads, kind='port', sample=sample),
+                e2e=dict(value=value, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tensorflow_yolo2_b200 import ops
+    from tensorflow_yolo2_b200.engine import Yolo2Engine
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    N = BATCH_PER_GPU
+    eng = Yolo2Engine(N, IMAGE_SIZE, OUTPUT_FILTER, score_thresh=SCORE_THRESH, iou_thresh=IOU_THRESH, max_keep=64,
+                      use_cuda_graph=True, device=dev, seed=0)
+    # 4 distinct synthetic batches (4 x 33 MB > L2 is not needed: L2 is flushed between steps anyway)
+    g = torch.Generator(device='cpu').manual_seed(1234 + rank)
+    host_batches = [torch.randint(0, 256, (N, IMAGE_SIZE, IMAGE_SIZE, 3), dtype=torch.uint8, generator=g).pin_memory()
+                    for _ in range(2)]
+    dev_batches = [b.to(dev) for b in host_batches]
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)      # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i, timed):
+        eng.in_u8.copy_(dev_batches[i % len(dev_batches)])       # device->device, outside the events
+        flush.zero_()                                            # L2 flush, outside the events
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            eng.run()
+            e1.record(stream)
+            return e0, e1
+        eng.run()
+        return None
+
+    for i in range(max(args.warmup, 3)):
+        one_step(i, False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [one_step(i, True) for i in range(args.steps)]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms = float(tt.item())
+    value = world * N * args.steps / (t_ms * 1e-3)
+    cand = int((eng.scores > 0).sum().item())
+    kept = int(eng.keep_count.sum().item())
+
+    # ---- e2e: pinned host uint8 -> H2D -> step -> D2H (keep lists + boxes of the batch) ----
+    res_host = dict(keep_idx=torch.empty(eng.keep_idx.shape, dtype=torch.int32).pin_memory(),
+                    keep_count=torch.empty(eng.keep_count.shape, dtype=torch.int32).pin_memory(),
+                    boxes=torch.empty(eng.boxes.shape, dtype=torch.float32).pin_memory())
+    h2d = host_batches[0].numel()
+    d2h = sum(t.numel() * t.element_size() for t in res_host.values())
+
+    def e2e_step(i):
+        eng.in_u8.copy_(host_batches[i % len(host_batches)], non_blocking=True)
+        eng.run()
+        res_host['keep_idx'].copy_(eng.keep_idx, non_blocking=True)
+        res_host['keep_count'].copy_(eng.keep_count, non_blocking=True)
+        res_host['boxes'].copy_(eng.boxes, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record(stream)
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * args.steps / (float(te.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (conv_tc_kernel), timed live per launch ----
+    eng.use_cuda_graph = False
+    conv_ms = conv_kernel_times(eng, ops, iters=max(3, min(args.steps, 10)))
+    flops_img, per_layer = conv_flops_per_image(IMAGE_SIZE, OUTPUT_FILTER)
+    peaks = load_peaks()
+    conv_total_ms = sum(conv_ms)
+    achieved = N * flops_img / (conv_total_ms * 1e-3) / 1e12
+    roofline = dict(bound='tensor', achieved=achieved, peak=peaks['sustained'], unit='TFLOP/s',
+                    frac=achieved / peaks['sustained'], traffic=None, peak_source=peaks['which'] + ' sustained bf16',
+                    kernel='conv_tc_kernel (22 launches/step)', conv_ms_per_step=conv_total_ms,
+                    per_layer_tflops=[round(N * f / (ms * 1e-3) / 1e12, 1) for f, ms in zip(per_layer, conv_ms)])
+
+    # ---- CPU baseline: oracle on a bounded sample ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            times, threads = cpu_reference_step(4, threads=os.cpu_count(), reps=2)
+            cpu = dict(value=4 / min(times), unit='images/s', cores=threads, kind='port',
+                       sample='batch 4 of 416x416 (fwd+decode+NMS), best of 2, torch-CPU fp32 restatement of the reference')
+        except Exception as e:  # noqa: BLE001
+            cpu = dict(value=None, unit='images/s', cores=os.cpu_count(), kind='port', sample='failed: %r' % (e,))
+
+    line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=t_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
+                data='synthetic',
+                config=dict(workload='Darknet19-YOLO2 416x416 inference, fwd + region decode + per-class NMS, '
+                                     'synthetic uint8 batch %d per GPU (BASELINE.json configs[1])' % N,
+                            global_batch=world * N, image_size=IMAGE_SIZE, output_filter=OUTPUT_FILTER,
+                            score_thresh=SCORE_THRESH, iou_thresh=IOU_THRESH, head_bn='batch statistics',
+                            l2='flushed (256 MiB memset) between timed steps', parallelism='batch sharding x%d' % world,
+                            nms_candidates=cand, nms_kept=kept),
+                e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                gpu_launches=int(eng.launches_per_step * args.steps), launches_per_step=int(eng.launches_per_step),
+                roofline=roofline, cpu_baseline=cpu, clocks=clocks)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def conv_kernel_times(eng, ops, iters=5):
+    """Per-layer conv kernel durations (ms) with CUDA events around each conv launch, eager mode."""
+    import torch
+    real = ops.conv_fwd_bf16
+    records = []
+
+    def timed_conv(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = real(*a, **k)
+        e1.record()
+        records.append((e0, e1))
+        return out
+
+    ops.conv_fwd_bf16 = timed_conv
+    try:
+        eng._enqueue()
+        torch.cuda.synchronize()
+        records.clear()
+        for _ in range(iters):
+            eng._enqueue()
+        torch.cuda.synchronize()
+    finally:
+        ops.conv_fwd_bf16 = real
+    nl = len(eng.layers)
+    ms = [0.0] * nl
+    for i, (a, b) in enumerate(records):
+        ms[i % nl] += a.elapsed_time(b) / iters
+    return ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -134,6 +134,10 @@ int y2_nms(const float* boxes, const float* scores, int N, int nbox, int C, floa
            float iou_thresh, int32_t* keep_idx, int32_t* keep_count, int max_keep,
            void* workspace, size_t workspace_bytes, y2_stream_t stream);
 
+/* ---- a7: IoU of n box pairs (yolo2_nets/net_utils.py:222-260 get_iou) ------------------------
+ * boxes1/boxes2 [n,4] (cx,cy,w,h) f32 -> iou [n]; float32 in the reference's op order. */
+int y2_iou(const float* boxes1, const float* boxes2, float* iou, size_t n, y2_stream_t stream);
+
 /* ---- a6+a7: YOLO loss forward + backward, one kernel (net_utils.py:263-372 + TF autodiff) ----
  * net [N,S,S,C+5B], labels [N,S,S,5+C] float32.  terms[5] = class, coord, object, noobject, total
  * (each already the batch mean, lambda applied).  ious/object_mask [N,S,S,B]; dnet like net

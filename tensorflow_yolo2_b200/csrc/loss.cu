@@ -152,6 +152,26 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_v1_kernel(
     for (int e = tid; e < ncell * ch; e += LOSS_THREADS) dnet[(size_t)cell0 * ch + e] = s_net[e];
 }
 
+// a7 stand-alone: yolo2_nets/net_utils.py:222-260 get_iou on n box pairs (cx,cy,w,h), float32 with the
+// NumPy op order (explicitly rounded ops, no FMA contraction) -> bit-identical to the oracle.
+__global__ void iou_pairs_kernel(const float4* __restrict__ b1, const float4* __restrict__ b2, float* __restrict__ out,
+                                 size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = b1[i], b = b2[i];
+  float x1a = __fsub_rn(a.x, __fdiv_rn(a.z, 2.0f)), y1a = __fsub_rn(a.y, __fdiv_rn(a.w, 2.0f));
+  float x2a = __fadd_rn(a.x, __fdiv_rn(a.z, 2.0f)), y2a = __fadd_rn(a.y, __fdiv_rn(a.w, 2.0f));
+  float x1b = __fsub_rn(b.x, __fdiv_rn(b.z, 2.0f)), y1b = __fsub_rn(b.y, __fdiv_rn(b.w, 2.0f));
+  float x2b = __fadd_rn(b.x, __fdiv_rn(b.z, 2.0f)), y2b = __fadd_rn(b.y, __fdiv_rn(b.w, 2.0f));
+  float iw = fmaxf(0.0f, __fsub_rn(fminf(x2a, x2b), fmaxf(x1a, x1b)));
+  float ih = fmaxf(0.0f, __fsub_rn(fminf(y2a, y2b), fmaxf(y1a, y1b)));
+  float inter = __fmul_rn(iw, ih);
+  float sq1 = __fmul_rn(__fsub_rn(x2a, x1a), __fsub_rn(y2a, y1a));
+  float sq2 = __fmul_rn(__fsub_rn(x2b, x1b), __fsub_rn(y2b, y1b));
+  float uni = fmaxf(__fsub_rn(__fadd_rn(sq1, sq2), inter), 1e-10f);
+  out[i] = fminf(fmaxf(__fdiv_rn(inter, uni), 0.0f), 1.0f);
+}
+
 __global__ void loss_finalize_kernel(const double* __restrict__ partials, int nblocks, int N, float lambda_coord,
                                      float lambda_noobj, float* __restrict__ terms) {
   int q = threadIdx.x;
@@ -174,6 +194,15 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partials, int nb
 using namespace y2;
 
 extern "C" {
+
+int y2_iou(const float* boxes1, const float* boxes2, float* iou, size_t n, y2_stream_t stream) {
+  Y2_ARG(boxes1 && boxes2 && iou && n > 0);
+  Y2_ARG((((uintptr_t)boxes1) & 15) == 0 && (((uintptr_t)boxes2) & 15) == 0);
+  iou_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)boxes1, (const float4*)boxes2, iou, n);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
 
 size_t y2_loss_v1_workspace_bytes(int N, int S) {
   int ncell = N * S * S;

@@ -1,0 +1,204 @@
+"""Batch inference engine: Darknet19 + detection head -> decode -> per-class NMS, all buffers
+pre-allocated, weights pre-packed, inference-mode BN pre-folded, the whole step captured in one
+CUDA graph.  It issues exactly the kernels the eager builders in yolo2_nets/darknet.py issue (same
+C-ABI entry points); it exists because a 22-layer network at >10 k images/s is launch-bound from
+Python otherwise.
+
+The layer semantics follow the reference scripts (src/pascal/pascal_detect_darknet.py:41-43):
+core with is_training=False (moving statistics), head with is_training=True (batch statistics
+over the batch the engine is given) unless overridden.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .variables import VariableStore
+from .yolo2_nets.darknet import CORE_PLAN
+from .yolo2_nets.net_utils import VOC_ANCHORS
+
+HEAD_SCOPES = ('conv1', 'conv2', 'conv3', 'output')
+
+
+def create_variables(store, output_filter):
+    """Create (or find) every variable in the reference's creation order and naming."""
+    store.reset_name_counters()
+    layers = []
+    with store.scope('darknet19'):
+        for (k, cin, cout, pool) in CORE_PLAN:
+            wn, _ = store.weight_variable([k, k, cin, cout])
+            bn_, _ = store.bias_variable([cout])
+            layers.append(dict(k=k, cin=cin, cout=cout, pool=pool, W=wn, b=bn_, bn=store.batch_norm_variables(cout),
+                               head=False))
+    with store.scope('darknet19_detection'):
+        for sc, (k, cin, cout) in zip(HEAD_SCOPES, [(3, 1024, 1024)] * 3 + [(1, 1024, output_filter)]):
+            with store.scope(sc):
+                wn, _ = store.weight_variable([k, k, cin, cout])
+                bn_, _ = store.bias_variable([cout])
+                layers.append(dict(k=k, cin=cin, cout=cout, pool=False, W=wn, b=bn_,
+                                   bn=store.batch_norm_variables(cout), head=True))
+    return layers
+
+
+class Yolo2Engine:
+    def __init__(self, batch, image_size=416, output_filter=125, store=None, core_training=False, head_training=True,
+                 anchors=VOC_ANCHORS, num_class=20, score_thresh=0.3, iou_thresh=0.45, max_keep=None,
+                 input_kind='u8', decode='region', use_cuda_graph=True, device=None, seed=0):
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.N, self.IS, self.OF = int(batch), int(image_size), int(output_filter)
+        assert self.IS % 32 == 0
+        self.S = self.IS // 32
+        self.C = num_class
+        self.core_training, self.head_training = bool(core_training), bool(head_training)
+        self.score_thresh, self.iou_thresh = float(score_thresh), float(iou_thresh)
+        self.input_kind = input_kind
+        self.decode = decode
+        self.store = store if store is not None else VariableStore(seed=seed)
+        self.layers = create_variables(self.store, self.OF)
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            self._to_device()
+            # ---- buffers ----
+            N, IS = self.N, self.IS
+            self.in_u8 = torch.zeros((N, IS, IS, 3), dtype=torch.uint8, device=dev)
+            self.in_f32 = torch.zeros((N, IS, IS, 3), **f32) if input_kind == 'f32' else None
+            self.x0 = torch.empty((N, IS, IS, 8), dtype=torch.bfloat16, device=dev)
+            self.acts, self.raw, self.stats = [], {}, {}
+            H = IS
+            max_ws = 1
+            for li, L in enumerate(self.layers):
+                Ho = H // 2 if L['pool'] else H
+                training = self.head_training if L['head'] else self.core_training
+                last = li == len(self.layers) - 1
+                if last:
+                    self.acts.append(torch.empty((N, Ho, Ho, L['cout']), **f32))
+                else:
+                    self.acts.append(torch.empty((N, Ho, Ho, L['cout']), dtype=torch.bfloat16, device=dev))
+                if training or last:
+                    ld = (L['cout'] + 31) // 32 * 32
+                    self.raw[li] = torch.empty((N * H * H, ld), **f32)
+                if training:
+                    self.stats[li] = (torch.empty((L['cout'],), **f32), torch.empty((L['cout'],), **f32),
+                                      torch.empty((L['cout'],), **f32), torch.empty((L['cout'],), **f32),
+                                      torch.zeros((L['cout'],), **f32))
+                    max_ws = max(max_ws, ops.bn_stats_workspace_bytes(N * H * H, L['cout']))
+                H = Ho
+            self.ws = torch.empty((max_ws,), dtype=torch.uint8, device=dev)
+            if decode == 'region':
+                assert self.OF % (5 + self.C) == 0
+                self.A = self.OF // (5 + self.C)
+                self.anchors = torch.as_tensor(np.asarray(anchors, dtype=np.float32)[:self.A]).to(dev).contiguous()
+                self.nbox = self.S * self.S * self.A
+                self.max_keep = int(max_keep or self.nbox)
+                self.boxes = torch.empty((N, self.nbox, 4), **f32)
+                self.scores = torch.empty((N, self.nbox, self.C), **f32)
+                self.keep_idx = torch.full((N, self.C, self.max_keep), -1, dtype=torch.int32, device=dev)
+                self.keep_count = torch.zeros((N, self.C), dtype=torch.int32, device=dev)
+            self.refresh_weights()
+            self.graph = None
+            self.use_cuda_graph = use_cuda_graph
+
+    # ------------------------------------------------------------------------------------------
+    def _to_device(self):
+        for k, v in list(self.store.vars.items()):
+            if isinstance(v, np.ndarray):
+                self.store.vars[k] = torch.from_numpy(v).to(self.device)
+            elif v.device != self.device:
+                self.store.vars[k] = v.to(self.device)
+
+    def refresh_weights(self):
+        """(Re)pack weights and fold inference-mode BN; call after the store changes."""
+        st = self.store
+        self.packed, self.fold = [], {}
+        for li, L in enumerate(self.layers):
+            self.packed.append(ops.pack_weights_bf16(st[L['W']]))
+            training = self.head_training if L['head'] else self.core_training
+            if not training:
+                bn = L['bn']
+                self.fold[li] = ops.bn_fold(st[bn['gamma']], st[bn['beta']], st[bn['moving_mean']],
+                                            st[bn['moving_variance']], st[L['b']])
+        self.graph = None
+        self._version = st.version
+
+    # ------------------------------------------------------------------------------------------
+    def _enqueue(self):
+        st = self.store
+        if self.input_kind == 'u8':
+            ops.preprocess_u8(self.in_u8, bf16c8=True, out=self.x0)
+        else:
+            ops.pad_cast_f32_to_bf16c8(self.in_f32, out=self.x0)
+        x = self.x0
+        H = self.IS
+        nl = len(self.layers)
+        for li, L in enumerate(self.layers):
+            training = self.head_training if L['head'] else self.core_training
+            last = li == nl - 1
+            out = self.acts[li]
+            if not training:
+                scale, shift = self.fold[li]
+                if last:
+                    raw = self.raw[li]
+                    ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], scale=scale, shift=shift,
+                                      leaky=True, pool=False, out_f32=True, ldy=raw.shape[1], out=raw)
+                    ops.affine_leaky_pool(raw, self.N, H, H, L['cout'], ldx=raw.shape[1], leaky=False, pool=False,
+                                          out_bf16=False, out=out)     # compact the padded rows
+                else:
+                    ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], scale=scale, shift=shift,
+                                      leaky=True, pool=L['pool'], out=out)
+            else:
+                raw = self.raw[li]
+                mean, var, scale, shift, zeros = self.stats[li]
+                bn = L['bn']
+                ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], scale=None, shift=st[L['b']],
+                                  leaky=False, pool=False, out_f32=True, ldy=raw.shape[1], out=raw)
+                ops.bn_stats(raw, L['cout'], ld=raw.shape[1], workspace=self.ws, mean=mean, var=var)
+                ops.bn_fold(st[bn['gamma']], st[bn['beta']], zeros, var, None, scale=scale, shift=shift)
+                ops.affine_leaky_pool(raw, self.N, H, H, L['cout'], ldx=raw.shape[1], sub=mean, scale=scale, shift=shift,
+                                      leaky=True, pool=L['pool'], out_bf16=not last, out=out)
+            x = out
+            if L['pool']:
+                H //= 2
+        if self.decode == 'region':
+            ops.decode_region(self.acts[-1], self.anchors, self.C, self.score_thresh, boxes=self.boxes,
+                              scores=self.scores)
+            ops.nms(self.boxes, self.scores, self.score_thresh, self.iou_thresh, self.max_keep, keep_idx=self.keep_idx,
+                    keep_count=self.keep_count)
+
+    def run(self):
+        """Enqueue one step (input already in self.in_u8 / self.in_f32) on the current stream."""
+        if self._version != self.store.version:
+            self.refresh_weights()
+        if not self.use_cuda_graph:
+            self._enqueue()
+            return
+        if self.graph is None:
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue()            # warm-up: sets func attributes, primes caches
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize(self.device)
+            n0 = ops.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.launches_per_step = ops.launch_count() - n0
+            self.graph = g
+        self.graph.replay()
+
+    @property
+    def net_out(self):
+        return self.acts[-1]
+
+    def infer(self, images):
+        """images: uint8 [N,IS,IS,3] BGR (host or device) or float32 (input_kind='f32').
+        Returns dict(net, boxes, scores, keep_idx, keep_count) of device tensors."""
+        dst = self.in_u8 if self.input_kind == 'u8' else self.in_f32
+        dst.copy_(torch.as_tensor(images), non_blocking=True)
+        self.run()
+        out = dict(net=self.acts[-1])
+        if self.decode == 'region':
+            out.update(boxes=self.boxes, scores=self.scores, keep_idx=self.keep_idx, keep_count=self.keep_count)
+        return out

@@ -120,15 +120,21 @@ def _workspace(nbytes, device):
     return ws
 
 
-def bn_stats(x2d, C_, ld=None, workspace=None):
+def bn_stats_workspace_bytes(M, C_):
+    return int(_lib.load().y2_bn_stats_workspace_bytes(M, C_))
+
+
+def bn_stats(x2d, C_, ld=None, workspace=None, mean=None, var=None):
     """x2d f32 [M, ld]; returns (mean[C], biased var[C])."""
     M = x2d.shape[0]
     ld = ld or x2d.shape[1]
     lib = _lib.load()
     need = int(lib.y2_bn_stats_workspace_bytes(M, C_))
     ws = workspace if workspace is not None else _workspace(need, x2d.device)
-    mean = torch.empty((C_,), dtype=torch.float32, device=x2d.device)
-    var = torch.empty((C_,), dtype=torch.float32, device=x2d.device)
+    if mean is None:
+        mean = torch.empty((C_,), dtype=torch.float32, device=x2d.device)
+    if var is None:
+        var = torch.empty((C_,), dtype=torch.float32, device=x2d.device)
     check(lib.y2_bn_stats(_p(x2d, torch.float32), M, C_, ld, _p(mean), _p(var), _p(ws), ws.numel(), _stream()),
           'y2_bn_stats')
     return mean, var
@@ -209,6 +215,15 @@ def nms(boxes, scores, score_thresh=0.3, iou_thresh=0.45, max_keep=None, keep_id
 
 
 # ---- a6 / a7 -------------------------------------------------------------------------------
+def iou(boxes1, boxes2):
+    """[..., 4] x [..., 4] (cx,cy,w,h) f32 -> [...] IoU (net_utils.get_iou arithmetic)."""
+    assert boxes1.shape == boxes2.shape and boxes1.shape[-1] == 4
+    out = torch.empty(boxes1.shape[:-1], dtype=torch.float32, device=boxes1.device)
+    check(_lib.load().y2_iou(_p(boxes1, torch.float32), _p(boxes2, torch.float32), _p(out), out.numel(), _stream()),
+          'y2_iou')
+    return out
+
+
 def loss_v1(net, labels, S, B, C_, image_size, lambda_coord=5.0, lambda_noobj=0.5, want_grad=True):
     """Returns (terms[5] = class, coord, object, noobject, total; ious; object_mask; dnet)."""
     N = net.shape[0]
