@@ -217,6 +217,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(16) float s_scale[BLOCK_N];
+  __shared__ __align__(16) float s_shift[BLOCK_N];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem base rounded up to 1024 B (swizzle-128B atoms)
@@ -270,8 +272,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (a.a_mode == 0)
                 tma_load_im2col_4d(sA + g * (TILE_M * 16), &tmA, bar, 0, t.w0 - a.pad, t.h0 - a.pad, t.n0, (uint16_t)kw,
                                    (uint16_t)kh);
-              else
-                tma_load_4d(sA + g * (TILE_M * 16), &tmA, bar, 0, t.w0 + kw - a.pad, t.h0 + kh - a.pad, t.n0);
+              else   // tiled box over the merged (W*8 channels) inner dimension: 256-byte TMA rows, not 16-byte ones
+                tma_load_3d(sA + g * (TILE_M * 16), &tmA, bar, (t.w0 + kw - a.pad) * 8, t.h0 + kh - a.pad, t.n0);
             }
             tma_load_3d(sB, &tmB, bar, 0, nrow0, 0);
           } else {
@@ -321,26 +323,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =========================== epilogue (warps 2..5) ===========================
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                    // accumulator row = pixel slot within the tile
+    const int et = threadIdx.x - 64;                // 0..127 within the epilogue warps
     const bool pool = (a.flags & Y2_CONV_POOL2) != 0;
     const bool leaky_on = (a.flags & Y2_CONV_LEAKY) != 0;
     const bool out_f32 = (a.flags & Y2_CONV_OUT_F32) != 0;
     int it = 0;
+    int staged_ntile = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const TileCoord t = decode_tile(a, tile);
+      const int nbase = t.n_tile * BLOCK_N;
+      // ---- per-channel scale/shift of this n-tile -> smem (once per change of n-tile) ----
+      if (t.n_tile != staged_ntile) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone finished reading the old values
+        for (int c = et; c < BLOCK_N; c += 128) {
+          const int col = nbase + c;
+          float sc = 1.0f, sh = 0.0f;
+          if (col < a.Cout) {
+            if (a.scale) sc = __ldg(a.scale + col);
+            if (a.shift) sh = __ldg(a.shift + col);
+          }
+          s_scale[c] = sc;
+          s_shift[c] = sh;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        staged_ntile = t.n_tile;
+      }
       // ---- where does my row go? ----
       bool valid;
       long long orow;     // output pixel row index
-      int tw = 0, th = 0;
       if (a.a_mode == 0) {
         long long m = t.m0 + r;
         valid = m < a.M;
         orow = m;
       } else {
-        tw = r & ((1 << a.tw_log2) - 1);
-        th = (r >> a.tw_log2) & ((1 << a.th_log2) - 1);
-        int nb = r >> (a.tw_log2 + a.th_log2);
-        int n = t.n0 + nb, h = t.h0 + th, w = t.w0 + tw;
+        const int tw = r & ((1 << a.tw_log2) - 1);
+        const int th = (r >> a.tw_log2) & ((1 << a.th_log2) - 1);
+        const int nb = r >> (a.tw_log2 + a.th_log2);
+        const int n = t.n0 + nb, h = t.h0 + th, w = t.w0 + tw;
         valid = n < a.N && h < a.H && w < a.W;
         if (pool) {
           valid = valid && ((tw | th) & 1) == 0;
@@ -352,7 +372,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full_bar[buf], ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N);
-      const int nbase = t.n_tile * BLOCK_N;
 #pragma unroll 1
       for (int cc = 0; cc < BLOCK_N; cc += 32) {
         uint32_t v[32];
@@ -368,53 +387,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (c0 < a.ldy) {                           // (warp-uniform) chunk has columns that are stored
           float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            int c = c0 + i;
-            float sc = 1.0f, sh = 0.0f;
-            if (c < a.Cout) {
-              if (a.scale) sc = __ldg(a.scale + c);
-              if (a.shift) sh = __ldg(a.shift + c);
-            }
-            float x = fmaf(__uint_as_float(v[i]), sc, sh);
-            if (leaky_on) x = fmaxf(x, a.alpha * x);
-            f[i] = x;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(&s_scale[cc + i]);   // smem broadcast
+            const float4 sh = *reinterpret_cast<const float4*>(&s_shift[cc + i]);
+            f[i + 0] = fmaf(__uint_as_float(v[i + 0]), sc.x, sh.x);
+            f[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
+            f[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z);
+            f[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc.w, sh.w);
           }
-          if (pool) {
+          if (leaky_on) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
-              f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1 << a.tw_log2));
-            }
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], a.alpha * f[i]);
           }
           const int ncols = min(32, a.ldy - c0);    // columns of this chunk that exist in the output row
-          if (valid) {
-            if (out_f32) {
+          if (out_f32) {
+            if (pool) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
+                f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1 << a.tw_log2));
+              }
+            }
+            if (valid) {
               float* dst = reinterpret_cast<float*>(a.y) + (size_t)orow * a.ldy + c0;
               if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
                   *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
               } else {
-                for (int i = 0; i < ncols; ++i) dst[i] = f[i];
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols) dst[i] = f[i];
               }
-            } else {
+            }
+          } else {
+            // pack to bf16x2 first: rounding is monotonic, so max(round(a),round(b)) == round(max(a,b))
+            // and the 2x2 max-pool can run on packed pairs with half the shuffles
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            if (pool) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                uint32_t o = __shfl_xor_sync(0xffffffffu, pk[i], 1);
+                __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[i]), *reinterpret_cast<__nv_bfloat162*>(&o));
+                pk[i] = *reinterpret_cast<uint32_t*>(&m);
+                o = __shfl_xor_sync(0xffffffffu, pk[i], 1 << a.tw_log2);
+                m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[i]), *reinterpret_cast<__nv_bfloat162*>(&o));
+                pk[i] = *reinterpret_cast<uint32_t*>(&m);
+              }
+            }
+            if (valid) {
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)orow * a.ldy + c0;
               if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  uint4 pk;
-                  __nv_bfloat162 p0 = __floats2bfloat162_rn(f[i + 0], f[i + 1]);
-                  __nv_bfloat162 p1 = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-                  __nv_bfloat162 p2 = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
-                  __nv_bfloat162 p3 = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
-                  pk.x = *reinterpret_cast<uint32_t*>(&p0);
-                  pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                  pk.z = *reinterpret_cast<uint32_t*>(&p2);
-                  pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                  *reinterpret_cast<uint4*>(dst + i) = pk;
-                }
+                for (int i = 0; i < 4; ++i)
+                  reinterpret_cast<uint4*>(dst)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
               } else {
-                for (int i = 0; i < ncols; ++i) dst[i] = __float2bfloat16_rn(f[i]);
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols)
+                    reinterpret_cast<uint16_t*>(dst)[i] = (uint16_t)((i & 1) ? (pk[i >> 1] >> 16) : (pk[i >> 1] & 0xffffu));
               }
             }
           }
@@ -559,8 +595,6 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
     set_error("y2_conv_fwd_bf16: Cin=%d unsupported (need 3, or a multiple of 32)", p->Cin);
     return Y2_ERR_UNSUPPORTED;
   }
-  int block_n = cout_p >= 128 ? 128 : (cout_p > 32 ? 64 : 32);
-  a.n_tiles = (cout_p + block_n - 1) / block_n;
   a.a_mode = pool ? 1 : 0;
   if (getenv("Y2_CONV_FORCE_TILED")) a.a_mode = 1;
   int TW = 1, TH = 1, NB = 128;
@@ -572,6 +606,22 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   } else {
     a.m_tiles = (int)((a.M + TILE_M - 1) / TILE_M);
   }
+  // N tile: the kernel is L2-bandwidth bound at 128x128 tiles (64 flop per L2 byte), so take 256 columns
+  // when that does not cost more in wave quantisation than it saves in operand traffic.
+  int block_n = cout_p >= 128 ? 128 : (cout_p > 32 ? 64 : 32);
+  if (cout_p >= 256 && !a.first_layer) {
+    auto cost = [&](int bn) {
+      long long tiles = (long long)a.m_tiles * ((cout_p + bn - 1) / bn);
+      long long rounds = (tiles + g_num_sms - 1) / g_num_sms;
+      return rounds * (16 + bn / 8);
+    };
+    if (cost(256) <= cost(128)) block_n = 256;
+  }
+  if (const char* e = getenv("Y2_CONV_BLOCK_N")) {
+    int v = atoi(e);
+    if ((v == 128 || v == 256) && cout_p >= v) block_n = v;
+  }
+  a.n_tiles = (cout_p + block_n - 1) / block_n;
   if (a.first_layer) {
     a.a_stage_bytes = 10 * TILE_M * 16;
     a.b_stage_bytes = 10 * block_n * 16;
@@ -610,6 +660,16 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
       // same small-tensor fix-up CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp) for drivers <= 13.1
       if (r == CUDA_SUCCESS && g_driver_version <= 13010 && (size_t)a.M * a.cin_p * 2 < 131072)
         reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
+    } else if (a.first_layer) {
+      // Cin_p == 8: pixels are 16 B, so (channel, w) is one contiguous dimension of W*8 elements.
+      // A [TW*8, TH, NB] box then moves 256-byte rows instead of 16-byte ones (16x fewer TMA requests);
+      // the left/right halo is still zero-filled because the shift is a multiple of one pixel.
+      cuuint64_t dims3[3] = {(cuuint64_t)p->W * 8, (cuuint64_t)p->H, (cuuint64_t)p->N};
+      cuuint64_t strides3[2] = {(cuuint64_t)p->W * 16, (cuuint64_t)p->H * p->W * 16};
+      cuuint32_t box3[3] = {(cuuint32_t)TW * 8, (cuuint32_t)TH, (cuuint32_t)NB};
+      r = g_encodeTiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->x), dims3, strides3, box3, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
       cuuint32_t box[4] = {(cuuint32_t)a.kchunk, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB};
       r = g_encodeTiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), dims, strides, box, estr,
@@ -651,6 +711,7 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   switch (block_n) {
     case 32: return launch_conv<32>(tmA, tmB, a, smem, st);
     case 64: return launch_conv<64>(tmA, tmB, a, smem, st);
+    case 256: return launch_conv<256>(tmA, tmB, a, smem, st);
     default: return launch_conv<128>(tmA, tmB, a, smem, st);
   }
 }
