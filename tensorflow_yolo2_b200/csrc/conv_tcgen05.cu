@@ -52,7 +52,7 @@ struct ConvArgs {
   int kblocks;            // pipeline stages per tile: taps * cin_p/kchunk   (first layer: 1)
   int cchunks;            // cin_p / kchunk
   int ksteps;             // MMAs per stage (K=16 each)
-  int a_mode;             // 0 im2col, 1 tiled box
+  int a_mode;             // 0 im2col, 1 tiled box, 2 halo patch (8x16 px tile, vertical tap reuse in smem)
   int tw_log2, th_log2, nb_log2;
   int tiles_w, tiles_h, tiles_nb;
   int m_tiles, n_tiles;
@@ -60,7 +60,23 @@ struct ConvArgs {
   uint32_t a_stage_bytes, b_stage_bytes;
   uint32_t a_sbo, a_lbo, b_sbo, b_lbo, layout_type, kstep_bytes;   // UMMA smem-descriptor fields (bytes)
   int first_layer;        // Cin_p == 8 special case (all taps in one stage, no swizzle)
+  int b_stationary;       // whole B operand resident in smem for the CTA's lifetime (n_tiles == 1, small B)
+  uint32_t b_total_bytes;
+  int sps;                // (tap, channel-chunk) sub-blocks per pipeline stage
+  int stages_per_tile;    // kblocks / sps
+  uint32_t a_sub_bytes, b_sub_bytes;
+  uint32_t tx_bytes;      // A bytes the TMA reports per stage
+  // magic-number division (single-thread roles must not spend their time in integer division)
+  uint32_t fd_ntiles_mul, fd_ntiles_shr;
+  uint32_t fd_w_mul, fd_w_shr;            // a_mode 0: W         a_mode 1: tiles_w
+  uint32_t fd_h_mul, fd_h_shr;            // a_mode 0: H         a_mode 1: tiles_h
+  uint32_t fd_cch_mul, fd_cch_shr;        // cchunks
 };
+
+// q = n / d for 0 <= n < 2^31 with host-computed (mul, shr); d == 1 encoded as mul == 0
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, uint32_t mul, uint32_t shr) {
+  return mul ? (__umulhi(n, mul) >> shr) : n;
+}
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -183,20 +199,24 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
   TileCoord t;
-  t.n_tile = tile % a.n_tiles;
-  int mt = tile / a.n_tiles;
+  const uint32_t mt = fdiv((uint32_t)tile, a.fd_ntiles_mul, a.fd_ntiles_shr);
+  t.n_tile = tile - (int)mt * a.n_tiles;
   if (a.a_mode == 0) {
-    t.m0 = (long long)mt * TILE_M;
-    t.w0 = (int)(t.m0 % a.W);
-    t.h0 = (int)((t.m0 / a.W) % a.H);
-    t.n0 = (int)(t.m0 / ((long long)a.W * a.H));
+    t.m0 = (long long)mt * TILE_M;                       // < 2^31 (checked on the host)
+    const uint32_t m = (uint32_t)t.m0;
+    const uint32_t row = fdiv(m, a.fd_w_mul, a.fd_w_shr);         // n*H + h
+    t.w0 = (int)(m - row * (uint32_t)a.W);
+    const uint32_t img = fdiv(row, a.fd_h_mul, a.fd_h_shr);
+    t.h0 = (int)(row - img * (uint32_t)a.H);
+    t.n0 = (int)img;
   } else {
-    int tw_i = mt % a.tiles_w;
-    int th_i = (mt / a.tiles_w) % a.tiles_h;
-    int tn_i = mt / (a.tiles_w * a.tiles_h);
-    t.w0 = tw_i << a.tw_log2;
-    t.h0 = th_i << a.th_log2;
-    t.n0 = tn_i << a.nb_log2;
+    const uint32_t q = fdiv(mt, a.fd_w_mul, a.fd_w_shr);          // / tiles_w
+    const uint32_t tw_i = mt - q * (uint32_t)a.tiles_w;
+    const uint32_t tn_i = fdiv(q, a.fd_h_mul, a.fd_h_shr);        // / tiles_h
+    const uint32_t th_i = q - tn_i * (uint32_t)a.tiles_h;
+    t.w0 = (int)(tw_i << a.tw_log2);
+    t.h0 = (int)(th_i << a.th_log2);
+    t.n0 = (int)(tn_i << a.nb_log2);
     t.m0 = 0;
   }
   return t;
@@ -216,14 +236,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t bfull_bar;
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_scale[BLOCK_N];
   __shared__ __align__(16) float s_shift[BLOCK_N];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem base rounded up to 1024 B (swizzle-128B atoms)
-  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = a.a_stage_bytes + a.b_stage_bytes;
+  // [stationary B (optional)] [stage 0: A | B] [stage 1: A | B] ...
+  const uint32_t smem_b_stat = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t smem_base = smem_b_stat + (a.b_stationary ? ((a.b_total_bytes + 1023u) & ~1023u) : 0u);
+  const uint32_t stage_bytes = a.a_stage_bytes + (a.b_stationary ? 0u : a.b_stage_bytes);
+  const uint32_t tx_bytes = a.tx_bytes + (a.b_stationary ? 0u : a.b_stage_bytes);
   const int total_tiles = a.m_tiles * a.n_tiles;
 
   if (warp == 0 && lane == 0) {
@@ -237,6 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 4);
     }
+    mbar_init(&bfull_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -252,42 +277,89 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(a, tile);
-        const int nrow0 = t.n_tile * BLOCK_N;
-        for (int kb = 0; kb < a.kblocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          const uint32_t sA = smem_base + stage * stage_bytes;
-          const uint32_t sB = sA + a.a_stage_bytes;
-          const uint32_t bar = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
-          if (a.first_layer) {
-            // all 9 taps (+ tap 0 again against zero weights) of 8 padded channels: 10 x [128 px][16 B]
-            for (int g = 0; g < 10; ++g) {
-              int tap = g < 9 ? g : 0;
-              int kh = tap / 3, kw = tap - kh * 3;
-              if (a.a_mode == 0)
-                tma_load_im2col_4d(sA + g * (TILE_M * 16), &tmA, bar, 0, t.w0 - a.pad, t.h0 - a.pad, t.n0, (uint16_t)kw,
-                                   (uint16_t)kh);
-              else   // tiled box over the merged (W*8 channels) inner dimension: 256-byte TMA rows, not 16-byte ones
-                tma_load_3d(sA + g * (TILE_M * 16), &tmA, bar, (t.w0 + kw - a.pad) * 8, t.h0 + kh - a.pad, t.n0);
-            }
-            tma_load_3d(sB, &tmB, bar, 0, nrow0, 0);
-          } else {
-            const int tap = kb / a.cchunks;
-            const int c0 = (kb - tap * a.cchunks) * a.kchunk;
-            const int kh = tap / a.ksize, kw = tap - kh * a.ksize;
-            if (a.a_mode == 0)
-              tma_load_im2col_4d(sA, &tmA, bar, c0, t.w0 - a.pad, t.h0 - a.pad, t.n0, (uint16_t)kw, (uint16_t)kh);
-            else
-              tma_load_4d(sA, &tmA, bar, c0, t.w0 + kw - a.pad, t.h0 + kh - a.pad, t.n0);
-            tma_load_2d(sB, &tmB, bar, tap * a.cin_p + c0, nrow0);
-          }
-          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+    // The whole warp runs the loop; lane 0 owns the barrier handshake, and the stage's TMA loads are
+    // issued by different lanes in the same instruction slot: lanes [0, sps) one A sub-block each,
+    // lanes [sps, 2*sps) one B sub-block each (first layer: 10 A taps + one B load).
+    int stage = 0;
+    uint32_t phase = 0;
+    const int sps = a.sps;
+    if (a.b_stationary) {
+      // weights of this layer fit in smem: fetch them once per CTA instead of once per tile
+      if (lane == 0) mbar_expect_tx(&bfull_bar, a.b_total_bytes);
+      __syncwarp();
+      const uint32_t bar = smem_u32(&bfull_bar);
+      if (a.first_layer) {
+        if (lane == 0) tma_load_3d(smem_b_stat, &tmB, bar, 0, 0, 0);
+      } else {
+        for (int sub = lane; sub < a.kblocks; sub += 32) {
+          const uint32_t tap = fdiv((uint32_t)sub, a.fd_cch_mul, a.fd_cch_shr);
+          const int c0 = (int)((uint32_t)sub - tap * (uint32_t)a.cchunks) * a.kchunk;
+          tma_load_2d(smem_b_stat + sub * a.b_sub_bytes, &tmB, bar, (int)tap * a.cin_p + c0, 0);
         }
+      }
+      __syncwarp();
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(a, tile);
+      const int nrow0 = t.n_tile * BLOCK_N;
+      for (int st = 0; st < a.stages_per_tile; ++st) {
+        if (lane == 0) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+        }
+        __syncwarp();
+        const uint32_t sA = smem_base + stage * stage_bytes;
+        const uint32_t sB = sA + a.a_stage_bytes;
+        const uint32_t bar = smem_u32(&full_bar[stage]);
+        if (a.a_mode == 2) {
+          // halo patch: ONE load of the (16+2) x (8[+2]) pixel neighbourhood serves 3 (or, first layer, all 9)
+          // filter taps; the taps become shifted UMMA descriptors over the same smem bytes.
+          if (a.first_layer) {
+            if (lane == 0) tma_load_3d(sA, &tmA, bar, (t.w0 - 1) * 8, t.h0 - 1, t.n0);     // 18 rows x 10 px x 16 B
+            else if (lane == 1 && !a.b_stationary) tma_load_3d(sB, &tmB, bar, 0, nrow0, 0);
+          } else {
+            const uint32_t cc = fdiv((uint32_t)st, 0xAAAAAAABu, 1);                        // st / 3
+            const int kw = st - (int)cc * 3;
+            const int c0 = (int)cc * a.kchunk;
+            if (lane == 0) {
+              tma_load_4d(sA, &tmA, bar, c0, t.w0 + kw - 1, t.h0 - 1, t.n0);               // 18 rows x 8 px x kchunk
+            } else if (lane < 4 && !a.b_stationary) {
+              const int kh = lane - 1;
+              tma_load_2d(sB + kh * a.b_sub_bytes, &tmB, bar, (kh * 3 + kw) * a.cin_p + c0, nrow0);
+            }
+          }
+        } else if (a.first_layer) {
+          // 9 taps (+ one group that meets zero weights) of 8 padded channels: 10 x [128 px][16 B]
+          if (lane < 10) {
+            const int tap = lane < 8 ? lane : (lane == 8 ? 0 : 8);      // k-groups: taps 0..7, zero weights, tap 8
+            const int kh = (tap * 11) >> 5, kw = tap - kh * 3;          // tap / 3 for tap < 9
+            if (a.a_mode == 0)
+              tma_load_im2col_4d(sA + lane * (TILE_M * 16), &tmA, bar, 0, t.w0 - a.pad, t.h0 - a.pad, t.n0, (uint16_t)kw,
+                                 (uint16_t)kh);
+            else   // tiled box over the merged (W*8 channels) inner dimension: 256-byte TMA rows, not 16-byte ones
+              tma_load_3d(sA + lane * (TILE_M * 16), &tmA, bar, (t.w0 + kw - a.pad) * 8, t.h0 + kh - a.pad, t.n0);
+          } else if (lane == 10 && !a.b_stationary) {
+            tma_load_3d(sB, &tmB, bar, 0, nrow0, 0);
+          }
+        } else if (lane < 2 * sps) {
+          const int j = lane < sps ? lane : lane - sps;
+          const uint32_t sub = (uint32_t)(st * sps + j);
+          const uint32_t tap = fdiv(sub, a.fd_cch_mul, a.fd_cch_shr);
+          const int c0 = (int)(sub - tap * (uint32_t)a.cchunks) * a.kchunk;
+          const int kh = a.ksize == 3 ? (int)((tap * 11) >> 5) : 0;
+          const int kw = (int)tap - kh * a.ksize;
+          if (lane < sps) {
+            if (a.a_mode == 0)
+              tma_load_im2col_4d(sA + j * a.a_sub_bytes, &tmA, bar, c0, t.w0 - a.pad, t.h0 - a.pad, t.n0, (uint16_t)kw,
+                                 (uint16_t)kh);
+            else
+              tma_load_4d(sA + j * a.a_sub_bytes, &tmA, bar, c0, t.w0 + kw - a.pad, t.h0 + kh - a.pad, t.n0);
+          } else if (!a.b_stationary) {
+            tma_load_2d(sB + j * a.b_sub_bytes, &tmB, bar, (int)tap * a.cin_p + c0, nrow0);
+          }
+        }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -295,6 +367,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      // descriptors differ only in the 14-bit start-address field: build once, then add (bytes >> 4)
+      const uint64_t adesc0 = make_smem_desc(smem_base, a.a_lbo, a.a_sbo, a.layout_type);
+      const uint64_t bdesc0 = make_smem_desc(a.b_stationary ? smem_b_stat : smem_base + a.a_stage_bytes, a.b_lbo, a.b_sbo,
+                                             a.layout_type);
+      if (a.b_stationary) {
+        mbar_wait(&bfull_bar, 0);
+        tc_fence_after();
+      }
+      const uint32_t a_kstep = (a.kstep_bytes * (a.first_layer ? TILE_M : 1)) >> 4;
+      const uint32_t b_kstep = (a.kstep_bytes * (a.first_layer ? BLOCK_N : 1)) >> 4;
+      const int subs = a.first_layer ? 1 : a.sps;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -303,15 +386,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tmem_empty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BLOCK_N);
-        for (int kb = 0; kb < a.kblocks; ++kb) {
+        uint32_t accum = 0;
+        for (int st = 0; st < a.stages_per_tile; ++st) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_base + stage * stage_bytes;
-          const uint32_t sB = sA + a.a_stage_bytes;
-          for (int ks = 0; ks < a.ksteps; ++ks) {
-            const uint64_t ad = make_smem_desc(sA + ks * a.kstep_bytes * (a.first_layer ? TILE_M : 1), a.a_lbo, a.a_sbo, a.layout_type);
-            const uint64_t bd = make_smem_desc(sB + ks * a.kstep_bytes * (a.first_layer ? BLOCK_N : 1), a.b_lbo, a.b_sbo, a.layout_type);
-            umma_bf16(tmem_d, ad, bd, idesc, (kb | ks) != 0 ? 1u : 0u);
+          const uint32_t soff = (uint32_t)(stage * stage_bytes) >> 4;
+          if (a.a_mode == 2 && a.first_layer) {
+            // patch [18][10 px][8 ch]: pixel = 16 B, 8 consecutive pixels = one un-swizzled core matrix.
+            // MMA p multiplies k-groups (2p, 2p+1): A start = first tap's pixel shift, LBO = distance to the
+            // second tap, SBO = one patch row (10 px).  k-groups are taps 0..7, a zero-weight group, tap 8;
+            // the zero-weight group re-reads tap 7's (finite) pixels so that 0 * x stays 0.
+            const uint32_t sA = smem_base + stage * stage_bytes;
+#pragma unroll
+            for (int pr = 0; pr < 5; ++pr) {
+              const int t0 = pr < 4 ? 2 * pr : 7, t1 = pr < 4 ? 2 * pr + 1 : 8;
+              const int o0 = ((t0 / 3) * 10 + (t0 % 3)) * 16, o1 = ((t1 / 3) * 10 + (t1 % 3)) * 16;
+              const uint32_t lbo = (uint32_t)(o1 - o0);
+              const uint64_t ad = make_smem_desc(sA + o0, lbo, 160u, 0u);
+              const uint64_t bd = (a.b_stationary ? bdesc0 : bdesc0 + soff) + (uint32_t)pr * b_kstep;
+              umma_bf16(tmem_d, ad, bd, idesc, accum);
+              accum = 1;
+            }
+          } else if (a.a_mode == 2) {
+            const uint32_t cc = fdiv((uint32_t)st, 0xAAAAAAABu, 1);
+            const int kw = st - (int)cc * 3;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              // rows of tap (kh, kw) = patch rows shifted down by kh: + kh * 8 px * row_bytes (a whole swizzle atom)
+              uint64_t ad = adesc0 + soff + ((uint32_t)(kh * 8 * a.row_bytes) >> 4);
+              uint64_t bd = a.b_stationary
+                                ? bdesc0 + ((uint32_t)(((kh * 3 + kw) * a.cchunks + (int)cc) * a.b_sub_bytes) >> 4)
+                                : bdesc0 + soff + ((uint32_t)(kh * a.b_sub_bytes) >> 4);
+              for (int ks = 0; ks < a.ksteps; ++ks) {
+                umma_bf16(tmem_d, ad, bd, idesc, accum);
+                accum = 1;
+                ad += a_kstep;
+                bd += b_kstep;
+              }
+            }
+          } else
+          for (int j = 0; j < subs; ++j) {
+            uint64_t ad = adesc0 + soff + ((uint32_t)(j * a.a_sub_bytes) >> 4);
+            uint64_t bd = a.b_stationary ? bdesc0 + ((uint32_t)((st * subs + j) * a.b_sub_bytes) >> 4)
+                                         : bdesc0 + soff + ((uint32_t)(j * a.b_sub_bytes) >> 4);
+            for (int ks = 0; ks < a.ksteps; ++ks) {
+              umma_bf16(tmem_d, ad, bd, idesc, accum);
+              accum = 1;
+              ad += a_kstep;
+              bd += b_kstep;
+            }
           }
           umma_commit(&empty_bar[stage]);           // frees the smem stage when these MMAs retire
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
@@ -516,6 +639,15 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
                                                                           : CU_TENSOR_MAP_SWIZZLE_NONE;
 }
 
+static void fastdiv_init(uint32_t d, uint32_t* mul, uint32_t* shr) {
+  if (d <= 1) { *mul = 0; *shr = 0; return; }
+  uint32_t l = 0;
+  while ((1u << l) < d) ++l;                       // ceil(log2 d)
+  uint32_t p = 31 + l;
+  *mul = (uint32_t)(((1ull << p) + d - 1) / d);
+  *shr = p - 32;
+}
+
 static int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -597,8 +729,17 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   }
   a.a_mode = pool ? 1 : 0;
   if (getenv("Y2_CONV_FORCE_TILED")) a.a_mode = 1;
+  // halo-patch mode for 3x3 layers on large maps: an 8 x 16 pixel tile whose (16+2)-row neighbourhood is
+  // loaded once per horizontal tap (first layer: once in total) instead of once per tap
+  if (p->ksize == 3 && p->H >= 64 && p->W >= 64 && !getenv("Y2_CONV_NO_PATCH")) a.a_mode = 2;
+  if (getenv("Y2_CONV_FORCE_PATCH") && p->ksize == 3) a.a_mode = 2;
   int TW = 1, TH = 1, NB = 128;
-  if (a.a_mode == 1) {
+  if (a.a_mode == 2) {
+    TW = 8; TH = 16; NB = 1;
+    a.tw_log2 = 3; a.th_log2 = 4; a.nb_log2 = 0;
+    a.tiles_w = (p->W + TW - 1) / TW; a.tiles_h = (p->H + TH - 1) / TH; a.tiles_nb = p->N;
+    a.m_tiles = a.tiles_w * a.tiles_h * a.tiles_nb;
+  } else if (a.a_mode == 1) {
     choose_box(p->N, p->H, p->W, pool, &TW, &TH, &NB);
     a.tw_log2 = ilog2(TW); a.th_log2 = ilog2(TH); a.nb_log2 = ilog2(NB);
     a.tiles_w = (p->W + TW - 1) / TW; a.tiles_h = (p->H + TH - 1) / TH; a.tiles_nb = (p->N + NB - 1) / NB;
@@ -633,15 +774,51 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
     a.a_sbo = 8 * a.row_bytes; a.b_sbo = 8 * a.row_bytes;
     a.a_lbo = 16; a.b_lbo = 16;           // ignored for swizzled K-major layouts (CUTLASS writes 1)
   }
+  // several (tap, chunk) sub-blocks per stage when they are small (Cin = 32: 12 KB), so that the barrier
+  // round trip is amortised over more MMAs
+  a.sps = 1;
+  if (!a.first_layer && a.a_mode != 2 && a.row_bytes == 64 && a.kblocks % 3 == 0) a.sps = 3;
+  a.a_sub_bytes = a.a_stage_bytes;
+  a.b_sub_bytes = a.b_stage_bytes;
+  if (a.a_mode == 2) {
+    if (a.first_layer) {
+      a.a_stage_bytes = 3072;                            // 18 x 10 px x 16 B = 2880, padded
+      a.a_sub_bytes = 2880;                              // bytes the TMA actually delivers
+      a.stages_per_tile = 1;
+    } else {
+      a.a_stage_bytes = 18 * 8 * a.row_bytes;            // one horizontally shifted patch
+      a.a_sub_bytes = a.a_stage_bytes;
+      a.b_stage_bytes = 3 * a.b_sub_bytes;               // the three taps (kh = 0..2) of this kw
+      a.stages_per_tile = a.cchunks * 3;
+    }
+  } else {
+    if (!a.first_layer) {
+      a.a_stage_bytes *= a.sps;
+      a.b_stage_bytes *= a.sps;
+    }
+    a.stages_per_tile = a.kblocks / a.sps;
+  }
+  Y2_ARG(a.M + TILE_M < (1ll << 31));
+  fastdiv_init((uint32_t)a.n_tiles, &a.fd_ntiles_mul, &a.fd_ntiles_shr);
+  fastdiv_init((uint32_t)(a.a_mode == 0 ? p->W : a.tiles_w), &a.fd_w_mul, &a.fd_w_shr);
+  fastdiv_init((uint32_t)(a.a_mode == 0 ? p->H : a.tiles_h), &a.fd_h_mul, &a.fd_h_shr);
+  // bytes per pipeline stage that the TMA unit will report on the stage's mbarrier
+  a.tx_bytes = (a.a_mode == 2 && a.first_layer ? a.a_sub_bytes : a.a_stage_bytes);
+  fastdiv_init((uint32_t)a.cchunks, &a.fd_cch_mul, &a.fd_cch_shr);
+  // B-stationary: with a single N tile and a small filter bank, every tile of the CTA needs the same B
+  a.b_total_bytes = a.first_layer ? a.b_sub_bytes : (uint32_t)a.kblocks * a.b_sub_bytes;
+  const size_t SMEM_BUDGET = 220 * 1024;           // dynamic smem for operands (static smem + slack stay below 227 KB)
+  a.b_stationary = (a.n_tiles == 1 && a.b_total_bytes + 4 * (size_t)a.a_stage_bytes <= SMEM_BUDGET &&
+                    !getenv("Y2_CONV_NO_BSTAT")) ? 1 : 0;
   // stages: B-stage must stay 1024-byte aligned for the 128B swizzle atoms
-  uint32_t stage_bytes = a.a_stage_bytes + a.b_stage_bytes;
+  uint32_t stage_bytes = a.a_stage_bytes + (a.b_stationary ? 0u : a.b_stage_bytes);
   Y2_ARG(a.first_layer || (a.a_stage_bytes % 1024 == 0 && a.b_stage_bytes % 1024 == 0));
-  int stages = (int)((196 * 1024) / stage_bytes);
+  const size_t b_region = a.b_stationary ? (((size_t)a.b_total_bytes + 1023) & ~(size_t)1023) : 0;
+  int stages = (int)((SMEM_BUDGET - b_region) / stage_bytes);
   if (stages > 12) stages = 12;
-  if (stages > a.kblocks * 4) stages = a.kblocks * 4 > 2 ? a.kblocks * 4 : 2;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  size_t smem = (size_t)stages * stage_bytes + 1024;
+  size_t smem = b_region + (size_t)stages * stage_bytes + 1024;
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB;
@@ -660,6 +837,19 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
       // same small-tensor fix-up CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp) for drivers <= 13.1
       if (r == CUDA_SUCCESS && g_driver_version <= 13010 && (size_t)a.M * a.cin_p * 2 < 131072)
         reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
+    } else if (a.a_mode == 2 && a.first_layer) {
+      // halo patch of the first layer: (8+2) px x 8 ch = 80 contiguous elements per row, 18 rows
+      cuuint64_t dims3[3] = {(cuuint64_t)p->W * 8, (cuuint64_t)p->H, (cuuint64_t)p->N};
+      cuuint64_t strides3[2] = {(cuuint64_t)p->W * 16, (cuuint64_t)p->H * p->W * 16};
+      cuuint32_t box3[3] = {80, 18, 1};
+      r = g_encodeTiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->x), dims3, strides3, box3, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (a.a_mode == 2) {
+      cuuint32_t box[4] = {(cuuint32_t)a.kchunk, 8, 18, 1};
+      r = g_encodeTiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else if (a.first_layer) {
       // Cin_p == 8: pixels are 16 B, so (channel, w) is one contiguous dimension of W*8 elements.
       // A [TW*8, TH, NB] box then moves 256-byte rows instead of 16-byte ones (16x fewer TMA requests);

@@ -57,7 +57,7 @@ __global__ void pad_cast_f32_bf16c8_kernel(const float* __restrict__ x, uint4* _
 // ---------------------------------------------------------------------------------------------
 // weight packing: TF HWIO [k,k,Cin,Cout] f32  ->  [Cout_p][Kp] bf16, K index = tap*Cin_p + c
 // (K-major rows, the B operand of the implicit GEMM).  Padding rows/columns are zero.
-// First layer (Cin 3 -> 8): [10 k-groups][Cout_p][8] instead, k-group 9 all zero.
+// First layer (Cin 3 -> 8): [10 k-groups][Cout_p][8] instead: taps 0..7, a zero group, tap 8.
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps, int Cin,
                                     int Cout, int Cin_p, int Cout_p, int Kp) {
@@ -67,11 +67,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   for (; i < total; i += stride) {
     int n = (int)(i / Kp);
     int kk = (int)(i % Kp);
-    int tap = kk / Cin_p, c = kk % Cin_p;
+    int grp = kk / Cin_p, c = kk % Cin_p;
+    // first layer (Cin_p == 8): k-groups are taps 0..7, one all-zero group, then tap 8 (conv_tcgen05.cu pairs the
+    // zero group with tap 8 in the last K=16 MMA)
+    int tap = (Cin_p == 8) ? (grp < 8 ? grp : (grp == 9 ? 8 : taps)) : grp;
     float v = 0.0f;
     if (n < Cout && tap < taps && c < Cin) v = w[((size_t)tap * Cin + c) * Cout + n];
-    // first layer (Cin_p == 8): smem-ready order [k-group = tap][Cout_p][8] (un-swizzled core matrices)
-    size_t o = (Cin_p == 8) ? ((size_t)tap * Cout_p + n) * 8 + c : i;
+    // first layer: smem-ready order [k-group][Cout_p][8] (un-swizzled core matrices)
+    size_t o = (Cin_p == 8) ? ((size_t)grp * Cout_p + n) * 8 + c : i;
     out[o] = __float2bfloat16_rn(v);
   }
 }

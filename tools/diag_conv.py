@@ -32,6 +32,13 @@ CASES = {
     'i1x1_1024_125_f32': (4, 13, 13, 1024, 125, 1, False, True, False),
     'i1x1_1024_30_f32': (4, 7, 7, 1024, 30, 1, False, True, False),
     'i3x3_1024_1024_f32': (8, 13, 13, 1024, 1024, 3, False, True, False),
+    'p3x3_64_128': (2, 64, 72, 64, 128, 3, False, False, False),
+    'p3x3_64_128_pool': (2, 64, 64, 64, 128, 3, True, False, False),
+    'p3x3_128_64': (2, 80, 64, 128, 64, 3, False, False, False),
+    'p3x3_32_64_pool': (2, 96, 64, 32, 64, 3, True, False, False),
+    'p3x3_3_32_pool': (2, 64, 96, 3, 32, 3, True, False, False),
+    'p3x3_3_32': (1, 70, 66, 3, 32, 3, False, False, False),
+    'p3x3_256_512': (1, 64, 64, 256, 512, 3, False, False, False),
     'big_l2': (8, 208, 208, 32, 64, 3, True, False, False),
     'big_l1': (8, 416, 416, 3, 32, 3, True, False, False),
     'big_l3': (8, 104, 104, 64, 128, 3, False, False, False),

@@ -1,0 +1,8 @@
+#!/bin/bash
+# ncu --set full on single-layer runs; reports land in gpurun_out/
+mkdir -p gpurun_out
+for L in "$@"; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 1 -c 1 -f -o gpurun_out/ncu_$L python tools/run_layer.py $L --iters 1 > gpurun_out/ncu_$L.log 2>&1
+  echo "ncu $L rc=$?"
+done
+ls -la gpurun_out/*.ncu-rep

@@ -21,7 +21,7 @@ def layer_specs(image_size=416, of=125):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    args = [a for a in sys.argv[1:] if a.startswith("L")]
     iters = int(sys.argv[sys.argv.index('--iters') + 1]) if '--iters' in sys.argv else 5
     N = int(sys.argv[sys.argv.index('--batch') + 1]) if '--batch' in sys.argv else 64
     specs = layer_specs()
