@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libyolo2_b200.so')
+LIB_PATH = os.environ.get('Y2_LIB_PATH') or os.path.join(_HERE, 'lib', 'libyolo2_b200.so')   # override: A/B experiments
 
 Y2_CONV_LEAKY, Y2_CONV_POOL2, Y2_CONV_OUT_F32 = 1, 2, 4
 
