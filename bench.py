@@ -171,7 +171,7 @@ def run_ours(args):
 
     N = BATCH_PER_GPU
     eng = Yolo2Engine(N, IMAGE_SIZE, OUTPUT_FILTER, score_thresh=SCORE_THRESH, iou_thresh=IOU_THRESH, max_keep=64,
-                      use_cuda_graph=True, device=dev, seed=0)
+                      use_cuda_graph=not args.no_graph, device=dev, seed=0)
     # 4 distinct synthetic batches (4 x 33 MB > L2 is not needed: L2 is flushed between steps anyway)
     g = torch.Generator(device='cpu').manual_seed(1234 + rank)
     host_batches = [torch.randint(0, 256, (N, IMAGE_SIZE, IMAGE_SIZE, 3), dtype=torch.uint8, generator=g).pin_memory()
@@ -250,6 +250,7 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel (conv_tc_kernel), timed live per launch ----
+    launches_per_step = eng.launches_per_step if not args.no_graph else None
     eng.use_cuda_graph = False
     conv_ms = conv_kernel_times(eng, ops, iters=max(3, min(args.steps, 10)))
     flops_img, per_layer = conv_flops_per_image(IMAGE_SIZE, OUTPUT_FILTER)
@@ -281,7 +282,7 @@ def run_ours(args):
                             l2='flushed (256 MiB memset) between timed steps', parallelism='batch sharding x%d' % world,
                             nms_candidates=cand, nms_kept=kept),
                 e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                gpu_launches=int(eng.launches_per_step * args.steps), launches_per_step=int(eng.launches_per_step),
+                gpu_launches=int((launches_per_step or 41) * args.steps), launches_per_step=int(launches_per_step or 41),
                 roofline=roofline, cpu_baseline=cpu, clocks=clocks)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -326,6 +327,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches (for ncu launch lists)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
