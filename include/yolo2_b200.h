@@ -149,6 +149,45 @@ int y2_loss_v1_fwd_bwd(const float* net, const float* labels, int N, int S, int 
                        float* ious, float* object_mask, float* dnet,
                        void* workspace, size_t workspace_bytes, y2_stream_t stream);
 
+/* ---- a': YOLOv2 region loss forward + backward, one kernel (absent from the reference) ---
+ * net [N,S,S,A*(5+C)] f32; anchors [A,2] (cell units); gt_boxes [N,G,4] normalised (cx,cy,w,h), 16-byte aligned;
+ * gt_classes [N,G] int32; gt_counts [N] int32 (<= G).  terms[5] = coord, obj, noobj, class, total (batch means);
+ * dnet like net (may be NULL).  Anchor<->ground-truth assignment, IoU, all four terms and the analytic gradient
+ * are evaluated per cell by one warp; deterministic reduction. */
+size_t y2_region_loss_workspace_bytes(int N, int S);
+int y2_region_loss_fwd_bwd(const float* net, const float* anchors, const float* gt_boxes, const int32_t* gt_classes,
+                           const int32_t* gt_counts, int N, int S, int A, int C, int G, float lambda_coord,
+                           float lambda_obj, float lambda_noobj, float lambda_class, float ignore_thresh, float* terms,
+                           float* dnet, void* workspace, size_t workspace_bytes, y2_stream_t stream);
+
+/* ---- a11: backward pass of conv_bn_layer (+ max_pool) -- TF autodiff of darknet.py:39-46, :24-25 ----------
+ * y2_bn_leaky_pool_bwd: dy = gradient of the layer output [N,Ho,Wo,C] (dy_dtype 0: float32, 1: bf16; Ho = H/2 when
+ * pool).  h_raw = the saved float32 pre-BN rows [N*H*W, ldh] (conv + bias), mean/var = the batch statistics of the
+ * forward pass.  Produces dgamma[C], dbeta[C] and dh = d loss / d h_raw as bf16 rows [N*H*W, ld_dh] (columns
+ * C..ld_dh-1 zero) -- the operand of both y2_conv_fwd_bf16 (data gradient) and y2_conv_wgrad_bf16.  z, x_hat and the
+ * pooling arg-max (first maximum in (dy,dx) scan order) are recomputed from h_raw.  The conv bias gradient is
+ * sum(dh) == 0 analytically (a bias in front of a batch-statistics BN is cancelled by the mean subtraction). */
+size_t y2_bn_bwd_workspace_bytes(int M, int C);
+int y2_bn_leaky_pool_bwd(const float* h_raw, int ldh, const void* dy, int dy_dtype, const float* mean, const float* var,
+                         const float* gamma, const float* beta, float eps, float alpha, int leaky, int pool, int N,
+                         int H, int W, int C, float* dgamma, float* dbeta, void* dh_bf16, int ld_dh, void* workspace,
+                         size_t workspace_bytes, y2_stream_t stream);
+/* Data gradient = the forward convolution of dh with the weights transposed (Cin <-> Cout) and flipped spatially:
+ * pack them with this, then call y2_conv_fwd_bf16 with Cin := ld_dh, Cout := Cin, no scale/shift/leaky. */
+size_t y2_conv_packed_weight_dgrad_elems(int ksize, int Cin, int ld_dh);
+int y2_pack_weights_dgrad_bf16(const float* w_hwio, void* w_packed, int ksize, int Cin, int Cout, int ld_dh,
+                               y2_stream_t stream);
+/* Weight gradient on tcgen05 (both operands MN-major from NHWC via TMA, split-K, fp32 reduction):
+ * dw HWIO [k,k,Cin,Cout] float32 += sum_pixels x (bf16 [N,H,W,Cin]) (x) dh (bf16 [N*H*W, ld_dh]).
+ * The caller zeroes dw.  Cin % 32 == 0, ld_dh % 64 == 0. */
+int y2_conv_wgrad_bf16(const void* x, const void* dh, int ld_dh, float* dw, int N, int H, int W, int Cin, int Cout,
+                       int ksize, y2_stream_t stream);
+/* First layer (Cin = 3 stored as bf16 [N,H,W,8], 3x3, Cout <= 32): FFMA kernel, dw [3,3,3,Cout] +=. */
+int y2_conv_wgrad_c3(const void* x_bf16c8, const void* dh_bf16, int ld_dh, int N, int H, int W, int Cout, float* dw,
+                     y2_stream_t stream);
+/* out[c] += sum over the M rows of a bf16 matrix [M, ld] (checks sum(dh) ~ 0; bias gradients of BN-free layers). */
+int y2_sum_rows_bf16(const void* a_bf16, int ld, size_t M, int C, float* out, y2_stream_t stream);
+
 /* ---- a11: Adam (tf.train.AdamOptimizer defaults, pascal_train_darknet.py:51) -----------------
  * p -= lr_t * m / (sqrt(v) + eps), lr_t = lr * sqrt(1-b2^t)/(1-b1^t) computed by the caller. */
 int y2_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1,

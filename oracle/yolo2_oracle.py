@@ -77,8 +77,10 @@ def yolo_grid_offset(S, B):
 # Convolution stack (darknet.py:20-46) on torch CPU
 # ----------------------------------------------------------------------------------------------
 def bf16_round(x):
-    """Round-to-nearest-even to bfloat16 and back (models the bf16 operand path)."""
-    return x.to(torch.bfloat16).to(x.dtype)
+    """Round-to-nearest-even to bfloat16 and back (models the bf16 operand path).  Straight-through for autograd:
+    the gradient is NOT rounded (a plain .to(bfloat16) would quantise the gradient flowing back as well)."""
+    r = x.detach().to(torch.bfloat16).to(x.dtype)
+    return x + (r - x.detach()) if x.requires_grad else r
 
 
 def conv2d_same(x_nhwc, w_hwio, dtype=None):
@@ -321,13 +323,12 @@ def _iou_backward(b1, b2, d_iou):
     return g
 
 
-def get_loss_torch(net, labels, num_class, batch_size, image_size, S, B,
-                   lambda_coord=LAMBDA_COORD, lambda_noobj=LAMBDA_NOOBJ):
-    """Same graph as get_loss on torch float64 with autograd -- an independent check of the
-    analytic gradient (torch splits max/min ties evenly, so only tie-free inputs compare)."""
-    net = torch.as_tensor(np.asarray(net), dtype=torch.float64).clone().requires_grad_(True)
-    labels = torch.as_tensor(np.asarray(labels), dtype=torch.float64)
+def loss_v1_graph(net, labels, num_class, batch_size, image_size, S, B,
+                  lambda_coord=LAMBDA_COORD, lambda_noobj=LAMBDA_NOOBJ):
+    """get_loss (net_utils.py:263-372) as a differentiable torch float64 graph; returns the scalar loss tensor
+    and the four terms (class, coord, object, noobject)."""
     N, C = batch_size, num_class
+    net = net.reshape(N, S, S, C + 5 * B)
     p_cls, p_conf = net[..., :C], net[..., C:C + B]
     p_box = net[..., C + B:].reshape(N, S, S, B, 4)
     resp = labels[..., 0].reshape(N, S, S, 1)
@@ -357,9 +358,43 @@ def get_loss_torch(net, labels, num_class, batch_size, image_size, S, B,
     coord = (delta ** 2).sum(dim=(1, 2, 3, 4)).mean() * lambda_coord
     obj = ((mask * (p_conf - ious)) ** 2).sum(dim=(1, 2, 3)).mean()
     noobj = ((nomask * p_conf) ** 2).sum(dim=(1, 2, 3)).mean() * lambda_noobj
-    loss = class_loss + obj + noobj + coord
+    return class_loss + obj + noobj + coord, (class_loss, coord, obj, noobj)
+
+
+def get_loss_torch(net, labels, num_class, batch_size, image_size, S, B,
+                   lambda_coord=LAMBDA_COORD, lambda_noobj=LAMBDA_NOOBJ):
+    """Same graph as get_loss on torch float64 with autograd -- an independent check of the
+    analytic gradient (torch splits max/min ties evenly, so only tie-free inputs compare)."""
+    net = torch.as_tensor(np.asarray(net), dtype=torch.float64).clone().requires_grad_(True)
+    labels = torch.as_tensor(np.asarray(labels), dtype=torch.float64)
+    loss, _ = loss_v1_graph(net, labels, num_class, batch_size, image_size, S, B, lambda_coord, lambda_noobj)
     loss.backward()
     return float(loss), net.grad.numpy()
+
+
+def train_step_reference(x_nhwc, params_core, params_head, loss_fn, bf16_operands=True):
+    """One iteration of pascal_train_darknet.py:96-102 up to the gradients: forward with is_training=True in
+    every layer (:36,39-40 feed is_training=True), loss, backward (TF autodiff == torch autograd on the same
+    graph).  loss_fn(net float64 tensor) -> scalar tensor.  Returns (loss, grads) with grads a list (layer order)
+    of dict(W, b, gamma, beta) float64 numpy arrays, plus the per-layer batch (mean, var)."""
+    leaves = []
+    for p in list(params_core) + list(params_head):
+        q = {k: torch.as_tensor(np.asarray(v), dtype=torch.float64).clone() for k, v in p.items()}
+        for k in ('W', 'b', 'gamma', 'beta'):
+            q[k].requires_grad_(True)
+        leaves.append(q)
+    nc = len(params_core)
+    x = torch.as_tensor(np.asarray(x_nhwc), dtype=torch.float64)
+    stats = []
+    for li, q in enumerate(leaves):
+        x, h, _ = conv_bn_layer(x, q, True, torch.float64, bf16_operands)
+        stats.append((h.detach().mean(dim=(0, 1, 2)).numpy(), h.detach().var(dim=(0, 1, 2), unbiased=False).numpy()))
+        if li < nc and CORE_PLAN[li][3]:
+            x = max_pool_2x2(x)
+    loss = loss_fn(x)
+    loss.backward()
+    grads = [{k: q[k].grad.numpy() for k in ('W', 'b', 'gamma', 'beta')} for q in leaves]
+    return float(loss.detach()), grads, stats, x.detach().numpy()
 
 
 # ----------------------------------------------------------------------------------------------

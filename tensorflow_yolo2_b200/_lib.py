@@ -46,6 +46,16 @@ _SIGNATURES = {
     'y2_iou': (_i, [_vp, _vp, _vp, _sz, _vp]),
     'y2_loss_v1_workspace_bytes': (_sz, [_i, _i]),
     'y2_loss_v1_fwd_bwd': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'y2_region_loss_workspace_bytes': (_sz, [_i, _i]),
+    'y2_region_loss_fwd_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    'y2_bn_bwd_workspace_bytes': (_sz, [_i, _i]),
+    'y2_bn_leaky_pool_bwd': (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i,
+                                  _vp, _sz, _vp]),
+    'y2_conv_packed_weight_dgrad_elems': (_sz, [_i, _i, _i]),
+    'y2_pack_weights_dgrad_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'y2_conv_wgrad_bf16': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'y2_conv_wgrad_c3': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    'y2_sum_rows_bf16': (_i, [_vp, _i, _sz, _i, _vp, _vp]),
     'y2_adam_step': (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _vp]),
 }
 

@@ -1,0 +1,403 @@
+// backward.cu -- a11: the HBM-bound half of the training step's backward pass (what TF autodiff emits for
+// conv_bn_layer, yolo2_nets/darknet.py:39-46, followed by max_pool, :24-25):
+//
+//   y2_bn_leaky_pool_bwd     dY (grad of the layer output, after the optional 2x2 max-pool) -> arg-max routing ->
+//                            leaky slope -> batch-norm backward (batch statistics):
+//                               dz      = dA * (z > 0 ? 1 : alpha)
+//                               dbeta   = sum dz          dgamma = sum dz * xhat
+//                               dh      = gamma*inv_std * (dz - dbeta/M - xhat * dgamma/M)        -> bf16 [M, ld_dh]
+//                            z / xhat / the pooling arg-max are recomputed from the saved fp32 pre-BN rows, so the
+//                            forward stores nothing extra.  Two passes over h (reduce in fp64, then apply).
+//   y2_pack_weights_dgrad_bf16   weights packed transposed + spatially flipped: the data gradient of a SAME stride-1
+//                            convolution is the same convolution of dh with those weights, so dgrad runs on
+//                            conv_tc_kernel (conv_tcgen05.cu) unchanged.
+//   y2_conv_wgrad_c3         weight gradient of the first layer (Cin = 3): K = 11 M pixels, 27 x Cout outputs -- a
+//                            shape the tensor cores cannot tile; persistent FFMA kernel with register accumulators.
+//   y2_sum_rows_bf16         bias gradient helper (column sums of dh).
+#include "common.cuh"
+
+namespace y2 {
+
+// ---------------------------------------------------------------------------------------------
+// pooled unit -> rows.  unit u indexes output pixels (n, ho, wo); rows are input pixels.
+// ---------------------------------------------------------------------------------------------
+struct UnitRows { size_t r[4]; int n; };
+
+__device__ __forceinline__ UnitRows unit_rows(size_t u, int H, int W, bool pool) {
+  UnitRows o;
+  if (!pool) { o.r[0] = u; o.n = 1; return o; }
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int wo = (int)(u % Wo);
+  const size_t t = u / Wo;
+  const int ho = (int)(t % Ho);
+  const size_t n = t / Ho;
+  const size_t base = (n * H + 2 * ho) * (size_t)W + 2 * wo;
+  o.r[0] = base; o.r[1] = base + 1; o.r[2] = base + W; o.r[3] = base + W + 1;
+  o.n = 4;
+  return o;
+}
+
+__device__ __forceinline__ float load_dy(const void* dy, int dy_f32, size_t i) {
+  return dy_f32 ? reinterpret_cast<const float*>(dy)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[i]);
+}
+
+// pass 1: grid (ceil(C/32), splits), block (32, 8).  part[split][c][2] = (sum dz, sum dz*xhat)
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ h, int ldh, const void* __restrict__ dy, int dy_f32,
+                                     const float* __restrict__ mean, const float* __restrict__ var,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                     float alpha, int leaky_on, int pool, int H, int W, int C, size_t units,
+                                     size_t units_per_split, double* __restrict__ part) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t u0 = (size_t)blockIdx.y * units_per_split;
+  const size_t u1 = min(units, u0 + units_per_split);
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C) {
+    const float mu = mean[c], inv = rsqrtf(var[c] + eps), g = gamma[c], b = beta[c];
+    float f1 = 0.0f, f2 = 0.0f;
+    int cnt = 0;
+    for (size_t u = u0 + threadIdx.y; u < u1; u += 8) {
+      const UnitRows ur = unit_rows(u, H, W, pool != 0);
+      float best = -INFINITY, bx = 0.0f, bz = 0.0f;
+      for (int k = 0; k < ur.n; ++k) {
+        const float xh = (h[ur.r[k] * ldh + c] - mu) * inv;
+        const float z = xh * g + b;
+        const float a = leaky_on ? fmaxf(z, alpha * z) : z;
+        if (a > best) { best = a; bx = xh; bz = z; }
+      }
+      float d = load_dy(dy, dy_f32, u * C + c);
+      if (leaky_on && !(bz > 0.0f)) d *= alpha;
+      f1 += d;
+      f2 += d * bx;
+      if (++cnt == 64) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.0f; cnt = 0; }
+    }
+    a1 += (double)f1;
+    a2 += (double)f2;
+  }
+  s1[threadIdx.y][threadIdx.x] = a1;
+  s2[threadIdx.y][threadIdx.x] = a2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int y = 1; y < 8; ++y) { a1 += s1[y][threadIdx.x]; a2 += s2[y][threadIdx.x]; }
+    part[((size_t)blockIdx.y * C + c) * 2 + 0] = a1;
+    part[((size_t)blockIdx.y * C + c) * 2 + 1] = a2;
+  }
+}
+
+__global__ void bn_bwd_final_kernel(const double* __restrict__ part, int splits, int C, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a1 = 0.0, a2 = 0.0;
+  for (int s = 0; s < splits; ++s) {
+    a1 += part[((size_t)s * C + c) * 2 + 0];
+    a2 += part[((size_t)s * C + c) * 2 + 1];
+  }
+  dbeta[c] = (float)a1;
+  dgamma[c] = (float)a2;
+}
+
+// pass 2: one thread per (unit, VEC channels); writes dh for every input pixel of the unit.
+template <int VEC>
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ h, int ldh, const void* __restrict__ dy, int dy_f32,
+                                    const float* __restrict__ mean, const float* __restrict__ var,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, float eps,
+                                    float alpha, int leaky_on, int pool, int H, int W, int C, size_t units, float invM,
+                                    __nv_bfloat16* __restrict__ dh, int ld_dh) {
+  const int CV = ld_dh / VEC;                       // channel groups incl. the zero padding columns
+  const size_t total = units * CV;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int cv = (int)(i % CV);
+    const size_t u = i / CV;
+    const int c0 = cv * VEC;
+    const UnitRows ur = unit_rows(u, H, W, pool != 0);
+    float xh[4][VEC];
+    int arg[VEC];
+    float zbest[VEC], abest[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { arg[v] = 0; abest[v] = -INFINITY; zbest[v] = 0.0f; }
+    for (int k = 0; k < ur.n; ++k) {
+      float t[VEC];
+      const float* px = h + ur.r[k] * ldh + c0;
+      if (VEC == 4 && c0 + 3 < C) {
+        const float4 q = *reinterpret_cast<const float4*>(px);
+        t[0] = q.x; t[1 % VEC] = q.y; t[2 % VEC] = q.z; t[3 % VEC] = q.w;
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) t[v] = (c0 + v < C) ? px[v] : 0.0f;
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int c = c0 + v;
+        if (c < C) {
+          const float x_ = (t[v] - mean[c]) * rsqrtf(var[c] + eps);
+          const float z = x_ * gamma[c] + beta[c];
+          const float a = leaky_on ? fmaxf(z, alpha * z) : z;
+          xh[k][v] = x_;
+          if (a > abest[v]) { abest[v] = a; arg[v] = k; zbest[v] = z; }
+        } else {
+          xh[k][v] = 0.0f;
+        }
+      }
+    }
+    float d[VEC], gi[VEC], m1[VEC], m2[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int c = c0 + v;
+      if (c < C) {
+        float g = load_dy(dy, dy_f32, u * C + c);
+        if (leaky_on && !(zbest[v] > 0.0f)) g *= alpha;
+        d[v] = g;
+        gi[v] = gamma[c] * rsqrtf(var[c] + eps);
+        m1[v] = dbeta[c] * invM;
+        m2[v] = dgamma[c] * invM;
+      } else {
+        d[v] = 0.0f; gi[v] = 0.0f; m1[v] = 0.0f; m2[v] = 0.0f;
+      }
+    }
+    for (int k = 0; k < ur.n; ++k) {
+      float o[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o[v] = gi[v] * ((arg[v] == k ? d[v] : 0.0f) - m1[v] - xh[k][v] * m2[v]);
+      __nv_bfloat16* po = dh + ur.r[k] * ld_dh + c0;
+      if (VEC == 4) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1 % VEC]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(o[2 % VEC], o[3 % VEC]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(po) = pk;
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) po[v] = __float2bfloat16_rn(o[v]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dgrad weights: conv'(dh)[n,h,w,ci] = sum_{kh',kw',co} dh[n, h+kh'-p, w+kw'-p, co] * W[k-1-kh', k-1-kw', ci, co]
+// packed like y2_pack_weights_bf16 for a convolution with Cin' = ld_dh (>= Cout, zero columns beyond Cout)
+// and Cout' = Cin:   out[ci][tap' * ld_dh + co]
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_weights_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps, int Cin,
+                                          int Cout, int cinp_rows, int ld_dh) {
+  const int Kp = taps * ld_dh;
+  const size_t total = (size_t)cinp_rows * Kp;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int ci = (int)(i / Kp);
+    const int kk = (int)(i % Kp);
+    const int tapf = kk / ld_dh, co = kk % ld_dh;
+    const int tap = taps - 1 - tapf;                 // (k-1-kh')*k + (k-1-kw') == taps-1-tap'
+    float v = 0.0f;
+    if (ci < Cin && co < Cout) v = w[((size_t)tap * Cin + ci) * Cout + co];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// first-layer weight gradient: x bf16 [N,H,W,8] (channels 0..2 real), dh bf16 [N*H*W, ld_dh], Cout <= 32.
+// dW[kh][kw][ci][co] += sum_pixels x[n, h+kh-1, w+kw-1, ci] * dh[n,h,w,co]
+// Persistent CTAs over 8 x 32 pixel tiles; warp = tile row, lane = co; 27 register accumulators per lane;
+// the x halo row slides through registers (3 new smem loads per pixel instead of 9).
+// ---------------------------------------------------------------------------------------------
+constexpr int W1_TH = 8, W1_TW = 32;
+
+__global__ void __launch_bounds__(256) conv_wgrad_c3_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ dh, int ld_dh, int N, int H,
+                                                            int W, int Cout, float* __restrict__ dw) {
+  __shared__ __align__(16) uint2 s_x[W1_TH + 2][W1_TW + 2];          // 4 bf16 per pixel (ch 0..3)
+  __shared__ __align__(16) __nv_bfloat16 s_dh[W1_TH][W1_TW][32];
+  __shared__ float s_red[8][27][33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_w = (W + W1_TW - 1) / W1_TW, tiles_h = (H + W1_TH - 1) / W1_TH;
+  const int total = N * tiles_h * tiles_w;
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.0f;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int h0 = th * W1_TH, w0 = tw * W1_TW;
+    __syncthreads();
+    for (int i = tid; i < (W1_TH + 2) * (W1_TW + 2); i += 256) {
+      const int r = i / (W1_TW + 2), cidx = i % (W1_TW + 2);
+      const int hh = h0 + r - 1, ww = w0 + cidx - 1;
+      uint2 v = make_uint2(0u, 0u);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+        v = *reinterpret_cast<const uint2*>(x + ((size_t)(n * H + hh) * W + ww) * 8);
+      s_x[r][cidx] = v;
+    }
+    for (int i = tid; i < W1_TH * W1_TW * 4; i += 256) {             // 4 x 16-byte chunks per pixel
+      const int p = i >> 2, q = i & 3;
+      const int r = p / W1_TW, cidx = p % W1_TW;
+      const int hh = h0 + r, ww = w0 + cidx;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (hh < H && ww < W && q * 8 < ld_dh)
+        v = *reinterpret_cast<const uint4*>(dh + ((size_t)(n * H + hh) * W + ww) * ld_dh + q * 8);
+      *reinterpret_cast<uint4*>(&s_dh[r][cidx][q * 8]) = v;
+    }
+    __syncthreads();
+    // warp = tile row; slide a 3-row x 3-column window of x along the row
+    float xw[3][3][3];                                               // [kh][kw][ci]
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 2; ++kw) {
+        const uint2 v = s_x[warp + kh][kw];
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+        xw[kh][kw + 1][0] = __low2float(a); xw[kh][kw + 1][1] = __high2float(a); xw[kh][kw + 1][2] = __low2float(b);
+      }
+#pragma unroll 4
+    for (int p = 0; p < W1_TW; ++p) {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) { xw[kh][0][ci] = xw[kh][1][ci]; xw[kh][1][ci] = xw[kh][2][ci]; }
+        const uint2 v = s_x[warp + kh][p + 2];
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+        xw[kh][2][0] = __low2float(a); xw[kh][2][1] = __high2float(a); xw[kh][2][2] = __low2float(b);
+      }
+      const float g = __bfloat162float(s_dh[warp][p][lane]);
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) acc[(kh * 3 + kw) * 3 + ci] = fmaf(xw[kh][kw][ci], g, acc[(kh * 3 + kw) * 3 + ci]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 27; ++i) s_red[warp][i][lane] = acc[i];
+  __syncthreads();
+  for (int i = tid; i < 27 * 32; i += 256) {
+    const int k = i >> 5, co = i & 31;
+    float s = 0.0f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += s_red[w8][k][co];
+    if (co < Cout) atomicAdd(dw + (size_t)k * Cout + co, s);
+  }
+}
+
+// column sums of a bf16 matrix [M, ld] -> out[C] (+=): conv bias gradient
+__global__ void sum_rows_bf16_kernel(const __nv_bfloat16* __restrict__ a, int ld, size_t M, int C, size_t rows_per_block,
+                                     float* __restrict__ out) {
+  __shared__ float s[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t r0 = (size_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float acc = 0.0f;
+  if (c < C)
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) acc += __bfloat162float(a[r * ld + c]);
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int y = 1; y < 8; ++y) acc += s[y][threadIdx.x];
+    atomicAdd(out + c, acc);
+  }
+}
+
+static int bwd_splits(size_t units) {
+  size_t s = (units + 255) / 256;
+  return (int)(s > 592 ? 592 : (s < 1 ? 1 : s));
+}
+
+}  // namespace y2
+
+using namespace y2;
+
+extern "C" {
+
+size_t y2_bn_bwd_workspace_bytes(int M, int C) { return (size_t)bwd_splits((size_t)M) * C * 2 * sizeof(double); }
+
+int y2_bn_leaky_pool_bwd(const float* h_raw, int ldh, const void* dy, int dy_dtype, const float* mean, const float* var,
+                         const float* gamma, const float* beta, float eps, float alpha, int leaky_on, int pool, int N,
+                         int H, int W, int C, float* dgamma, float* dbeta, void* dh_bf16, int ld_dh, void* workspace,
+                         size_t workspace_bytes, y2_stream_t stream) {
+  Y2_ARG(h_raw && dy && mean && var && gamma && beta && dgamma && dbeta && dh_bf16);
+  Y2_ARG(N > 0 && H > 0 && W > 0 && C > 0 && ldh >= C && ld_dh >= C && (dy_dtype == 0 || dy_dtype == 1));
+  if (pool) Y2_ARG(H % 2 == 0 && W % 2 == 0);
+  const size_t M = (size_t)N * H * W;
+  const size_t units = pool ? M / 4 : M;
+  if (!workspace || workspace_bytes < y2_bn_bwd_workspace_bytes((int)M, C)) {
+    set_error("y2_bn_leaky_pool_bwd: workspace too small (%zu < %zu)", workspace_bytes, y2_bn_bwd_workspace_bytes((int)M, C));
+    return Y2_ERR_WORKSPACE;
+  }
+  Y2_ARG(((uintptr_t)workspace & 7) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  int splits = bwd_splits(units);
+  size_t ups = (units + splits - 1) / splits;
+  splits = (int)((units + ups - 1) / ups);
+  dim3 grid((C + 31) / 32, splits), block(32, 8);
+  bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(h_raw, ldh, dy, dy_dtype == 0, mean, var, gamma, beta, eps, alpha, leaky_on,
+                                               pool, H, W, C, units, ups, (double*)workspace);
+  Y2_LAUNCHED();
+  bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, st>>>((const double*)workspace, splits, C, dgamma, dbeta);
+  Y2_LAUNCHED();
+  const bool vec4 = (ld_dh % 4 == 0) && (ldh % 4 == 0) && (((uintptr_t)h_raw & 15) == 0) && (((uintptr_t)dh_bf16 & 7) == 0);
+  const float invM = 1.0f / (float)M;
+  if (vec4) {
+    size_t total = units * (ld_dh / 4);
+    size_t g = (total + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    bn_bwd_apply_kernel<4><<<(int)g, 256, 0, st>>>(h_raw, ldh, dy, dy_dtype == 0, mean, var, gamma, beta, dgamma, dbeta, eps,
+                                                   alpha, leaky_on, pool, H, W, C, units, invM, (__nv_bfloat16*)dh_bf16, ld_dh);
+  } else {
+    size_t total = units * ld_dh;
+    size_t g = (total + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    bn_bwd_apply_kernel<1><<<(int)g, 256, 0, st>>>(h_raw, ldh, dy, dy_dtype == 0, mean, var, gamma, beta, dgamma, dbeta, eps,
+                                                   alpha, leaky_on, pool, H, W, C, units, invM, (__nv_bfloat16*)dh_bf16, ld_dh);
+  }
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+size_t y2_conv_packed_weight_dgrad_elems(int ksize, int Cin, int ld_dh) {
+  const int rows = (Cin + 15) / 16 * 16;
+  return (size_t)rows * ksize * ksize * ld_dh;
+}
+
+int y2_pack_weights_dgrad_bf16(const float* w_hwio, void* w_packed, int ksize, int Cin, int Cout, int ld_dh,
+                               y2_stream_t stream) {
+  Y2_ARG(w_hwio && w_packed && (ksize == 1 || ksize == 3) && Cin > 0 && Cout > 0 && ld_dh >= Cout && ld_dh % 32 == 0);
+  const int rows = (Cin + 15) / 16 * 16;
+  const size_t total = (size_t)rows * ksize * ksize * ld_dh;
+  size_t g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  pack_weights_dgrad_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w_hwio, (__nv_bfloat16*)w_packed, ksize * ksize, Cin,
+                                                                      Cout, rows, ld_dh);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_conv_wgrad_c3(const void* x_bf16c8, const void* dh_bf16, int ld_dh, int N, int H, int W, int Cout, float* dw,
+                     y2_stream_t stream) {
+  Y2_ARG(x_bf16c8 && dh_bf16 && dw && N > 0 && H > 0 && W > 0 && Cout > 0 && Cout <= 32 && ld_dh >= Cout && ld_dh % 8 == 0);
+  const int tiles = N * ((H + W1_TH - 1) / W1_TH) * ((W + W1_TW - 1) / W1_TW);
+  const int grid = tiles < 148 * 2 ? tiles : 148 * 2;
+  conv_wgrad_c3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16c8, (const __nv_bfloat16*)dh_bf16,
+                                                               ld_dh, N, H, W, Cout, dw);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_sum_rows_bf16(const void* a_bf16, int ld, size_t M, int C, float* out, y2_stream_t stream) {
+  Y2_ARG(a_bf16 && out && M > 0 && C > 0 && ld >= C);
+  size_t blocks = (M + 2047) / 2048;
+  if (blocks > 1024) blocks = 1024;
+  const size_t rpb = (M + blocks - 1) / blocks;
+  blocks = (M + rpb - 1) / rpb;
+  dim3 grid((C + 31) / 32, (unsigned)blocks), block(32, 8);
+  sum_rows_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a_bf16, ld, M, C, rpb, out);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+}  // extern "C"

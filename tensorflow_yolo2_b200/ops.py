@@ -77,10 +77,12 @@ def conv_cin_padded(cin):
     return int(_lib.load().y2_conv_cin_padded(cin))
 
 
-def pack_weights_bf16(w_hwio):
+def pack_weights_bf16(w_hwio, out=None):
     k, _, Cin, Cout = w_hwio.shape
     n = int(_lib.load().y2_conv_packed_weight_elems(k, Cin, Cout))
-    out = torch.empty((n,), dtype=torch.bfloat16, device=w_hwio.device)
+    if out is None:
+        out = torch.empty((n,), dtype=torch.bfloat16, device=w_hwio.device)
+    assert out.numel() >= n
     check(_lib.load().y2_pack_weights_bf16(_p(w_hwio, torch.float32), _p(out), k, Cin, Cout, _stream()),
           'y2_pack_weights_bf16')
     return out
@@ -224,21 +226,123 @@ def iou(boxes1, boxes2):
     return out
 
 
-def loss_v1(net, labels, S, B, C_, image_size, lambda_coord=5.0, lambda_noobj=0.5, want_grad=True):
+def loss_v1(net, labels, S, B, C_, image_size, lambda_coord=5.0, lambda_noobj=0.5, want_grad=True, terms=None,
+            ious=None, object_mask=None, dnet=None):
     """Returns (terms[5] = class, coord, object, noobject, total; ious; object_mask; dnet)."""
     N = net.shape[0]
     dev = net.device
     lib = _lib.load()
-    terms = torch.empty((5,), dtype=torch.float32, device=dev)
-    ious = torch.empty((N, S, S, B), dtype=torch.float32, device=dev)
-    mask = torch.empty((N, S, S, B), dtype=torch.float32, device=dev)
-    dnet = torch.empty_like(net) if want_grad else None
+    if terms is None:
+        terms = torch.empty((5,), dtype=torch.float32, device=dev)
+    if ious is None:
+        ious = torch.empty((N, S, S, B), dtype=torch.float32, device=dev)
+    if object_mask is None:
+        object_mask = torch.empty((N, S, S, B), dtype=torch.float32, device=dev)
+    if dnet is None and want_grad:
+        dnet = torch.empty_like(net)
     need = int(lib.y2_loss_v1_workspace_bytes(N, S))
     ws = _workspace(need, dev)
     check(lib.y2_loss_v1_fwd_bwd(_p(net, torch.float32), _p(labels, torch.float32), N, S, B, C_, float(image_size),
-                                 lambda_coord, lambda_noobj, _p(terms), _p(ious), _p(mask), _p(dnet), _p(ws),
+                                 lambda_coord, lambda_noobj, _p(terms), _p(ious), _p(object_mask), _p(dnet), _p(ws),
                                  ws.numel(), _stream()), 'y2_loss_v1_fwd_bwd')
-    return terms, ious, mask, dnet
+    return terms, ious, object_mask, dnet
+
+
+def region_loss(net, anchors, gt_boxes, gt_classes, gt_counts, C_=20, lambda_coord=1.0, lambda_obj=5.0, lambda_noobj=1.0,
+                lambda_class=1.0, ignore_thresh=0.6, want_grad=True, terms=None, dnet=None):
+    """YOLOv2 region loss.  net f32 [N,S,S,A*(5+C)]; gt_boxes f32 [N,G,4] normalised
+    (cx,cy,w,h); gt_classes int32 [N,G]; gt_counts int32 [N].  Returns (terms[5] = coord, obj, noobj, class,
+    total; dnet)."""
+    N, S = net.shape[0], net.shape[1]
+    A = anchors.shape[0]
+    G = gt_boxes.shape[1]
+    assert net.numel() == N * S * S * A * (5 + C_)
+    dev = net.device
+    lib = _lib.load()
+    if terms is None:
+        terms = torch.empty((5,), dtype=torch.float32, device=dev)
+    if dnet is None and want_grad:
+        dnet = torch.empty_like(net)
+    need = int(lib.y2_region_loss_workspace_bytes(N, S))
+    ws = _workspace(need, dev)
+    check(lib.y2_region_loss_fwd_bwd(_p(net, torch.float32), _p(anchors, torch.float32), _p(gt_boxes, torch.float32),
+                                     _p(gt_classes, torch.int32), _p(gt_counts, torch.int32), N, S, A, C_, G,
+                                     lambda_coord, lambda_obj, lambda_noobj, lambda_class, ignore_thresh, _p(terms),
+                                     _p(dnet), _p(ws), ws.numel(), _stream()), 'y2_region_loss_fwd_bwd')
+    return terms, dnet
+
+
+# ---- a11: backward --------------------------------------------------------------------------
+def bn_bwd_workspace_bytes(M, C_):
+    return int(_lib.load().y2_bn_bwd_workspace_bytes(M, C_))
+
+
+def bn_leaky_pool_bwd(h_raw, dy, mean, var, gamma, beta, N, H, W, C_, ldh=None, leaky=True, pool=False, ld_dh=None,
+                      dgamma=None, dbeta=None, dh=None, workspace=None, alpha=ALPHA, eps=BN_EPS):
+    """Backward of max_pool(leaky(batch_norm(h_raw))) (batch statistics).  dy: grad of the layer output
+    [N,Ho,Wo,C] (f32 or bf16).  Returns (dgamma[C], dbeta[C], dh bf16 [N*H*W, ld_dh])."""
+    ldh = ldh or C_
+    ld_dh = ld_dh or (C_ + 63) // 64 * 64
+    dev = h_raw.device
+    if dy.dtype not in (torch.float32, torch.bfloat16):
+        raise _lib.Y2Error('dy must be float32 or bfloat16')
+    if dgamma is None:
+        dgamma = torch.empty((C_,), dtype=torch.float32, device=dev)
+    if dbeta is None:
+        dbeta = torch.empty((C_,), dtype=torch.float32, device=dev)
+    M = N * H * W
+    if dh is None:
+        dh = torch.empty((M, ld_dh), dtype=torch.bfloat16, device=dev)
+    assert dh.numel() >= M * ld_dh
+    lib = _lib.load()
+    need = int(lib.y2_bn_bwd_workspace_bytes(M, C_))
+    ws = workspace if workspace is not None else _workspace(need, dev)
+    check(lib.y2_bn_leaky_pool_bwd(_p(h_raw, torch.float32), ldh, _p(dy), 0 if dy.dtype == torch.float32 else 1,
+                                   _p(mean, torch.float32), _p(var, torch.float32), _p(gamma, torch.float32),
+                                   _p(beta, torch.float32), eps, alpha, 1 if leaky else 0, 1 if pool else 0, N, H, W, C_,
+                                   _p(dgamma, torch.float32), _p(dbeta, torch.float32), _p(dh, torch.bfloat16), ld_dh,
+                                   _p(ws), ws.numel(), _stream()), 'y2_bn_leaky_pool_bwd')
+    return dgamma, dbeta, dh
+
+
+def pack_weights_dgrad_bf16(w_hwio, ld_dh, out=None):
+    """Weights for the data-gradient convolution (transposed + flipped), to be used with
+    conv_fwd_bf16(dh, packed, ksize, cin=ld_dh, cout=Cin, leaky=False)."""
+    k, _, Cin, Cout = w_hwio.shape
+    lib = _lib.load()
+    n = int(lib.y2_conv_packed_weight_dgrad_elems(k, Cin, ld_dh))
+    if out is None:
+        out = torch.empty((n,), dtype=torch.bfloat16, device=w_hwio.device)
+    assert out.numel() >= n
+    check(lib.y2_pack_weights_dgrad_bf16(_p(w_hwio, torch.float32), _p(out), k, Cin, Cout, ld_dh, _stream()),
+          'y2_pack_weights_dgrad_bf16')
+    return out
+
+
+def conv_wgrad_bf16(x, dh, ksize, cin, cout, dw):
+    """dw (HWIO f32, pre-zeroed) += weight gradient; x bf16 [N,H,W,cin], dh bf16 [N*H*W, ld_dh]."""
+    N, H, W, cx = x.shape
+    assert cx == cin
+    ld_dh = dh.shape[-1]
+    check(_lib.load().y2_conv_wgrad_bf16(_p(x, torch.bfloat16), _p(dh, torch.bfloat16), ld_dh, _p(dw, torch.float32), N, H,
+                                         W, cin, cout, ksize, _stream()), 'y2_conv_wgrad_bf16')
+    return dw
+
+
+def conv_wgrad_c3(x8, dh, cout, dw):
+    """First layer: x bf16 [N,H,W,8] (3 real channels), dh bf16 [N*H*W, ld_dh]; dw [3,3,3,cout] f32 +=."""
+    N, H, W, c8 = x8.shape
+    assert c8 == 8
+    check(_lib.load().y2_conv_wgrad_c3(_p(x8, torch.bfloat16), _p(dh, torch.bfloat16), dh.shape[-1], N, H, W, cout,
+                                       _p(dw, torch.float32), _stream()), 'y2_conv_wgrad_c3')
+    return dw
+
+
+def sum_rows_bf16(a, C_, out):
+    M, ld = a.shape
+    check(_lib.load().y2_sum_rows_bf16(_p(a, torch.bfloat16), ld, M, C_, _p(out, torch.float32), _stream()),
+          'y2_sum_rows_bf16')
+    return out
 
 
 # ---- a11 -----------------------------------------------------------------------------------

@@ -1,0 +1,284 @@
+"""Training step of the reference's Pascal script on the B200 kernels.
+
+What the reference runs per iteration (src/pascal/pascal_train_darknet.py:96-102) is one
+``sess.run([loss, train_op, ious, object_mask], feed_dict)``: forward of darknet19_core +
+darknet19_detection with batch-statistics batch norm in all 22 layers, the BN moving-average
+UPDATE_OPS (:49-50), get_loss (:44-46), TF autodiff, and ``AdamOptimizer().minimize`` (:51, TF defaults
+lr 1e-3, beta 0.9/0.999, eps 1e-8).  ``Yolo2Trainer.step`` enqueues exactly that on the current CUDA stream:
+
+  forward   conv_tc_kernel (tcgen05) -> fp32 pre-BN rows, bn_stats, affine_leaky_pool -> bf16 activation
+  loss      loss_v1 (the reference's get_loss, C+5B channels) or region_loss (YOLOv2, A*(5+C) channels): loss terms
+            and d loss / d net in one kernel
+  backward  per layer, last to first: y2_bn_leaky_pool_bwd -> (dgamma, dbeta, dh bf16);
+            y2_conv_wgrad_bf16 (tcgen05, MN-major operands, split-K) / y2_conv_wgrad_c3 (first layer);
+            data gradient = conv_tc_kernel on dh with transposed+flipped packed weights
+  all-reduce (world > 1) NCCL, bucketed in reverse layer order, each bucket issued as soon as its layers'
+            gradients are enqueued so it overlaps the rest of the backward pass; gradients are averaged
+            (each rank's loss is the mean over its local batch, net_utils.py:296)
+  update    one y2_adam_step over the flat parameter arena
+
+Parameters, gradients and Adam moments live in flat fp32 arenas (layers in REVERSE order so that a bucket is a
+contiguous slice that becomes ready early); the VariableStore entries are views into the parameter arena, so
+checkpoints (net_utils.save_checkpoint) see the live weights under their TF names.
+The conv bias sits in front of a batch-statistics BN, so its gradient is identically zero (TF computes rounding
+noise there); it is left at exactly 0.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import create_variables
+from .variables import VariableStore
+from .yolo2_nets.net_utils import VOC_ANCHORS
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Yolo2Trainer:
+    def __init__(self, batch, image_size=416, output_filter=None, store=None, loss='v1', num_class=20, B=5,
+                 anchors=VOC_ANCHORS, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, lambda_coord=None, lambda_noobj=None,
+                 max_gt=32, device=None, seed=0, process_group=None, bucket_bytes=48 << 20, update_moving=True):
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.N, self.IS = int(batch), int(image_size)
+        assert self.IS % 32 == 0
+        self.S = self.IS // 32
+        self.C = int(num_class)
+        self.loss_kind = loss
+        if loss == 'v1':
+            self.B = int(B)
+            of = self.C + 5 * self.B                     # net_utils.py:279-285 channel layout
+            self.lambda_coord = 5.0 if lambda_coord is None else lambda_coord      # config.py:44
+            self.lambda_noobj = 0.5 if lambda_noobj is None else lambda_noobj      # config.py:45
+        elif loss == 'region':
+            self.anchors_np = np.asarray(anchors, dtype=np.float32)
+            self.A = self.anchors_np.shape[0]
+            of = self.A * (5 + self.C)
+            self.lambda_coord = 1.0 if lambda_coord is None else lambda_coord
+            self.lambda_noobj = 1.0 if lambda_noobj is None else lambda_noobj
+            self.max_gt = int(max_gt)
+        else:
+            raise ValueError('loss must be "v1" or "region"')
+        self.OF = int(output_filter) if output_filter is not None else of
+        assert self.OF == of, 'output_filter %d does not match the %s loss layout (%d)' % (self.OF, loss, of)
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.update_moving = update_moving
+        self.store = store if store is not None else VariableStore(seed=seed)
+        self.layers = create_variables(self.store, self.OF)
+        self.iteration = 0
+        dev = self.device
+        with torch.cuda.device(dev):
+            self._build_arenas()
+            self._build_buffers()
+            self._build_buckets(bucket_bytes)
+
+    # ------------------------------------------------------------------------------------------
+    def _build_arenas(self):
+        """Flat fp32 arenas, layers in reverse order, per layer [W | b | gamma | beta], 64-float aligned."""
+        st, dev = self.store, self.device
+        off = 0
+        self.slots = [None] * len(self.layers)
+        for li in reversed(range(len(self.layers))):
+            L = self.layers[li]
+            names = (L['W'], L['b'], L['bn']['gamma'], L['bn']['beta'])
+            sl = {}
+            start = off
+            for key, nm in zip(('W', 'b', 'gamma', 'beta'), names):
+                n = int(np.prod(np.shape(st[nm])))
+                sl[key] = (off, n, tuple(np.shape(st[nm])))
+                off = _round_up(off + n, 64)
+            sl['range'] = (start, off)
+            self.slots[li] = sl
+        self.arena_elems = off
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.params = torch.zeros((off,), **f32)
+        self.grads = torch.zeros((off,), **f32)
+        self.adam_m = torch.zeros((off,), **f32)
+        self.adam_v = torch.zeros((off,), **f32)
+        self.P, self.G = [], []
+        for li, L in enumerate(self.layers):
+            sl = self.slots[li]
+            pv, gv = {}, {}
+            for key, nm in zip(('W', 'b', 'gamma', 'beta'), (L['W'], L['b'], L['bn']['gamma'], L['bn']['beta'])):
+                o, n, shp = sl[key]
+                pv[key] = self.params[o:o + n].view(shp)
+                gv[key] = self.grads[o:o + n].view(shp)
+                src = st[nm]
+                pv[key].copy_(torch.as_tensor(src).to(dev) if not isinstance(src, torch.Tensor) else src.to(dev))
+                st.vars[nm] = pv[key]                       # the store now aliases the arena
+            for nm in (L['bn']['moving_mean'], L['bn']['moving_variance']):
+                v = st[nm]
+                st.vars[nm] = (torch.as_tensor(v) if not isinstance(v, torch.Tensor) else v).to(dev).contiguous()
+            self.P.append(pv)
+            self.G.append(gv)
+        st.version += 1
+
+    def _build_buffers(self):
+        N, IS, dev = self.N, self.IS, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        bf16 = dict(dtype=torch.bfloat16, device=dev)
+        self.in_u8 = torch.zeros((N, IS, IS, 3), dtype=torch.uint8, device=dev)
+        self.x0 = torch.empty((N, IS, IS, 8), **bf16)
+        self.acts, self.raw, self.stats, self.geom = [], [], [], []
+        self.packed, self.packed_dgrad = [], []
+        H = IS
+        max_ws, max_dh, max_dx = 1, 1, 1
+        nl = len(self.layers)
+        for li, L in enumerate(self.layers):
+            Ho = H // 2 if L['pool'] else H
+            last = li == nl - 1
+            cout, cin, k = L['cout'], L['cin'], L['k']
+            ldh = _round_up(cout, 32)
+            ld_dh = 32 if li == 0 else _round_up(cout, 64)
+            self.geom.append(dict(H=H, Ho=Ho, ldh=ldh, ld_dh=ld_dh, M=N * H * H))
+            self.acts.append(torch.empty((N, Ho, Ho, cout), **(f32 if last else bf16)))
+            self.raw.append(torch.empty((N * H * H, ldh), **f32))
+            self.stats.append(dict(mean=torch.empty((cout,), **f32), var=torch.empty((cout,), **f32),
+                                   scale=torch.empty((cout,), **f32), shift=torch.empty((cout,), **f32),
+                                   zeros=torch.zeros((cout,), **f32)))
+            max_ws = max(max_ws, ops.bn_stats_workspace_bytes(N * H * H, cout), ops.bn_bwd_workspace_bytes(N * H * H, cout))
+            max_dh = max(max_dh, N * H * H * ld_dh)
+            if li > 0:
+                max_dx = max(max_dx, N * H * H * cin)
+            self.packed.append(torch.empty((int(ops._lib.load().y2_conv_packed_weight_elems(k, cin, cout)),), **bf16))
+            self.packed_dgrad.append(None if li == 0 else torch.empty(
+                (int(ops._lib.load().y2_conv_packed_weight_dgrad_elems(k, cin, ld_dh)),), **bf16))
+            H = Ho
+        self.ws = torch.empty((max_ws,), dtype=torch.uint8, device=dev)
+        self.dh = torch.empty((max_dh,), **bf16)
+        self.dx = [torch.empty((max_dx,), **bf16), torch.empty((max_dx,), **bf16)]
+        S = self.S
+        self.terms = torch.zeros((5,), **f32)
+        self.dnet = torch.empty((N, S, S, self.OF), **f32)
+        if self.loss_kind == 'v1':
+            self.labels = torch.zeros((N, S, S, 5 + self.C), **f32)
+            self.ious = torch.empty((N, S, S, self.B), **f32)
+            self.object_mask = torch.empty((N, S, S, self.B), **f32)
+        else:
+            self.anchors = torch.as_tensor(self.anchors_np).to(dev).contiguous()
+            self.gt_boxes = torch.zeros((N, self.max_gt, 4), **f32)
+            self.gt_classes = torch.zeros((N, self.max_gt), dtype=torch.int32, device=dev)
+            self.gt_counts = torch.zeros((N,), dtype=torch.int32, device=dev)
+
+    def _build_buckets(self, bucket_bytes):
+        """Contiguous arena slices in backward order; bucket i is complete after layer `ready_after[i]`."""
+        self.buckets = []
+        start, cur = 0, 0
+        nl = len(self.layers)
+        for li in reversed(range(nl)):
+            cur = self.slots[li]['range'][1]
+            if (cur - start) * 4 >= bucket_bytes or li == 0:
+                self.buckets.append(dict(start=start, end=cur, ready_after=li))
+                start = cur
+
+    # ------------------------------------------------------------------------------------------
+    def set_labels(self, labels):
+        """v1 loss: labels [N,S,S,5+C] as produced by pascal_voc.get() (float64 numpy in the reference,
+        pascal_voc.py:43-46; cast to float32 at the feed like the TF placeholder does)."""
+        assert self.loss_kind == 'v1'
+        self.labels.copy_(torch.as_tensor(np.asarray(labels), dtype=torch.float32), non_blocking=True)
+
+    def set_ground_truth(self, gt_boxes, gt_classes, gt_counts):
+        assert self.loss_kind == 'region'
+        self.gt_boxes.copy_(torch.as_tensor(np.asarray(gt_boxes), dtype=torch.float32), non_blocking=True)
+        self.gt_classes.copy_(torch.as_tensor(np.asarray(gt_classes), dtype=torch.int32), non_blocking=True)
+        self.gt_counts.copy_(torch.as_tensor(np.asarray(gt_counts), dtype=torch.int32), non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self):
+        ops.preprocess_u8(self.in_u8, bf16c8=True, out=self.x0)
+        x = self.x0
+        nl = len(self.layers)
+        for li, L in enumerate(self.layers):
+            g, s, P = self.geom[li], self.stats[li], self.P[li]
+            H, last = g['H'], li == nl - 1
+            ops.pack_weights_bf16(P['W'], out=self.packed[li])
+            raw = self.raw[li]
+            ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], scale=None, shift=P['b'], leaky=False,
+                              pool=False, out_f32=True, ldy=g['ldh'], out=raw)
+            ops.bn_stats(raw, L['cout'], ld=g['ldh'], workspace=self.ws, mean=s['mean'], var=s['var'])
+            if self.update_moving:
+                bn = L['bn']
+                ops.bn_update_moving(self.store[bn['moving_mean']], self.store[bn['moving_variance']], s['mean'], s['var'])
+            ops.bn_fold(P['gamma'], P['beta'], s['zeros'], s['var'], None, scale=s['scale'], shift=s['shift'])
+            ops.affine_leaky_pool(raw, self.N, H, H, L['cout'], ldx=g['ldh'], sub=s['mean'], scale=s['scale'],
+                                  shift=s['shift'], leaky=True, pool=L['pool'], out_bf16=not last, out=self.acts[li])
+            x = self.acts[li]
+        return self.acts[-1]
+
+    def loss(self):
+        net = self.acts[-1]
+        if self.loss_kind == 'v1':
+            ops.loss_v1(net, self.labels, self.S, self.B, self.C, float(self.IS), self.lambda_coord, self.lambda_noobj,
+                        want_grad=True, terms=self.terms, ious=self.ious, object_mask=self.object_mask, dnet=self.dnet)
+        else:
+            ops.region_loss(net, self.anchors, self.gt_boxes, self.gt_classes, self.gt_counts, self.C,
+                            lambda_coord=self.lambda_coord, lambda_noobj=self.lambda_noobj, terms=self.terms,
+                            dnet=self.dnet)
+        return self.terms
+
+    def backward(self, capture=None):
+        """capture: optional dict; receives {layer index: clone of the gradient w.r.t. that layer's output} (tests)."""
+        self.grads.zero_()
+        nl = len(self.layers)
+        dy = self.dnet
+        works = []
+        bucket_i = 0
+        for li in reversed(range(nl)):
+            L, g, s, P, G = self.layers[li], self.geom[li], self.stats[li], self.P[li], self.G[li]
+            H, M, cout, cin, k = g['H'], g['M'], L['cout'], L['cin'], L['k']
+            if capture is not None:
+                capture[li] = dy.clone()
+            dh = self.dh[:M * g['ld_dh']].view(M, g['ld_dh'])
+            ops.bn_leaky_pool_bwd(self.raw[li], dy, s['mean'], s['var'], P['gamma'], P['beta'], self.N, H, H, cout,
+                                  ldh=g['ldh'], leaky=True, pool=L['pool'], ld_dh=g['ld_dh'], dgamma=G['gamma'],
+                                  dbeta=G['beta'], dh=dh, workspace=self.ws)
+            xin = self.x0 if li == 0 else self.acts[li - 1]
+            if li == 0:
+                ops.conv_wgrad_c3(xin, dh, cout, G['W'])
+            else:
+                ops.conv_wgrad_bf16(xin, dh, k, cin, cout, G['W'])
+                ops.pack_weights_dgrad_bf16(P['W'], g['ld_dh'], out=self.packed_dgrad[li])
+                dx = self.dx[li & 1][:M * cin].view(self.N, H, H, cin)
+                ops.conv_fwd_bf16(dh.view(self.N, H, H, g['ld_dh']), self.packed_dgrad[li], k, g['ld_dh'], cin, scale=None,
+                                  shift=None, leaky=False, pool=False, out=dx)
+                dy = dx
+            if self.world > 1 and bucket_i < len(self.buckets) and self.buckets[bucket_i]['ready_after'] == li:
+                b = self.buckets[bucket_i]
+                works.append(torch.distributed.all_reduce(self.grads[b['start']:b['end']], group=self.pg, async_op=True))
+                bucket_i += 1
+        for w in works:
+            w.wait()
+        if self.world > 1:
+            self.grads.mul_(1.0 / self.world)
+
+    def update(self):
+        self.iteration += 1
+        ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.iteration, lr=self.lr, b1=self.beta1,
+                      b2=self.beta2, eps=self.eps)
+        self.store.version += 1
+
+    def step(self, images=None, capture=None):
+        """One training iteration on the current stream.  images: uint8 [N,IS,IS,3] BGR (host or device) or None
+        to reuse self.in_u8.  Returns the device tensor terms[5] (the loss is terms[4])."""
+        if images is not None:
+            self.in_u8.copy_(torch.as_tensor(images), non_blocking=True)
+        self.forward()
+        self.loss()
+        self.backward(capture)
+        self.update()
+        return self.terms
+
+    # helpers for tests / checkpoints
+    def gradient(self, li, key):
+        return self.G[li][key]
+
+    def num_parameters(self):
+        return sum(sl[k][1] for sl in self.slots for k in ('W', 'b', 'gamma', 'beta'))
