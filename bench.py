@@ -12,8 +12,9 @@ batch-statistics mode -- the reference detect script's graph).  Prints ONE JSON 
 
 value      device-timed throughput with the batch already resident in HBM (CUDA events per step on
            the launching stream, L2 flushed between steps, max over ranks).
-e2e        same metric through Yolo2Engine.infer(): pinned host uint8 batch -> H2D -> step -> D2H of
-           the detections, copies inside the timed region.
+e2e        same metric through Yolo2Engine.submit(): pinned host uint8 batch -> H2D -> step -> D2H of
+           the detections, every copy inside the timed region (the H2D of batch i+1 runs on a copy
+           stream and overlaps the kernels of batch i, as a serving loop would).
 roofline   tensor-core bound: algorithmic conv FLOPs of one step / summed conv-kernel time per step,
            measured live with CUDA events around each conv launch, vs MEASURED_PEAKS.json.
 cpu_baseline  the oracle (CPU restatement of the reference, PyTorch-CPU fp32) on a bounded sample.
@@ -60,47 +61,57 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle reasons DURING the timed region, sampled in-process through NVML every 20 ms (the
+    B200_PROFILING.md recipe's nvidia-smi query, without a subprocess' start-up latency)."""
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.samples, self.reasons, self.maxclk = index, [], set(), None
+        self._stop = None
+        self._thr = None
 
     def start(self):
+        import threading
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = 'GPU-' + str(torch.cuda.get_device_properties(self.index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.maxclk = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            return
+        names = dict(hw_slowdown=0x8, hw_thermal_slowdown=0x40, sw_thermal_slowdown=0x20, sw_power_cap=0x4)   # NVML reason bits
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    try:
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+                self._stop.wait(0.02)
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.proc is None:
+        if self._thr is None:
             return None
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
+        self._stop.set()
+        self._thr.join(timeout=2)
+        if not self.samples:
             return None
-        sm, mx, reasons = [], [], set()
-        for ln in out.strip().splitlines():
-            f = [x.strip() for x in ln.split(',')]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        if not sm:
-            return None
-        # under-load samples: the top half of the observed clocks
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=statistics.median(self.samples), sm_min_mhz=min(self.samples), sm_max_mhz=self.maxclk,
+                    reasons=sorted(self.reasons), samples=len(self.samples))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -224,11 +235,7 @@ def run_ours(args):
     d2h = sum(t.numel() * t.element_size() for t in res_host.values())
 
     def e2e_step(i):
-        eng.in_u8.copy_(host_batches[i % len(host_batches)], non_blocking=True)
-        eng.run()
-        res_host['keep_idx'].copy_(eng.keep_idx, non_blocking=True)
-        res_host['keep_count'].copy_(eng.keep_count, non_blocking=True)
-        res_host['boxes'].copy_(eng.boxes, non_blocking=True)
+        eng.submit(host_batches[i % len(host_batches)], res_host)     # H2D (copy stream) | step | D2H, pipelined
 
     for i in range(3):
         e2e_step(i)
@@ -323,7 +330,7 @@ def conv_kernel_times(eng, ops, iters=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -84,15 +84,107 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ h, int ldh, const
   }
 }
 
+// Vectorised pass 1 (C % 4 == 0): a thread owns 4 channels (16-byte loads of h, 8-byte loads of bf16 dy) and keeps
+// UNR units in flight; block = TX channel groups x (256/TX) unit lanes.
+template <bool POOL, int TX>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_v4_kernel(
+    const float* __restrict__ h, int ldh, const void* __restrict__ dy, int dy_f32, const float* __restrict__ mean,
+    const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float alpha,
+    int leaky_on, int H, int W, int C, size_t units, size_t units_per_split, double* __restrict__ part) {
+  constexpr int TY = 256 / TX;
+  constexpr int NR = POOL ? 4 : 1;
+  constexpr int UNR = POOL ? 2 : 4;
+  __shared__ double sm[TY][TX][8];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int c0 = (blockIdx.x * TX + tx) * 4;
+  const size_t u0 = (size_t)blockIdx.y * units_per_split, u1 = min(units, u0 + units_per_split);
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c0), vr = *reinterpret_cast<const float4*>(var + c0);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c0), b = *reinterpret_cast<const float4*>(beta + c0);
+    const float pm[4] = {mu.x, mu.y, mu.z, mu.w};
+    const float pi[4] = {rsqrtf(vr.x + eps), rsqrtf(vr.y + eps), rsqrtf(vr.z + eps), rsqrtf(vr.w + eps)};
+    const float pg[4] = {g.x, g.y, g.z, g.w}, pb[4] = {b.x, b.y, b.z, b.w};
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (size_t ub = u0 + ty; ub < u1; ub += (size_t)UNR * TY) {
+      float4 hv[UNR][NR];
+      float dv[UNR][4];
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t u = ub + (size_t)j * TY;
+        if (u < u1) {
+          const UnitRows ur = unit_rows(u, H, W, POOL);
+#pragma unroll
+          for (int k = 0; k < NR; ++k) hv[j][k] = __ldg(reinterpret_cast<const float4*>(h + ur.r[k] * ldh + c0));
+          if (dy_f32) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + u * C + c0));
+            dv[j][0] = q.x; dv[j][1] = q.y; dv[j][2] = q.z; dv[j][3] = q.w;
+          } else {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + u * C + c0));
+            const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&q.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+            dv[j][0] = __low2float(lo); dv[j][1] = __high2float(lo); dv[j][2] = __low2float(hi); dv[j][3] = __high2float(hi);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < NR; ++k) hv[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.0f;          // contributes nothing
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float best = -INFINITY, bx = 0.0f, bz = 0.0f;
+#pragma unroll
+          for (int k = 0; k < NR; ++k) {
+            const float t = v == 0 ? hv[j][k].x : (v == 1 ? hv[j][k].y : (v == 2 ? hv[j][k].z : hv[j][k].w));
+            const float xh = (t - pm[v]) * pi[v];
+            const float z = xh * pg[v] + pb[v];
+            const float a = leaky_on ? fmaxf(z, alpha * z) : z;
+            if (a > best) { best = a; bx = xh; bz = z; }
+          }
+          float d = dv[j][v];
+          if (leaky_on && !(bz > 0.0f)) d *= alpha;
+          f[v] += d;
+          f[4 + v] = fmaf(d, bx, f[4 + v]);
+        }
+      }
+      if (++cnt == 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i] += (double)f[i]; f[i] = 0.0f; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += (double)f[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[ty][tx][i] = acc[i];
+  __syncthreads();
+  if (ty < 8 && c0 < C) {
+    double a = 0.0;
+    for (int y = 0; y < TY; ++y) a += sm[y][tx][ty];
+    part[((size_t)blockIdx.y * C + c0 + (ty & 3)) * 2 + (ty >> 2)] = a;
+  }
+}
+
 __global__ void bn_bwd_final_kernel(const double* __restrict__ part, int splits, int C, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double s1[8][33], s2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   double a1 = 0.0, a2 = 0.0;
-  for (int s = 0; s < splits; ++s) {
-    a1 += part[((size_t)s * C + c) * 2 + 0];
-    a2 += part[((size_t)s * C + c) * 2 + 1];
-  }
+  if (c < C)
+    for (int s = threadIdx.y; s < splits; s += 8) {
+      const double2 p = *reinterpret_cast<const double2*>(part + ((size_t)s * C + c) * 2);
+      a1 += p.x;
+      a2 += p.y;
+    }
+  s1[threadIdx.y][threadIdx.x] = a1;
+  s2[threadIdx.y][threadIdx.x] = a2;
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= C) return;
+  for (int y = 1; y < 8; ++y) { a1 += s1[y][threadIdx.x]; a2 += s2[y][threadIdx.x]; }
   dbeta[c] = (float)a1;
   dgamma[c] = (float)a2;
 }
@@ -304,8 +396,8 @@ __global__ void sum_rows_bf16_kernel(const __nv_bfloat16* __restrict__ a, int ld
 }
 
 static int bwd_splits(size_t units) {
-  size_t s = (units + 255) / 256;
-  return (int)(s > 592 ? 592 : (s < 1 ? 1 : s));
+  size_t s = (units + 127) / 128;
+  return (int)(s > 1024 ? 1024 : (s < 1 ? 1 : s));
 }
 
 }  // namespace y2
@@ -329,16 +421,26 @@ int y2_bn_leaky_pool_bwd(const float* h_raw, int ldh, const void* dy, int dy_dty
     set_error("y2_bn_leaky_pool_bwd: workspace too small (%zu < %zu)", workspace_bytes, y2_bn_bwd_workspace_bytes((int)M, C));
     return Y2_ERR_WORKSPACE;
   }
-  Y2_ARG(((uintptr_t)workspace & 7) == 0);
+  Y2_ARG(((uintptr_t)workspace & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   int splits = bwd_splits(units);
   size_t ups = (units + splits - 1) / splits;
   splits = (int)((units + ups - 1) / ups);
-  dim3 grid((C + 31) / 32, splits), block(32, 8);
-  bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(h_raw, ldh, dy, dy_dtype == 0, mean, var, gamma, beta, eps, alpha, leaky_on,
-                                               pool, H, W, C, units, ups, (double*)workspace);
+  if (C % 4 == 0 && ldh % 4 == 0 && (((uintptr_t)h_raw) & 15) == 0 && (((uintptr_t)dy) & 15) == 0) {
+    const int cg = C / 4;
+#define Y2_LAUNCH_RED(POOL_, TX_)                                                                                     \
+  bn_bwd_reduce_v4_kernel<POOL_, TX_><<<dim3((cg + TX_ - 1) / TX_, splits), 256, 0, st>>>(                            \
+      h_raw, ldh, dy, dy_dtype == 0, mean, var, gamma, beta, eps, alpha, leaky_on, H, W, C, units, ups, (double*)workspace)
+    if (pool) { if (cg <= 8) Y2_LAUNCH_RED(true, 8); else if (cg <= 16) Y2_LAUNCH_RED(true, 16); else Y2_LAUNCH_RED(true, 32); }
+    else      { if (cg <= 8) Y2_LAUNCH_RED(false, 8); else if (cg <= 16) Y2_LAUNCH_RED(false, 16); else Y2_LAUNCH_RED(false, 32); }
+#undef Y2_LAUNCH_RED
+  } else {
+    dim3 grid((C + 31) / 32, splits), block(32, 8);
+    bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(h_raw, ldh, dy, dy_dtype == 0, mean, var, gamma, beta, eps, alpha, leaky_on,
+                                                 pool, H, W, C, units, ups, (double*)workspace);
+  }
   Y2_LAUNCHED();
-  bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, st>>>((const double*)workspace, splits, C, dgamma, dbeta);
+  bn_bwd_final_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>((const double*)workspace, splits, C, dgamma, dbeta);
   Y2_LAUNCHED();
   const bool vec4 = (ld_dh % 4 == 0) && (ldh % 4 == 0) && (((uintptr_t)h_raw & 15) == 0) && (((uintptr_t)dh_bf16 & 7) == 0);
   const float invM = 1.0f / (float)M;

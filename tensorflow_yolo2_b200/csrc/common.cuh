@@ -26,6 +26,7 @@ void count_launch(int n = 1);
     cudaError_t e__ = (expr);                                                     \
     if (e__ != cudaSuccess) {                                                     \
       y2::set_error("%s: %s -> %s", __func__, #expr, cudaGetErrorString(e__));    \
+      (void)cudaGetLastError(); /* non-sticky errors must not leak into the caller's next CUDA call */ \
       return (int)e__;                                                            \
     }                                                                             \
   } while (0)

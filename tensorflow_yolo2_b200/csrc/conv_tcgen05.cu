@@ -776,6 +776,8 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
     };
     if (cost(256) <= cost(128)) block_n = 256;
   }
+  // halo-patch mode keeps three taps of B per stage: 256-wide tiles would leave room for a single stage
+  if (a.a_mode == 2 && block_n == 256) block_n = 128;
   if (const char* e = getenv("Y2_CONV_BLOCK_N")) {
     int v = atoi(e);
     if ((v == 128 || v == 256) && cout_p >= v && !a.first_layer) block_n = v;
@@ -842,7 +844,10 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   const size_t b_region = a.b_stationary ? (((size_t)a.b_total_bytes + 1023) & ~(size_t)1023) : 0;
   int stages = (int)((SMEM_BUDGET - b_region) / stage_bytes);
   if (stages > 12) stages = 12;
-  if (stages < 2) stages = 2;
+  if (stages < 2) {
+    set_error("y2_conv_fwd_bf16: tile configuration needs %u B per stage; fewer than 2 stages fit", stage_bytes);
+    return Y2_ERR_UNSUPPORTED;
+  }
   a.stages = stages;
   size_t smem = b_region + (size_t)stages * stage_bytes + 1024;
 

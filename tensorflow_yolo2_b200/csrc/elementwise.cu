@@ -116,15 +116,73 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ x, int M, int 
   }
 }
 
+// Vectorised variant (C % 4 == 0): a thread owns 4 consecutive channels (16-byte loads) and keeps four rows in
+// flight; block = TX channel groups x (256/TX) row lanes, so narrow layers (C = 32) still fill 256 threads.
+template <int TX>
+__global__ void __launch_bounds__(256) bn_stats_partial_v4_kernel(const float* __restrict__ x, int M, int C, int ld,
+                                                                  int rows_per_split, double* __restrict__ part) {
+  constexpr int TY = 256 / TX;
+  __shared__ double sm[TY][TX][8];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int c0 = (blockIdx.x * TX + tx) * 4;
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(M, r0 + rows_per_split);
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C) {
+    const float4 k = *reinterpret_cast<const float4*>(x + c0);
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (int rb = r0 + ty; rb < r1; rb += 4 * TY) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = rb + j * TY;
+        v[j] = r < r1 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ld + c0)) : k;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d0 = v[j].x - k.x, d1 = v[j].y - k.y, d2 = v[j].z - k.z, d3 = v[j].w - k.w;
+        f[0] += d0; f[1] += d1; f[2] += d2; f[3] += d3;
+        f[4] = fmaf(d0, d0, f[4]); f[5] = fmaf(d1, d1, f[5]); f[6] = fmaf(d2, d2, f[6]); f[7] = fmaf(d3, d3, f[7]);
+      }
+      if (++cnt == 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i] += (double)f[i]; f[i] = 0.0f; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += (double)f[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[ty][tx][i] = acc[i];
+  __syncthreads();
+  // fold the TY row lanes: thread (tx, i = ty < 8) handles one of the 8 sums
+  if (ty < 8 && c0 < C) {
+    double a = 0.0;
+    for (int y = 0; y < TY; ++y) a += sm[y][tx][ty];
+    const int c = c0 + (ty & 3);
+    part[((size_t)blockIdx.y * C + c) * 2 + (ty >> 2)] = a;
+  }
+}
+
+// grid ceil(C/32), block (32, 8): the 8 thread rows fold interleaved subsets of the splits (fixed order ->
+// deterministic), then one row folds the 8 partials.
 __global__ void bn_stats_final_kernel(const float* __restrict__ x, const double* __restrict__ part, int splits, int M,
                                       int C, float* __restrict__ mean, float* __restrict__ var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double s1[8][33], s2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   double a1 = 0.0, a2 = 0.0;
-  for (int s = 0; s < splits; ++s) {
-    a1 += part[((size_t)s * C + c) * 2 + 0];
-    a2 += part[((size_t)s * C + c) * 2 + 1];
-  }
+  if (c < C)
+    for (int s = threadIdx.y; s < splits; s += 8) {
+      const double2 p = *reinterpret_cast<const double2*>(part + ((size_t)s * C + c) * 2);
+      a1 += p.x;
+      a2 += p.y;
+    }
+  s1[threadIdx.y][threadIdx.x] = a1;
+  s2[threadIdx.y][threadIdx.x] = a2;
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= C) return;
+  for (int y = 1; y < 8; ++y) { a1 += s1[y][threadIdx.x]; a2 += s2[y][threadIdx.x]; }
   double md = a1 / (double)M;
   double v = a2 / (double)M - md * md;
   if (v < 0.0) v = 0.0;
@@ -299,8 +357,8 @@ int y2_pack_weights_bf16(const float* w_hwio, void* w_packed, int ksize, int Cin
 }
 
 static int bn_splits(int M) {
-  int s = (M + 255) / 256;
-  return s > 512 ? 512 : (s < 1 ? 1 : s);
+  int s = (M + 127) / 128;
+  return s > 1024 ? 1024 : (s < 1 ? 1 : s);
 }
 
 size_t y2_bn_stats_workspace_bytes(int M, int C) { return (size_t)bn_splits(M) * C * 2 * sizeof(double); }
@@ -312,15 +370,22 @@ int y2_bn_stats(const float* x, int M, int C, int ld, float* mean, float* var, v
     set_error("y2_bn_stats: workspace too small (%zu < %zu)", workspace_bytes, y2_bn_stats_workspace_bytes(M, C));
     return Y2_ERR_WORKSPACE;
   }
-  Y2_ARG(((uintptr_t)workspace & 7) == 0);
+  Y2_ARG(((uintptr_t)workspace & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   int splits = bn_splits(M);
   int rows = (M + splits - 1) / splits;
   splits = (M + rows - 1) / rows;
-  dim3 grid((C + 31) / 32, splits), block(32, 8);
-  bn_stats_partial_kernel<<<grid, block, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
+  if (C % 4 == 0 && ld % 4 == 0 && (((uintptr_t)x) & 15) == 0) {
+    const int cg = C / 4;
+    if (cg <= 8) bn_stats_partial_v4_kernel<8><<<dim3((cg + 7) / 8, splits), 256, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
+    else if (cg <= 16) bn_stats_partial_v4_kernel<16><<<dim3(1, splits), 256, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
+    else bn_stats_partial_v4_kernel<32><<<dim3((cg + 31) / 32, splits), 256, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
+  } else {
+    dim3 grid((C + 31) / 32, splits), block(32, 8);
+    bn_stats_partial_kernel<<<grid, block, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
+  }
   Y2_LAUNCHED();
-  bn_stats_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(x, (const double*)workspace, splits, M, C, mean, var);
+  bn_stats_final_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(x, (const double*)workspace, splits, M, C, mean, var);
   Y2_LAUNCHED();
   return Y2_OK;
 }

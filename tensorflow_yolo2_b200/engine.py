@@ -188,6 +188,45 @@ class Yolo2Engine:
             self.graph = g
         self.graph.replay()
 
+    # ------------------------------------------------------------------------------------------
+    # pipelined serving path: H2D of batch i+1 overlaps the compute of batch i
+    # ------------------------------------------------------------------------------------------
+    def _pipeline_init(self):
+        dev = self.device
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        src = self.in_u8 if self.input_kind == 'u8' else self.in_f32
+        self._staging = [torch.empty_like(src) for _ in range(2)]
+        self._ready = [torch.cuda.Event() for _ in range(2)]
+        self._free = [torch.cuda.Event() for _ in range(2)]
+        self._slot = 0
+        for e in self._free:
+            e.record(torch.cuda.current_stream(dev))
+
+    def submit(self, host_images, out_host=None):
+        """Enqueue one batch from (pinned) host memory: the host->device copy runs on a copy stream into one of two
+        staging buffers, so it overlaps the previous batch's kernels; the step itself and the device->host copy of
+        the detections (into `out_host`: dict of pinned tensors keyed keep_idx / keep_count / boxes / scores / net)
+        run on the current stream.  Returns immediately; synchronise the current stream before reading `out_host`."""
+        if not hasattr(self, '_copy_stream'):
+            self._pipeline_init()
+        cur = torch.cuda.current_stream(self.device)
+        i = self._slot
+        self._slot ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._free[i])
+            self._staging[i].copy_(torch.as_tensor(host_images), non_blocking=True)
+            self._ready[i].record(self._copy_stream)
+        cur.wait_event(self._ready[i])
+        (self.in_u8 if self.input_kind == 'u8' else self.in_f32).copy_(self._staging[i], non_blocking=True)
+        self._free[i].record(cur)
+        self.run()
+        if out_host is not None:
+            srcs = dict(net=self.acts[-1])
+            if self.decode == 'region':
+                srcs.update(boxes=self.boxes, scores=self.scores, keep_idx=self.keep_idx, keep_count=self.keep_count)
+            for k, dst in out_host.items():
+                dst.copy_(srcs[k], non_blocking=True)
+
     @property
     def net_out(self):
         return self.acts[-1]

@@ -30,6 +30,7 @@ import torch
 
 from . import ops
 from .engine import create_variables
+from .parallel import BucketedAllReduce, make_buckets
 from .variables import VariableStore
 from .yolo2_nets.net_utils import VOC_ANCHORS
 
@@ -168,15 +169,10 @@ class Yolo2Trainer:
             self.gt_counts = torch.zeros((N,), dtype=torch.int32, device=dev)
 
     def _build_buckets(self, bucket_bytes):
-        """Contiguous arena slices in backward order; bucket i is complete after layer `ready_after[i]`."""
-        self.buckets = []
-        start, cur = 0, 0
-        nl = len(self.layers)
-        for li in reversed(range(nl)):
-            cur = self.slots[li]['range'][1]
-            if (cur - start) * 4 >= bucket_bytes or li == 0:
-                self.buckets.append(dict(start=start, end=cur, ready_after=li))
-                start = cur
+        """Contiguous arena slices in backward order; a bucket is launched once its last layer's gradients are enqueued."""
+        ranges = [(li,) + self.slots[li]['range'] for li in reversed(range(len(self.layers)))]
+        self.buckets = make_buckets(ranges, bucket_bytes)
+        self.reducer = BucketedAllReduce(self.grads, self.buckets, self.pg, self.world)
 
     # ------------------------------------------------------------------------------------------
     def set_labels(self, labels):
@@ -229,8 +225,7 @@ class Yolo2Trainer:
         self.grads.zero_()
         nl = len(self.layers)
         dy = self.dnet
-        works = []
-        bucket_i = 0
+        self.reducer.begin()
         for li in reversed(range(nl)):
             L, g, s, P, G = self.layers[li], self.geom[li], self.stats[li], self.P[li], self.G[li]
             H, M, cout, cin, k = g['H'], g['M'], L['cout'], L['cin'], L['k']
@@ -250,14 +245,8 @@ class Yolo2Trainer:
                 ops.conv_fwd_bf16(dh.view(self.N, H, H, g['ld_dh']), self.packed_dgrad[li], k, g['ld_dh'], cin, scale=None,
                                   shift=None, leaky=False, pool=False, out=dx)
                 dy = dx
-            if self.world > 1 and bucket_i < len(self.buckets) and self.buckets[bucket_i]['ready_after'] == li:
-                b = self.buckets[bucket_i]
-                works.append(torch.distributed.all_reduce(self.grads[b['start']:b['end']], group=self.pg, async_op=True))
-                bucket_i += 1
-        for w in works:
-            w.wait()
-        if self.world > 1:
-            self.grads.mul_(1.0 / self.world)
+            self.reducer.layer_done(li)
+        self.reducer.finish()
 
     def update(self):
         self.iteration += 1

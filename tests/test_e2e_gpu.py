@@ -144,3 +144,58 @@ def test_engine_full_size_416_batch8_vs_fp32_path(fresh):
     print('tensor-core engine vs fp32 path at 416x416 batch 8: rel_l2=%.3g' % err)
     assert err < 6e-2, err            # bf16 operands through 22 layers vs fp32 (documented in DESIGN.md)
     assert r['net'].shape == (N, 13, 13, 125)
+
+
+def test_engine_608_config4_detections(fresh):
+    """BASELINE.json configs[3]: 608x608 -> 19x19 grid, 1805 boxes per image (batch 2 here): tensor-core engine vs
+    the exact fp32 kernels, and decode + NMS bit-exact against the oracle on the engine's own network output."""
+    from tensorflow_yolo2_b200.engine import Yolo2Engine
+    from tensorflow_yolo2_b200.yolo2_nets.darknet import darknet19_core, darknet19_detection
+    st, layers = make_store(125, tame=True)
+    N, IS = 2, 608
+    img = np.random.RandomState(8).randint(0, 256, (N, IS, IS, 3)).astype(np.uint8)
+    eng = Yolo2Engine(N, IS, 125, store=st, score_thresh=0.02, use_cuda_graph=True)
+    r = eng.infer(torch.tensor(img))
+    torch.cuda.synchronize()
+    assert r['net'].shape == (N, 19, 19, 125) and r['boxes'].shape == (N, 1805, 4)
+    fresh.COMPUTE = 'fp32'
+    _install(st)
+    want = darknet19_detection(darknet19_core(torch.tensor(O.preprocess_u8(img)).cuda(), is_training=False), 125)
+    fresh.COMPUTE = 'bf16'
+    err = rel_l2(r['net'].cpu().numpy(), want.cpu().numpy())
+    print('608x608 tensor-core engine vs fp32 path: rel_l2=%.3g' % err)
+    assert err < 6e-2
+    net = r['net'].cpu().numpy()
+    wb, _, _ = O.region_decode_v2(net, O.VOC_ANCHORS, 20, 0.02)
+    np.testing.assert_allclose(r['boxes'].cpu().numpy(), wb, rtol=1e-5, atol=1e-7)
+    boxes, scores = r['boxes'].cpu().numpy(), r['scores'].cpu().numpy()
+    ki, kc = r['keep_idx'].cpu().numpy(), r['keep_count'].cpu().numpy()
+    total = 0
+    for n in range(N):
+        keeps = O.nms_per_class(boxes[n], scores[n], 0.45, 0.02)
+        for k in range(20):
+            assert kc[n, k] == len(keeps[k])
+            np.testing.assert_array_equal(ki[n, k, :kc[n, k]], keeps[k])
+            total += len(keeps[k])
+    assert total > 0
+
+
+def test_engine_pipelined_submit_equals_infer(fresh):
+    from tensorflow_yolo2_b200.engine import Yolo2Engine
+    st, _ = make_store(125, tame=True)
+    N, IS = 2, 96
+    eng = Yolo2Engine(N, IS, 125, store=st, score_thresh=0.05, use_cuda_graph=True)
+    rs = np.random.RandomState(11)
+    batches = [torch.tensor(rs.randint(0, 256, (N, IS, IS, 3)).astype(np.uint8)).pin_memory() for _ in range(3)]
+    want = []
+    for b in batches:
+        r = eng.infer(b)
+        torch.cuda.synchronize()
+        want.append((r['net'].cpu().clone(), r['keep_count'].cpu().clone()))
+    outs = [dict(net=torch.empty((N, 3, 3, 125)).pin_memory(), keep_count=torch.empty((N, 20), dtype=torch.int32).pin_memory())
+            for _ in batches]
+    for b, o in zip(batches, outs):
+        eng.submit(b, o)
+    torch.cuda.synchronize()
+    for (wn, wk), o in zip(want, outs):
+        assert torch.equal(wn, o['net']) and torch.equal(wk, o['keep_count'])

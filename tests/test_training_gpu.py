@@ -257,3 +257,18 @@ def test_training_loss_decreases(ops):
     losses = [float(tr.step(img)[4]) for _ in range(12)]
     print(losses)
     assert losses[-1] < 0.7 * losses[0]
+
+
+def test_ddp_two_gpus_matches_mean_of_shard_gradients():
+    """World-size-2 NCCL run of tools/ddp_check.py (skipped on a single-GPU box)."""
+    import subprocess
+    import sys
+    import os
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.join(root, 'tools', 'ddp_check.py')],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and 'OK' in r.stdout
