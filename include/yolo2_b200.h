@@ -134,6 +134,15 @@ int y2_nms(const float* boxes, const float* scores, int N, int nbox, int C, floa
            float iou_thresh, int32_t* keep_idx, int32_t* keep_count, int max_keep,
            void* workspace, size_t workspace_bytes, y2_stream_t stream);
 
+/* ---- a': decode + threshold + per-class NMS fused, one CTA per image (same results as y2_decode_region + y2_nms) -
+ * net [N,S,S,A*(5+C)] f32 -> boxes [N,S*S*A,4]; scores [N,S*S*A,C] dense thresholded scores (optional, NULL to skip;
+ * needed for the overflow path: images with > 2048 candidates are re-done by the y2_nms kernel -- without `scores`
+ * such images report keep_count = -1); keep_idx [N,C,max_keep], keep_count [N,C]; keep_score [N,C,max_keep]
+ * (optional) = score of each kept box.  C must be 20 and S*S*A <= 4095. */
+int y2_detect_fused(const float* net, const float* anchors, int N, int S, int A, int C, float score_thresh,
+                    float iou_thresh, float* boxes, float* scores, int32_t* keep_idx, int32_t* keep_count,
+                    float* keep_score, int max_keep, y2_stream_t stream);
+
 /* ---- a7: IoU of n box pairs (yolo2_nets/net_utils.py:222-260 get_iou) ------------------------
  * boxes1/boxes2 [n,4] (cx,cy,w,h) f32 -> iou [n]; float32 in the reference's op order. */
 int y2_iou(const float* boxes1, const float* boxes2, float* iou, size_t n, y2_stream_t stream);

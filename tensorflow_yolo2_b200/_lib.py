@@ -43,6 +43,7 @@ _SIGNATURES = {
     'y2_decode_region': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     'y2_nms_workspace_bytes': (_sz, [_i, _i, _i]),
     'y2_nms': (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _i, _vp, _sz, _vp]),
+    'y2_detect_fused': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'y2_iou': (_i, [_vp, _vp, _vp, _sz, _vp]),
     'y2_loss_v1_workspace_bytes': (_sz, [_i, _i]),
     'y2_loss_v1_fwd_bwd': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

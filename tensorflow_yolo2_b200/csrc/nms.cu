@@ -8,49 +8,26 @@
 // IoU uses the op order of yolo2_nets/net_utils.py:231-260 with explicitly rounded float32 ops
 // (no FMA contraction), so keep lists are bit-identical to the NumPy oracle.
 // Candidates beyond the bit-matrix capacity (n > NMS_MAX_MATRIX) fall back to an on-the-fly sweep.
-#include "common.cuh"
+#include "nms_common.cuh"
 
 namespace y2 {
 
 constexpr int NMS_THREADS = 256;
 constexpr int NMS_MAX_MATRIX = 1024;   // 32 lanes x 32 bits
 
-struct Corner { float x1, y1, x2, y2, area; };
-
-__device__ __forceinline__ Corner to_corner(float4 b) {
-  Corner c;
-  float hw = __fdiv_rn(b.z, 2.0f), hh = __fdiv_rn(b.w, 2.0f);
-  c.x1 = __fsub_rn(b.x, hw);
-  c.y1 = __fsub_rn(b.y, hh);
-  c.x2 = __fadd_rn(b.x, hw);
-  c.y2 = __fadd_rn(b.y, hh);
-  c.area = __fmul_rn(__fsub_rn(c.x2, c.x1), __fsub_rn(c.y2, c.y1));
-  return c;
-}
-
-__device__ __forceinline__ float iou_corner(const Corner& a, const Corner& b) {
-  float lux = fmaxf(a.x1, b.x1), luy = fmaxf(a.y1, b.y1);
-  float rdx = fminf(a.x2, b.x2), rdy = fminf(a.y2, b.y2);
-  float iw = fmaxf(0.0f, __fsub_rn(rdx, lux)), ih = fmaxf(0.0f, __fsub_rn(rdy, luy));
-  float inter = __fmul_rn(iw, ih);
-  float uni = fmaxf(__fsub_rn(__fadd_rn(a.area, b.area), inter), 1e-10f);
-  float q = __fdiv_rn(inter, uni);
-  return fminf(fmaxf(q, 0.0f), 1.0f);
-}
-
 // smem layout (dynamic): keys[P] u64 | corners[n] (5 floats) | matrix[n * words] u32
-__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const float* __restrict__ boxes,
-                                                          const float* __restrict__ scores, int nbox, int C,
-                                                          float score_thresh, float iou_thresh,
-                                                          int32_t* __restrict__ keep_idx,
-                                                          int32_t* __restrict__ keep_count, int max_keep, int P) {
+__device__ __forceinline__ void nms_body(const float* __restrict__ boxes, const float* __restrict__ scores, int nbox, int C,
+                                         float score_thresh, float iou_thresh, int32_t* __restrict__ keep_idx,
+                                         int32_t* __restrict__ keep_count, float* __restrict__ keep_score, int max_keep,
+                                         int P, int unit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_n;
   __shared__ int s_count;
   __shared__ int s_next;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
   const int tid = threadIdx.x;
-  const int img = blockIdx.x / C, k = blockIdx.x % C;
+  const int img = unit / C, k = unit % C;
+  __syncthreads();                                   // a previous unit of this CTA may still be reading the shared state
   const float* sc = scores + (size_t)img * nbox * C + k;
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)img * nbox;
 
@@ -68,7 +45,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const float* __restric
   __syncthreads();
   const int n = s_n;
   if (n == 0) {
-    if (tid == 0) keep_count[blockIdx.x] = 0;
+    if (tid == 0) keep_count[unit] = 0;
     return;
   }
   // 2. bitonic sort over the smallest power of two >= n
@@ -89,7 +66,8 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const float* __restric
   Corner* corners = reinterpret_cast<Corner*>(smem_raw + (size_t)P * 8);
   for (int i = tid; i < n; i += NMS_THREADS) corners[i] = to_corner(bx[(unsigned)(keys[i] & 0xffffffffu)]);
   __syncthreads();
-  int32_t* out = keep_idx + (size_t)blockIdx.x * max_keep;
+  int32_t* out = keep_idx + (size_t)unit * max_keep;
+  float* outs = keep_score ? keep_score + (size_t)unit * max_keep : nullptr;
 
   if (n <= NMS_MAX_MATRIX) {
     // 3. suppression matrix, upper triangle only: row i, word w covers j = 32w..32w+31, j > i
@@ -127,12 +105,15 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const float* __restric
         int wl = __ffs(ball) - 1;
         unsigned aw = __shfl_sync(0xffffffffu, alive, wl);
         int i = 32 * wl + (__ffs(aw) - 1);
-        if (lane == 0 && count < max_keep) out[count] = (int32_t)(keys[i] & 0xffffffffu);
+        if (lane == 0 && count < max_keep) {
+          out[count] = (int32_t)(keys[i] & 0xffffffffu);
+          if (outs) outs[count] = __uint_as_float(~(unsigned)(keys[i] >> 32));
+        }
         ++count;
         if (lane < words) removed |= mat[i * words + lane];
         if (lane == wl) removed |= 1u << (i & 31);   // visited
       }
-      if (lane == 0) keep_count[blockIdx.x] = count;
+      if (lane == 0) keep_count[unit] = count;
     }
   } else {
     // fallback: removed-bit array in smem, one block-wide pass per kept candidate
@@ -147,7 +128,10 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const float* __restric
         while (i < n && ((removed[i >> 5] >> (i & 31)) & 1u)) ++i;
         s_next = i;
         if (i < n) {
-          if (s_count < max_keep) out[s_count] = (int32_t)(keys[i] & 0xffffffffu);
+          if (s_count < max_keep) {
+            out[s_count] = (int32_t)(keys[i] & 0xffffffffu);
+            if (outs) outs[s_count] = __uint_as_float(~(unsigned)(keys[i] >> 32));
+          }
           ++s_count;
         }
       }
@@ -160,7 +144,30 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const float* __restric
       cur = i + 1;
       __syncthreads();
     }
-    if (tid == 0) keep_count[blockIdx.x] = s_count;
+    if (tid == 0) keep_count[unit] = s_count;
+  }
+}
+
+__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                                                          int nbox, int C, float score_thresh, float iou_thresh,
+                                                          int32_t* __restrict__ keep_idx, int32_t* __restrict__ keep_count,
+                                                          int max_keep, int P) {
+  nms_body(boxes, scores, nbox, C, score_thresh, iou_thresh, keep_idx, keep_count, nullptr, max_keep, P, (int)blockIdx.x);
+}
+
+// y2_detect_fused hand-over: persistent CTAs walk the images and redo only those flagged keep_count[img][0] < 0
+// (more candidates than the fused kernel's list holds).  Normally nothing is flagged and every CTA exits at once.
+__global__ void __launch_bounds__(NMS_THREADS) nms_flagged_kernel(const float* __restrict__ boxes,
+                                                                  const float* __restrict__ scores, int N, int nbox, int C,
+                                                                  float score_thresh, float iou_thresh,
+                                                                  int32_t* __restrict__ keep_idx,
+                                                                  int32_t* __restrict__ keep_count,
+                                                                  float* __restrict__ keep_score, int max_keep, int P) {
+  for (int img = blockIdx.x; img < N; img += gridDim.x) {
+    if (keep_count[(size_t)img * C] >= 0) continue;          // uniform across the CTA; written by an earlier kernel
+    __syncthreads();                                         // everyone has seen the flag before class 0 overwrites it
+    for (int k = 0; k < C; ++k)
+      nms_body(boxes, scores, nbox, C, score_thresh, iou_thresh, keep_idx, keep_count, keep_score, max_keep, P, img * C + k);
   }
 }
 
@@ -173,6 +180,26 @@ static size_t nms_smem_bytes(int nbox, int* P_out) {
   size_t mat = (size_t)nm * ((nm + 31) / 32) * 4;
   size_t rem = (size_t)((nbox + 31) / 32) * 4;
   return (size_t)P * 8 + corners + (mat > rem ? mat : rem);
+}
+
+int launch_nms_flagged(const float* boxes, const float* scores, int N, int nbox, int C, float score_thresh, float iou_thresh,
+                       int32_t* keep_idx, int32_t* keep_count, float* keep_score, int max_keep, cudaStream_t st) {
+  int P;
+  size_t smem = nms_smem_bytes(nbox, &P);
+  if (smem > 200 * 1024) {
+    set_error("y2_detect_fused: nbox=%d needs %zu B of shared memory in the overflow path", nbox, smem);
+    return Y2_ERR_UNSUPPORTED;
+  }
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    Y2_CUDA(cudaFuncSetAttribute(nms_flagged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int grid = N < 148 ? N : 148;
+  nms_flagged_kernel<<<grid, NMS_THREADS, smem, st>>>(boxes, scores, N, nbox, C, score_thresh, iou_thresh, keep_idx,
+                                                      keep_count, keep_score, max_keep, P);
+  Y2_LAUNCHED();
+  return Y2_OK;
 }
 
 }  // namespace y2

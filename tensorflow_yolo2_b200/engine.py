@@ -44,7 +44,7 @@ def create_variables(store, output_filter):
 class Yolo2Engine:
     def __init__(self, batch, image_size=416, output_filter=125, store=None, core_training=False, head_training=True,
                  anchors=VOC_ANCHORS, num_class=20, score_thresh=0.3, iou_thresh=0.45, max_keep=None,
-                 input_kind='u8', decode='region', use_cuda_graph=True, device=None, seed=0):
+                 input_kind='u8', decode='region', use_cuda_graph=True, device=None, seed=0, fused_detect=True):
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.N, self.IS, self.OF = int(batch), int(image_size), int(output_filter)
         assert self.IS % 32 == 0
@@ -54,6 +54,7 @@ class Yolo2Engine:
         self.score_thresh, self.iou_thresh = float(score_thresh), float(iou_thresh)
         self.input_kind = input_kind
         self.decode = decode
+        self.fused_detect = bool(fused_detect)
         self.store = store if store is not None else VariableStore(seed=seed)
         self.layers = create_variables(self.store, self.OF)
         dev = self.device
@@ -161,10 +162,14 @@ class Yolo2Engine:
             if L['pool']:
                 H //= 2
         if self.decode == 'region':
-            ops.decode_region(self.acts[-1], self.anchors, self.C, self.score_thresh, boxes=self.boxes,
-                              scores=self.scores)
-            ops.nms(self.boxes, self.scores, self.score_thresh, self.iou_thresh, self.max_keep, keep_idx=self.keep_idx,
-                    keep_count=self.keep_count)
+            if self.C == 20 and self.nbox <= 4095 and self.fused_detect:
+                ops.detect_fused(self.acts[-1], self.anchors, self.C, self.score_thresh, self.iou_thresh, self.max_keep,
+                                 boxes=self.boxes, scores=self.scores, keep_idx=self.keep_idx, keep_count=self.keep_count)
+            else:
+                ops.decode_region(self.acts[-1], self.anchors, self.C, self.score_thresh, boxes=self.boxes,
+                                  scores=self.scores)
+                ops.nms(self.boxes, self.scores, self.score_thresh, self.iou_thresh, self.max_keep,
+                        keep_idx=self.keep_idx, keep_count=self.keep_count)
 
     def run(self):
         """Enqueue one step (input already in self.in_u8 / self.in_f32) on the current stream."""

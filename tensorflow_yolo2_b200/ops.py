@@ -216,6 +216,31 @@ def nms(boxes, scores, score_thresh=0.3, iou_thresh=0.45, max_keep=None, keep_id
     return keep_idx, keep_count
 
 
+def detect_fused(net, anchors, C_=20, score_thresh=0.3, iou_thresh=0.45, max_keep=None, boxes=None, scores=None,
+                 keep_idx=None, keep_count=None, keep_score=None, want_scores=True):
+    """Region decode + per-class NMS in one kernel (one CTA per image).  Returns (boxes, scores or None, keep_idx,
+    keep_count, keep_score)."""
+    N, S = net.shape[0], net.shape[1]
+    A = anchors.shape[0]
+    nbox = S * S * A
+    assert net.numel() == N * nbox * (5 + C_)
+    max_keep = max_keep or nbox
+    dev = net.device
+    if boxes is None:
+        boxes = torch.empty((N, nbox, 4), dtype=torch.float32, device=dev)
+    if scores is None and want_scores:
+        scores = torch.empty((N, nbox, C_), dtype=torch.float32, device=dev)
+    if keep_idx is None:
+        keep_idx = torch.full((N, C_, max_keep), -1, dtype=torch.int32, device=dev)
+    if keep_count is None:
+        keep_count = torch.empty((N, C_), dtype=torch.int32, device=dev)
+    check(_lib.load().y2_detect_fused(_p(net, torch.float32), _p(anchors, torch.float32), N, S, A, C_, score_thresh,
+                                      iou_thresh, _p(boxes, torch.float32), _p(scores, torch.float32),
+                                      _p(keep_idx, torch.int32), _p(keep_count, torch.int32), _p(keep_score, torch.float32),
+                                      max_keep, _stream()), 'y2_detect_fused')
+    return boxes, scores, keep_idx, keep_count, keep_score
+
+
 # ---- a6 / a7 -------------------------------------------------------------------------------
 def iou(boxes1, boxes2):
     """[..., 4] x [..., 4] (cx,cy,w,h) f32 -> [...] IoU (net_utils.get_iou arithmetic)."""

@@ -126,6 +126,7 @@ class Yolo2Trainer:
         f32 = dict(dtype=torch.float32, device=dev)
         bf16 = dict(dtype=torch.bfloat16, device=dev)
         self.in_u8 = torch.zeros((N, IS, IS, 3), dtype=torch.uint8, device=dev)
+        self.in_f32 = None
         self.x0 = torch.empty((N, IS, IS, 8), **bf16)
         self.acts, self.raw, self.stats, self.geom = [], [], [], []
         self.packed, self.packed_dgrad = [], []
@@ -189,7 +190,10 @@ class Yolo2Trainer:
 
     # ------------------------------------------------------------------------------------------
     def forward(self):
-        ops.preprocess_u8(self.in_u8, bf16c8=True, out=self.x0)
+        if self.in_f32 is not None:
+            ops.pad_cast_f32_to_bf16c8(self.in_f32, out=self.x0)        # pascal_voc.get() images: already x/255*2-1
+        else:
+            ops.preprocess_u8(self.in_u8, bf16c8=True, out=self.x0)
         x = self.x0
         nl = len(self.layers)
         for li, L in enumerate(self.layers):
@@ -258,7 +262,14 @@ class Yolo2Trainer:
         """One training iteration on the current stream.  images: uint8 [N,IS,IS,3] BGR (host or device) or None
         to reuse self.in_u8.  Returns the device tensor terms[5] (the loss is terms[4])."""
         if images is not None:
-            self.in_u8.copy_(torch.as_tensor(images), non_blocking=True)
+            t = torch.as_tensor(images)
+            if t.dtype == torch.uint8:
+                self.in_f32 = None
+                self.in_u8.copy_(t, non_blocking=True)
+            else:       # float images as produced by pascal_voc.get() (float64 in the reference, cast at the feed)
+                if self.in_f32 is None:
+                    self.in_f32 = torch.empty((self.N, self.IS, self.IS, 3), dtype=torch.float32, device=self.device)
+                self.in_f32.copy_(t.to(torch.float32), non_blocking=True)
         self.forward()
         self.loss()
         self.backward(capture)

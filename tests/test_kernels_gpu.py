@@ -222,3 +222,57 @@ def test_adam_step(ops):
     np.testing.assert_allclose(pt.cpu().numpy(), wp, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(mt.cpu().numpy(), wm, rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(vt.cpu().numpy(), wv, rtol=1e-5, atol=1e-7)
+
+
+# ---- fused decode + NMS ---------------------------------------------------------------------------
+@pytest.mark.parametrize('N,S,thr', [(7, 13, 0.3), (3, 19, 0.2), (2, 13, 0.01), (2, 7, 0.3)])
+def test_detect_fused_equals_decode_plus_nms_and_oracle(ops, N, S, thr):
+    rs = np.random.RandomState(S * 10 + N)
+    net = (2.0 * rs.randn(N, S, S, 125)).astype(np.float32)
+    an = cu(O.VOC_ANCHORS)
+    b0, s0 = ops.decode_region(cu(net), an, 20, thr)
+    ki0, kc0 = ops.nms(b0, s0, thr, 0.45)
+    ks = torch.zeros((N, 20, S * S * 5), dtype=torch.float32, device='cuda')
+    b1, s1, ki1, kc1, _ = ops.detect_fused(cu(net), an, 20, thr, 0.45, keep_score=ks)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(b1.cpu().numpy(), b0.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(s1.cpu().numpy(), s0.cpu().numpy(), rtol=2e-6, atol=1e-7)
+    # oracle: decode parity, then NMS on the fused kernel's own boxes/scores must give its keep lists bit-exactly
+    wb, wst, _ = O.region_decode_v2(net, O.VOC_ANCHORS, 20, thr)
+    np.testing.assert_allclose(b1.cpu().numpy(), wb, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(s1.cpu().numpy(), wst, rtol=1e-4, atol=1e-6)
+    boxes, scores = b1.cpu().numpy(), s1.cpu().numpy()
+    ki, kc, ksc = ki1.cpu().numpy(), kc1.cpu().numpy(), ks.cpu().numpy()
+    total = 0
+    for n in range(N):
+        keeps = O.nms_per_class(boxes[n], scores[n], 0.45, thr)
+        for k in range(20):
+            assert kc[n, k] == len(keeps[k])
+            np.testing.assert_array_equal(ki[n, k, :kc[n, k]], keeps[k])
+            np.testing.assert_array_equal(ksc[n, k, :kc[n, k]], scores[n, keeps[k], k])
+            total += len(keeps[k])
+    assert total > 0
+    if float((s0 != s1).sum()) == 0:        # identical scores -> identical keep lists from the two-kernel path
+        assert torch.equal(kc0, kc1)
+
+
+def test_detect_fused_overflow_falls_back_to_bitmatrix_kernel(ops):
+    """threshold 0: all 845 x 20 candidates (> 2048) -> image flagged and re-done by nms_kernel; and a mixed batch."""
+    rs = np.random.RandomState(77)
+    net = (1.0 * rs.randn(3, 13, 13, 125)).astype(np.float32)
+    net[1, ..., 4::25] = -30.0                       # image 1: objectness ~ 0 -> scores underflow below any threshold
+    an = cu(O.VOC_ANCHORS)
+    b1, s1, ki1, kc1, _ = ops.detect_fused(cu(net), an, 20, 1e-12, 0.45, max_keep=845)
+    torch.cuda.synchronize()
+    boxes, scores = b1.cpu().numpy(), s1.cpu().numpy()
+    ki, kc = ki1.cpu().numpy(), kc1.cpu().numpy()
+    assert (kc >= 0).all()
+    for n in range(3):
+        keeps = O.nms_per_class(boxes[n], scores[n], 0.45, 1e-12)
+        for k in range(20):
+            assert kc[n, k] == len(keeps[k])
+            np.testing.assert_array_equal(ki[n, k, :kc[n, k]], keeps[k])
+    # without a scores buffer the overflowed images are reported, not silently dropped
+    _, _, _, kc2, _ = ops.detect_fused(cu(net), an, 20, 1e-12, 0.45, max_keep=845, want_scores=False)
+    torch.cuda.synchronize()
+    assert (kc2.cpu().numpy()[0] == -1).all()
