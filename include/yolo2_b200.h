@@ -89,6 +89,17 @@ size_t y2_conv_packed_weight_elems(int ksize, int Cin, int Cout);
 int y2_pack_weights_bf16(const float* w_hwio, void* w_packed, int ksize, int Cin, int Cout, y2_stream_t stream);
 int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream);
 
+/* ---- a10+a1+a2+a3 fused for the FIRST layer (inference-mode BN): uint8 image -> pooled bf16 activation ---------
+ * pascal_voc.py:62-64 (x/255*2-1) + darknet.py:150-151 (conv 3x3 3->32, +bias, BN, leaky, 2x2 max-pool) in one
+ * kernel; the padded bf16 input is never materialised.  img uint8 [N,H,W,3] (H % 32 == 0, W % 16 == 0, 16-byte
+ * aligned); w_packed from y2_pack_weights_conv1_u8 (the BN scale is folded INTO the bf16 weights because the kernel
+ * pools before the affine/leaky step; `scale` NULL = 1); shift [32] = beta + (bias - mean) * scale;
+ * y bf16 [N,H/2,W/2,32] = maxpool(leaky(conv * scale + shift)).  Cout is fixed at 32 (Darknet19). */
+size_t y2_conv1_u8_packed_weight_elems(void);
+int y2_pack_weights_conv1_u8(const float* w_hwio, const float* scale, void* w_packed, y2_stream_t stream);
+int y2_conv1_u8_pool_fwd(const uint8_t* img, const void* w_packed, const float* shift, void* y, int N, int H, int W,
+                         float alpha, y2_stream_t stream);
+
 /* ---- a2: batch normalisation pieces (darknet.py:42-44, tf.layers.batch_normalization) -------
  * y2_bn_stats: per-channel mean and BIASED variance over the M rows of x [M, ld] (float32),
  * accumulated in float64 (activations reach 1e9+ with the reference's initialiser; see DESIGN).

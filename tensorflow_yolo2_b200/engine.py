@@ -44,7 +44,8 @@ def create_variables(store, output_filter):
 class Yolo2Engine:
     def __init__(self, batch, image_size=416, output_filter=125, store=None, core_training=False, head_training=True,
                  anchors=VOC_ANCHORS, num_class=20, score_thresh=0.3, iou_thresh=0.45, max_keep=None,
-                 input_kind='u8', decode='region', use_cuda_graph=True, device=None, seed=0, fused_detect=True):
+                 input_kind='u8', decode='region', use_cuda_graph=True, device=None, seed=0, fused_detect=True,
+                 fused_conv1=True):
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.N, self.IS, self.OF = int(batch), int(image_size), int(output_filter)
         assert self.IS % 32 == 0
@@ -55,6 +56,8 @@ class Yolo2Engine:
         self.input_kind = input_kind
         self.decode = decode
         self.fused_detect = bool(fused_detect)
+        # first layer fused with the uint8 preprocessing and the pool (conv1_fused.cu): inference-mode BN, u8 input
+        self.fused_conv1 = bool(fused_conv1) and input_kind == 'u8' and not self.core_training
         self.store = store if store is not None else VariableStore(seed=seed)
         self.layers = create_variables(self.store, self.OF)
         dev = self.device
@@ -120,13 +123,17 @@ class Yolo2Engine:
                 bn = L['bn']
                 self.fold[li] = ops.bn_fold(st[bn['gamma']], st[bn['beta']], st[bn['moving_mean']],
                                             st[bn['moving_variance']], st[L['b']])
+        if self.fused_conv1:
+            self.packed_c1 = ops.pack_weights_conv1_u8(st[self.layers[0]['W']], self.fold[0][0])
         self.graph = None
         self._version = st.version
 
     # ------------------------------------------------------------------------------------------
     def _enqueue(self):
         st = self.store
-        if self.input_kind == 'u8':
+        if self.fused_conv1:
+            pass                                     # the first conv reads self.in_u8 directly
+        elif self.input_kind == 'u8':
             ops.preprocess_u8(self.in_u8, bf16c8=True, out=self.x0)
         else:
             ops.pad_cast_f32_to_bf16c8(self.in_f32, out=self.x0)
@@ -137,7 +144,9 @@ class Yolo2Engine:
             training = self.head_training if L['head'] else self.core_training
             last = li == nl - 1
             out = self.acts[li]
-            if not training:
+            if li == 0 and self.fused_conv1:
+                ops.conv1_u8_pool(self.in_u8, self.packed_c1, self.fold[0][1], out=out)
+            elif not training:
                 scale, shift = self.fold[li]
                 if last:
                     raw = self.raw[li]

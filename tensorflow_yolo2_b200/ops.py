@@ -109,6 +109,29 @@ def conv_fwd_bf16(x, w_packed, ksize, cin, cout, scale=None, shift=None, leaky=T
     return out
 
 
+def pack_weights_conv1_u8(w_hwio, scale=None, out=None):
+    """First-layer weights [3,3,3,32] (TF HWIO) with the BN scale folded in -> operand of conv1_u8_pool."""
+    assert tuple(w_hwio.shape) == (3, 3, 3, 32), 'the fused first layer is Darknet19\'s 3x3 3->32 conv'
+    n = int(_lib.load().y2_conv1_u8_packed_weight_elems())
+    if out is None:
+        out = torch.empty((n,), dtype=torch.bfloat16, device=w_hwio.device)
+    check(_lib.load().y2_pack_weights_conv1_u8(_p(w_hwio, torch.float32), _p(scale, torch.float32), _p(out), _stream()),
+          'y2_pack_weights_conv1_u8')
+    return out
+
+
+def conv1_u8_pool(img_u8, w_packed_c1, shift, out=None, alpha=ALPHA):
+    """uint8 [N,H,W,3] BGR -> bf16 [N,H/2,W/2,32]: preprocessing + conv1 + BN(scale folded, +shift) + leaky + pool."""
+    N, H, W, c = img_u8.shape
+    assert c == 3
+    if out is None:
+        out = torch.empty((N, H // 2, W // 2, 32), dtype=torch.bfloat16, device=img_u8.device)
+    check(_lib.load().y2_conv1_u8_pool_fwd(_p(img_u8, torch.uint8), _p(w_packed_c1, torch.bfloat16),
+                                           _p(shift, torch.float32), _p(out, torch.bfloat16), N, H, W, alpha, _stream()),
+          'y2_conv1_u8_pool_fwd')
+    return out
+
+
 # ---- a2 / a3 -------------------------------------------------------------------------------
 _ws_cache = {}
 

@@ -36,3 +36,18 @@ def test_ops_refuse_cpu_tensors():
     from tensorflow_yolo2_b200 import ops
     with pytest.raises(_lib.Y2Error):
         ops._p(torch.zeros(4))
+
+
+def test_conv1_fused_byte_conversion_identity():
+    """conv1_fused.cu converts a byte with ONE fma, bf16_rn(fma(v, 2/255, -1)); the preprocessing kernels (and the
+    reference, pascal_voc.py:62-64) compute (v/255)*2-1 in float32.  The two agree after the bf16 rounding for every
+    byte value -- that identity is what makes the fused first layer's input bit-identical."""
+    import numpy as np
+    import torch
+    v = np.arange(256, dtype=np.float32)
+    ref = ((v / np.float32(255.0)) * np.float32(2.0) - np.float32(1.0)).astype(np.float32)
+    k = np.float32(2.0 / 255.0)
+    fma = (v.astype(np.float64) * np.float64(k) - 1.0).astype(np.float32)      # exact product, one rounding
+    a = torch.tensor(ref).to(torch.bfloat16).view(torch.int16)
+    b = torch.tensor(fma).to(torch.bfloat16).view(torch.int16)
+    assert torch.equal(a, b)

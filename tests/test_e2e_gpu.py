@@ -97,13 +97,23 @@ def test_engine_matches_builders_and_oracle_detections(fresh):
     st, layers = make_store(125, tame=True)
     N, IS = 4, 160
     img = np.random.RandomState(5).randint(0, 256, (N, IS, IS, 3)).astype(np.uint8)
-    eng = Yolo2Engine(N, IS, 125, store=st, score_thresh=0.05, iou_thresh=0.45, use_cuda_graph=True)
+    # default engine: first layer fused with preprocessing + pool (BN scale folded into its bf16 weights)
+    engf = Yolo2Engine(N, IS, 125, store=st, score_thresh=0.05, iou_thresh=0.45, use_cuda_graph=True)
+    assert engf.fused_conv1
+    net_fused = engf.infer(torch.tensor(img))['net'].clone()
+    # same engine with the generic first layer: issues exactly the kernels the builders issue
+    eng = Yolo2Engine(N, IS, 125, store=st, score_thresh=0.05, iou_thresh=0.45, use_cuda_graph=True, fused_conv1=False)
     r = eng.infer(torch.tensor(img))
     torch.cuda.synchronize()
     net_graph = r['net'].clone()
     r = eng.infer(torch.tensor(img))                 # replay
     torch.cuda.synchronize()
     assert torch.equal(net_graph, r['net'])
+    e = rel_l2(net_fused.cpu().numpy(), net_graph.cpu().numpy())
+    print('fused first layer vs generic first layer: rel_l2(net)=%.3g' % e)
+    # differs only by where the first layer's weights are rounded (before / after the BN scale); the head's batch-
+    # statistics BN over 4*5*5 = 100 samples amplifies it to the same ~2% either path shows against the oracle
+    assert e < 5e-2
     # builders on the same store
     _install(st)
     x = torch.tensor(O.preprocess_u8(img)).cuda()

@@ -37,6 +37,32 @@ def test_preprocess_u8_bit_exact(ops, golden_dir):
     assert np.all(got8[..., 3:] == 0)
 
 
+# ---------------------------------------------------------------------------------- a10+a1+a2+a3 first layer fused
+@pytest.mark.parametrize('N,H,W', [(2, 32, 16, ), (3, 96, 96), (1, 64, 160), (2, 416, 416)])
+def test_conv1_u8_pool_vs_oracle(ops, N, H, W):
+    """uint8 image -> preprocessing -> conv 3x3 3->32 (+bias, BN incl. NEGATIVE gammas) -> leaky -> 2x2 pool, one
+    kernel, against the oracle's conv_bn_layer + max_pool on bf16-rounded operands (the kernel folds the BN scale into
+    the bf16 weights, so the oracle's weights are rounded after the same folding)."""
+    rs = np.random.RandomState(7 + H)
+    img = rs.randint(0, 256, (N, H, W, 3)).astype(np.uint8)
+    w = (rs.randn(3, 3, 3, 32) * 0.3).astype(np.float32)
+    b = (rs.randn(32) * 0.1).astype(np.float32)
+    gamma = (rs.uniform(0.5, 1.5, 32) * np.where(rs.rand(32) < 0.3, -1, 1)).astype(np.float32)
+    beta, mm = (rs.randn(32) * 0.2).astype(np.float32), (rs.randn(32) * 0.2).astype(np.float32)
+    mv = rs.uniform(0.5, 2.0, 32).astype(np.float32)
+    scale, shift = ops.bn_fold(cu(gamma), cu(beta), cu(mm), cu(mv), cu(b))
+    wp = ops.pack_weights_conv1_u8(cu(w), scale)
+    got = ops.conv1_u8_pool(cu(img), wp, shift).float().cpu().numpy()
+    assert got.shape == (N, H // 2, W // 2, 32)
+    # oracle: same folding, operands rounded to bf16 at the same points, float64 accumulation
+    x = O.bf16_round(torch.tensor(O.preprocess_u8(img))).double()
+    wf = O.bf16_round(torch.tensor(w) * scale.cpu().reshape(1, 1, 1, 32)).double()
+    h = O.conv2d_same(x, wf, torch.float64) + shift.cpu().double()
+    want = O.max_pool_2x2(torch.maximum(O.ALPHA * h, h)).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-2, atol=1e-2)        # output is bf16 (8 mantissa bits)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 3e-3
+
+
 # ---------------------------------------------------------------------------------- a1 (fp32 path)
 @pytest.mark.parametrize('N,H,W,Cin,Cout,k', [(2, 13, 13, 64, 48, 3), (1, 16, 20, 3, 32, 3), (2, 7, 7, 128, 30, 1),
                                               (1, 26, 26, 32, 125, 3)])
