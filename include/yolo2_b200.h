@@ -123,6 +123,17 @@ int y2_affine_leaky_pool(const float* x, int ldx, const float* sub, const float*
                          int leaky, int pool, void* out, int out_dtype, int N, int H, int W, int C,
                          y2_stream_t stream);
 
+/* Same, with an output row stride `ldo` (elements; the result may be a channel slice of a wider, concatenated tensor)
+ * and, with space_to_depth != 0, the passthrough / reorg layer (absent from the reference) folded
+ * into the store address: tf.space_to_depth(block_size=2) semantics, pixel (h, w) -> row (h/2, w/2), channels
+ * [((h%2)*2 + (w%2))*C, +C).  `out` then points at the first channel of the slice inside [N, H/2, W/2, ldo]. */
+int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const float* scale, const float* shift, float alpha,
+                            int leaky, int pool, void* out, int out_dtype, int ldo, int space_to_depth, int N, int H, int W,
+                            int C, y2_stream_t stream);
+/* a3: tf.nn.max_pool 2x2/2 (darknet.py:24-25) on bf16 [N,H,W,C] -> [N,H/2,W/2,C]; C % 8 == 0.  (The pool normally runs
+ * in the conv epilogue; this kernel serves the layer whose un-pooled output is also the passthrough source.) */
+int y2_maxpool2x2_bf16(const void* x, void* y, int N, int H, int W, int C, y2_stream_t stream);
+
 /* ---- a8: grid decode of show_yolo_detection (yolo2_nets/net_utils.py:393-407,418) -----------
  * net [N,S,S,C+5B] f32.  boxes [N,S,S,B,4] = ((x+j)/S, (y+i)/S, w^2, h^2); conf [N,S,S,B];
  * keep [N,S,S,B] u8 = conf > thresh; cls [N,S,S] int32 = argmax of the cell's class vector. */

@@ -134,20 +134,41 @@ def conv_bn_layer(x, p, training, dtype, bf16_operands=False):
     return y, h, (mm, mv)
 
 
+def space_to_depth2(x_nhwc):
+    """Passthrough / reorg layer (ABSENT from the reference -- SURVEY Appendix A; parity unpinned): tf.space_to_depth
+    with block_size 2 on NHWC, out[n, i, j, (di*2 + dj)*C + c] = x[n, 2i+di, 2j+dj, c]."""
+    n, h, w, c = x_nhwc.shape
+    assert h % 2 == 0 and w % 2 == 0
+    return x_nhwc.reshape(n, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 4 * c)
+
+
+PASSTHROUGH_LAYER = 12          # CORE_PLAN index of the 26x26x512 layer (darknet.py:170), taken BEFORE its max-pool
+
+
 def darknet19_forward(x_nhwc, params_core, params_head, core_training=False, head_training=True,
-                      dtype=None, bf16_operands=False, return_intermediates=False):
+                      dtype=None, bf16_operands=False, return_intermediates=False, params_passthrough=None):
     """darknet.py:126-179 (core) + :182-201 (head).  Defaults reproduce the detect script:
     core is_training=False (pascal_detect_darknet.py:41), head is_training=True (darknet.py:184
-    default, not overridden at pascal_detect_darknet.py:42)."""
+    default, not overridden at pascal_detect_darknet.py:42).
+
+    params_passthrough (extension, SURVEY Appendix A, default off = the reference's graph): a 1x1 conv_bn_layer
+    (512 -> F) on the un-pooled output of core layer 13, space_to_depth(2), channel-concatenated AFTER the 1024
+    channels of head conv2; head conv3 then has 1024 + 4F input channels."""
     dtype = dtype or torch.float64
     x = x_nhwc.to(dtype)
     inter = []
-    for (k, cin, cout, pool), p in zip(CORE_PLAN, params_core):
+    pt_src = None
+    for li, ((k, cin, cout, pool), p) in enumerate(zip(CORE_PLAN, params_core)):
         x, _, _ = conv_bn_layer(x, p, core_training, dtype, bf16_operands)
+        if li == PASSTHROUGH_LAYER:
+            pt_src = x
         if pool:
             x = max_pool_2x2(x)
         inter.append(x)
-    for p in params_head:
+    for hi, p in enumerate(params_head):
+        if hi == 2 and params_passthrough is not None:
+            pt, _, _ = conv_bn_layer(pt_src, params_passthrough, head_training, dtype, bf16_operands)
+            x = torch.cat([x, space_to_depth2(pt)], dim=-1)
         x, _, _ = conv_bn_layer(x, p, head_training, dtype, bf16_operands)
         inter.append(x)
     if return_intermediates:

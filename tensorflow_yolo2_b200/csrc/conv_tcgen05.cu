@@ -123,7 +123,7 @@ constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 constexpr int WARP_PRODUCER = EPI_WARPS;
 constexpr int WARP_MMA = EPI_WARPS + 1;
 constexpr int MAX_STAGES = 12;
-constexpr int MAX_UNITS = 160;                     // (tap, channel-chunk) units per tile: 9 * 1024/64 = 144
+constexpr int MAX_UNITS = 192;                     // (tap, channel-chunk) units per tile: 9 * 1280/64 = 180 (passthrough concat)
 
 // per-unit constants, computed once per CTA so that the single-thread roles do no index arithmetic
 struct __align__(16) UnitDesc {

@@ -217,7 +217,7 @@ __global__ void bn_update_moving_kernel(float* __restrict__ mm, float* __restric
 template <int VEC, bool BF16OUT>
 __global__ void affine_leaky_pool_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ sub,
                                          const float* __restrict__ scale, const float* __restrict__ shift, float alpha, int leaky_on, int pool,
-                                         void* __restrict__ out, int N, int H, int W, int C) {
+                                         void* __restrict__ out, int N, int H, int W, int C, int ldo, int s2d) {
   int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   int CV = C / VEC;
   size_t total = (size_t)N * Ho * Wo * CV;
@@ -255,7 +255,10 @@ __global__ void affine_leaky_pool_kernel(const float* __restrict__ x, int ldx, c
           r[v] = fmaxf(r[v], y);
         }
       }
-    size_t o = pix * C + c0;
+    // dense rows of stride ldo, or (s2d, passthrough/reorg) tf.space_to_depth(block 2): pixel (h, w) lands in
+    // row (h/2, w/2) at channel block (h%2)*2 + (w%2) -- the reorg layer is this store address, never a copy
+    size_t o = s2d ? ((size_t)(n * (Ho >> 1) + (ho >> 1)) * (Wo >> 1) + (wo >> 1)) * ldo + (size_t)(((ho & 1) * 2 + (wo & 1)) * C) + c0
+                   : pix * ldo + c0;
     if (BF16OUT) {
       __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out) + o;
       if (VEC == 4) {
@@ -278,6 +281,31 @@ __global__ void affine_leaky_pool_kernel(const float* __restrict__ x, int ldx, c
         for (int v = 0; v < VEC; ++v) of[v] = r[v];
       }
     }
+  }
+}
+
+// a3  tf.nn.max_pool 2x2/2 (darknet.py:24-25) on a bf16 NHWC tensor, 8 channels (16 B) per thread.  Used when a layer's
+// un-pooled output is needed as well (the passthrough source, darknet.py:170) so the pool cannot live in the conv epilogue.
+__global__ void maxpool2x2_bf16_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int CV) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Ho * Wo * CV;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int cv = (int)(i % CV);
+    const size_t pix = i / CV;
+    const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
+    const uint4* p = x + ((size_t)(n * H + 2 * ho) * W + 2 * wo) * CV + cv;
+    uint4 a = p[0], b = p[CV], c = p[(size_t)W * CV], d = p[(size_t)W * CV + CV];
+    uint4 r;
+    uint32_t* ra = &a.x; uint32_t* rb = &b.x; uint32_t* rc = &c.x; uint32_t* rd = &d.x; uint32_t* rr = &r.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 m = __hmax2(__hmax2(*reinterpret_cast<__nv_bfloat162*>(&ra[k]), *reinterpret_cast<__nv_bfloat162*>(&rb[k])),
+                                 __hmax2(*reinterpret_cast<__nv_bfloat162*>(&rc[k]), *reinterpret_cast<__nv_bfloat162*>(&rd[k])));
+      rr[k] = *reinterpret_cast<uint32_t*>(&m);
+    }
+    y[i] = r;
   }
 }
 
@@ -408,26 +436,45 @@ int y2_bn_update_moving(float* moving_mean, float* moving_var, const float* mean
   return Y2_OK;
 }
 
-int y2_affine_leaky_pool(const float* x, int ldx, const float* sub, const float* scale, const float* shift, float alpha, int leaky_on,
-                         int pool, void* out, int out_dtype, int N, int H, int W, int C, y2_stream_t stream) {
+int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const float* scale, const float* shift, float alpha,
+                            int leaky_on, int pool, void* out, int out_dtype, int ldo, int space_to_depth, int N, int H, int W,
+                            int C, y2_stream_t stream) {
   Y2_ARG(x && out && N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && (out_dtype == 0 || out_dtype == 1));
   if (pool) Y2_ARG(H % 2 == 0 && W % 2 == 0);
+  if (ldo <= 0) ldo = C;
+  if (space_to_depth) Y2_ARG(!pool && H % 2 == 0 && W % 2 == 0 && ldo >= 4 * C);
+  else Y2_ARG(ldo >= C);
   cudaStream_t st = (cudaStream_t)stream;
   int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
-  bool vec4 = (C % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  bool vec4 = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)out & 15) == 0);
   size_t total = (size_t)N * Ho * Wo * (vec4 ? C / 4 : C);
   int g = grid_for(total, 256);
+  const int s2d = space_to_depth ? 1 : 0;
   if (vec4) {
     if (out_dtype == 1)
-      affine_leaky_pool_kernel<4, true><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C);
+      affine_leaky_pool_kernel<4, true><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d);
     else
-      affine_leaky_pool_kernel<4, false><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C);
+      affine_leaky_pool_kernel<4, false><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d);
   } else {
     if (out_dtype == 1)
-      affine_leaky_pool_kernel<1, true><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C);
+      affine_leaky_pool_kernel<1, true><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d);
     else
-      affine_leaky_pool_kernel<1, false><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C);
+      affine_leaky_pool_kernel<1, false><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d);
   }
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_affine_leaky_pool(const float* x, int ldx, const float* sub, const float* scale, const float* shift, float alpha, int leaky_on,
+                         int pool, void* out, int out_dtype, int N, int H, int W, int C, y2_stream_t stream) {
+  return y2_affine_leaky_pool_ex(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, out_dtype, C, 0, N, H, W, C, stream);
+}
+
+int y2_maxpool2x2_bf16(const void* x, void* y, int N, int H, int W, int C, y2_stream_t stream) {
+  Y2_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0);
+  Y2_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+  size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool2x2_bf16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, N, H, W, C / 8);
   Y2_LAUNCHED();
   return Y2_OK;
 }

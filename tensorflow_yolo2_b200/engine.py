@@ -21,8 +21,14 @@ from .yolo2_nets.net_utils import VOC_ANCHORS
 HEAD_SCOPES = ('conv1', 'conv2', 'conv3', 'output')
 
 
-def create_variables(store, output_filter):
-    """Create (or find) every variable in the reference's creation order and naming."""
+PASSTHROUGH_LAYER = 12       # CORE_PLAN index of the 26x26x512 layer (darknet.py:170); its UN-pooled output is the source
+PASSTHROUGH_FILTERS = 64
+
+
+def create_variables(store, output_filter, passthrough=False):
+    """Create (or find) every variable in the reference's creation order and naming.  passthrough=True adds the
+    YOLOv2 passthrough branch (absent from the reference): scope darknet19_detection/passthrough
+    (1x1, 512 -> 64), and conv3 takes 1024 + 256 input channels."""
     store.reset_name_counters()
     layers = []
     with store.scope('darknet19'):
@@ -32,12 +38,17 @@ def create_variables(store, output_filter):
             layers.append(dict(k=k, cin=cin, cout=cout, pool=pool, W=wn, b=bn_, bn=store.batch_norm_variables(cout),
                                head=False))
     with store.scope('darknet19_detection'):
-        for sc, (k, cin, cout) in zip(HEAD_SCOPES, [(3, 1024, 1024)] * 3 + [(1, 1024, output_filter)]):
+        cat = 1024 + 4 * PASSTHROUGH_FILTERS if passthrough else 1024
+        plan = [('conv1', 3, 1024, 1024), ('conv2', 3, 1024, 1024)]
+        if passthrough:
+            plan.append(('passthrough', 1, 512, PASSTHROUGH_FILTERS))
+        plan += [('conv3', 3, cat, 1024), ('output', 1, 1024, output_filter)]
+        for sc, k, cin, cout in plan:
             with store.scope(sc):
                 wn, _ = store.weight_variable([k, k, cin, cout])
                 bn_, _ = store.bias_variable([cout])
                 layers.append(dict(k=k, cin=cin, cout=cout, pool=False, W=wn, b=bn_,
-                                   bn=store.batch_norm_variables(cout), head=True))
+                                   bn=store.batch_norm_variables(cout), head=True, role=sc))
     return layers
 
 
@@ -45,7 +56,7 @@ class Yolo2Engine:
     def __init__(self, batch, image_size=416, output_filter=125, store=None, core_training=False, head_training=True,
                  anchors=VOC_ANCHORS, num_class=20, score_thresh=0.3, iou_thresh=0.45, max_keep=None,
                  input_kind='u8', decode='region', use_cuda_graph=True, device=None, seed=0, fused_detect=True,
-                 fused_conv1=True):
+                 fused_conv1=True, passthrough=False):
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.N, self.IS, self.OF = int(batch), int(image_size), int(output_filter)
         assert self.IS % 32 == 0
@@ -59,7 +70,8 @@ class Yolo2Engine:
         # first layer fused with the uint8 preprocessing and the pool (conv1_fused.cu): inference-mode BN, u8 input
         self.fused_conv1 = bool(fused_conv1) and input_kind == 'u8' and not self.core_training
         self.store = store if store is not None else VariableStore(seed=seed)
-        self.layers = create_variables(self.store, self.OF)
+        self.passthrough = bool(passthrough)
+        self.layers = create_variables(self.store, self.OF, passthrough=self.passthrough)
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -72,22 +84,34 @@ class Yolo2Engine:
             self.acts, self.raw, self.stats = [], {}, {}
             H = IS
             max_ws = 1
+            self.pt_src = None
             for li, L in enumerate(self.layers):
                 Ho = H // 2 if L['pool'] else H
                 training = self.head_training if L['head'] else self.core_training
                 last = li == len(self.layers) - 1
+                role = L.get('role')
+                Hin = 2 * H if role == 'passthrough' else H           # the passthrough conv runs on the 26x26 map
                 if last:
                     self.acts.append(torch.empty((N, Ho, Ho, L['cout']), **f32))
+                elif self.passthrough and role == 'conv2':
+                    # conv2's 1024 channels and the reorganised passthrough's 256 share one [N,S,S,1280] tensor: the
+                    # concat is the two producers' store addresses, never a copy
+                    self.acts.append(torch.empty((N, Ho, Ho, L['cout'] + 4 * PASSTHROUGH_FILTERS), dtype=torch.bfloat16,
+                                                 device=dev))
+                elif role == 'passthrough':
+                    self.acts.append(self.acts[-1])
                 else:
                     self.acts.append(torch.empty((N, Ho, Ho, L['cout']), dtype=torch.bfloat16, device=dev))
-                if training or last:
+                if self.passthrough and li == PASSTHROUGH_LAYER:
+                    self.pt_src = torch.empty((N, H, H, L['cout']), dtype=torch.bfloat16, device=dev)
+                if training or last or role == 'passthrough':
                     ld = (L['cout'] + 31) // 32 * 32
-                    self.raw[li] = torch.empty((N * H * H, ld), **f32)
+                    self.raw[li] = torch.empty((N * Hin * Hin, ld), **f32)
                 if training:
                     self.stats[li] = (torch.empty((L['cout'],), **f32), torch.empty((L['cout'],), **f32),
                                       torch.empty((L['cout'],), **f32), torch.empty((L['cout'],), **f32),
                                       torch.zeros((L['cout'],), **f32))
-                    max_ws = max(max_ws, ops.bn_stats_workspace_bytes(N * H * H, L['cout']))
+                    max_ws = max(max_ws, ops.bn_stats_workspace_bytes(N * Hin * Hin, L['cout']))
                 H = Ho
             self.ws = torch.empty((max_ws,), dtype=torch.uint8, device=dev)
             if decode == 'region':
@@ -144,19 +168,33 @@ class Yolo2Engine:
             training = self.head_training if L['head'] else self.core_training
             last = li == nl - 1
             out = self.acts[li]
+            role = L.get('role')
+            pt_source = self.passthrough and li == PASSTHROUGH_LAYER      # un-pooled output wanted too
+            pool = L['pool'] and not pt_source
+            if pt_source:
+                out = self.pt_src
+            # where the layer's activation goes: dense, or a channel slice of the concat buffer
+            ldo, col, s2d = None, 0, False
+            Hl = H
+            if self.passthrough and role == 'conv2':
+                ldo = out.shape[-1]
+            elif role == 'passthrough':
+                x, Hl = self.pt_src, 2 * H
+                ldo, col, s2d = out.shape[-1], 1024, True
             if li == 0 and self.fused_conv1:
                 ops.conv1_u8_pool(self.in_u8, self.packed_c1, self.fold[0][1], out=out)
             elif not training:
                 scale, shift = self.fold[li]
-                if last:
+                if last or s2d:
                     raw = self.raw[li]
                     ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], scale=scale, shift=shift,
                                       leaky=True, pool=False, out_f32=True, ldy=raw.shape[1], out=raw)
-                    ops.affine_leaky_pool(raw, self.N, H, H, L['cout'], ldx=raw.shape[1], leaky=False, pool=False,
-                                          out_bf16=False, out=out)     # compact the padded rows
+                    # compact the padded rows (detection output) / scatter them space-to-depth (passthrough)
+                    ops.affine_leaky_pool(raw, self.N, Hl, Hl, L['cout'], ldx=raw.shape[1], leaky=False, pool=False,
+                                          out_bf16=not last, out=out, ldo=ldo, out_col=col, space_to_depth=s2d)
                 else:
                     ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], scale=scale, shift=shift,
-                                      leaky=True, pool=L['pool'], out=out)
+                                      leaky=True, pool=pool, out=out, ldy=ldo)
             else:
                 raw = self.raw[li]
                 mean, var, scale, shift, zeros = self.stats[li]
@@ -165,9 +203,12 @@ class Yolo2Engine:
                                   leaky=False, pool=False, out_f32=True, ldy=raw.shape[1], out=raw)
                 ops.bn_stats(raw, L['cout'], ld=raw.shape[1], workspace=self.ws, mean=mean, var=var)
                 ops.bn_fold(st[bn['gamma']], st[bn['beta']], zeros, var, None, scale=scale, shift=shift)
-                ops.affine_leaky_pool(raw, self.N, H, H, L['cout'], ldx=raw.shape[1], sub=mean, scale=scale, shift=shift,
-                                      leaky=True, pool=L['pool'], out_bf16=not last, out=out)
-            x = out
+                ops.affine_leaky_pool(raw, self.N, Hl, Hl, L['cout'], ldx=raw.shape[1], sub=mean, scale=scale, shift=shift,
+                                      leaky=True, pool=pool, out_bf16=not last, out=out, ldo=ldo, out_col=col,
+                                      space_to_depth=s2d)
+            if pt_source:
+                ops.maxpool2x2_bf16(self.pt_src, out=self.acts[li])
+            x = self.acts[li]
             if L['pool']:
                 H //= 2
         if self.decode == 'region':

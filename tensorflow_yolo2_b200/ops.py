@@ -89,7 +89,7 @@ def pack_weights_bf16(w_hwio, out=None):
 
 
 def conv_fwd_bf16(x, w_packed, ksize, cin, cout, scale=None, shift=None, leaky=True, pool=False, out_f32=False,
-                  ldy=None, out=None, alpha=ALPHA):
+                  ldy=None, out=None, alpha=ALPHA, out_col=0):
     """x bf16 [N,H,W,Cin_p]; returns bf16 [N,Ho,Wo,Cout] or (out_f32) f32 [N*H*W, ldy]."""
     N, H, W, cin_p = x.shape
     assert cin_p == conv_cin_padded(cin), (cin_p, cin)
@@ -103,7 +103,7 @@ def conv_fwd_bf16(x, w_packed, ksize, cin, cout, scale=None, shift=None, leaky=T
             assert ld == cout
             out = torch.empty((N, Ho, Wo, cout), dtype=torch.bfloat16, device=x.device)
     prm = ConvParams(x=_p(x, torch.bfloat16), w_packed=_p(w_packed, torch.bfloat16), scale=_p(scale, torch.float32),
-                     shift=_p(shift, torch.float32), y=_p(out), N=N, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize,
+                     shift=_p(shift, torch.float32), y=_p_off(out, out_col), N=N, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize,
                      flags=flags, alpha=alpha, ldy=ld, reserved=0)
     check(_lib.load().y2_conv_fwd_bf16(C.byref(prm), _stream()), 'y2_conv_fwd_bf16')
     return out
@@ -183,17 +183,38 @@ def bn_update_moving(mm, mv, mean, var, momentum=BN_MOMENTUM):
           'y2_bn_update_moving')
 
 
+def _p_off(t, col):
+    """Pointer to channel `col` of the first row of a contiguous tensor (a channel slice of a concatenated buffer)."""
+    base = _p(t)
+    return C.c_void_p(base.value + int(col) * t.element_size()) if col else base
+
+
 def affine_leaky_pool(x, N, H, W, C_, ldx=None, sub=None, scale=None, shift=None, leaky=True, pool=False,
-                      out_bf16=False, alpha=ALPHA, out=None):
-    """x f32 rows [N*H*W, ldx] (or [N,H,W,C]); y = leaky((x-sub)*scale+shift), optional 2x2 pool."""
+                      out_bf16=False, alpha=ALPHA, out=None, ldo=None, out_col=0, space_to_depth=False):
+    """x f32 rows [N*H*W, ldx] (or [N,H,W,C]); y = leaky((x-sub)*scale+shift), optional 2x2 pool.
+    ldo / out_col: write into channels [out_col, out_col+C) of rows of stride ldo (`out` = the whole wider tensor);
+    space_to_depth: the passthrough reorg (block 2) folded into the store address (out = [N,H/2,W/2,ldo])."""
     ldx = ldx or C_
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
     if out is None:
+        assert not ldo and not space_to_depth
         out = torch.empty((N, Ho, Wo, C_), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
-    check(_lib.load().y2_affine_leaky_pool(_p(x, torch.float32), ldx, _p(sub, torch.float32), _p(scale, torch.float32),
-                                           _p(shift, torch.float32), alpha, 1 if leaky else 0, 1 if pool else 0,
-                                           _p(out), 1 if out_bf16 else 0, N, H, W, C_, _stream()),
-          'y2_affine_leaky_pool')
+    assert out.dtype == (torch.bfloat16 if out_bf16 else torch.float32)
+    check(_lib.load().y2_affine_leaky_pool_ex(_p(x, torch.float32), ldx, _p(sub, torch.float32), _p(scale, torch.float32),
+                                              _p(shift, torch.float32), alpha, 1 if leaky else 0, 1 if pool else 0,
+                                              _p_off(out, out_col), 1 if out_bf16 else 0, int(ldo or C_),
+                                              1 if space_to_depth else 0, N, H, W, C_, _stream()),
+          'y2_affine_leaky_pool_ex')
+    return out
+
+
+def maxpool2x2_bf16(x, out=None):
+    """bf16 [N,H,W,C] -> [N,H/2,W/2,C] (darknet.py:24-25) for the layer whose un-pooled output is the passthrough source."""
+    N, H, W, C_ = x.shape
+    if out is None:
+        out = torch.empty((N, H // 2, W // 2, C_), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().y2_maxpool2x2_bf16(_p(x, torch.bfloat16), _p(out, torch.bfloat16), N, H, W, C_, _stream()),
+          'y2_maxpool2x2_bf16')
     return out
 
 

@@ -207,28 +207,59 @@ class _variable_scope:
         return self.ctx.__exit__(*exc)
 
 
+PASSTHROUGH_LAYER = 12            # CORE_PLAN index of the 26x26x512 layer (darknet.py:170)
+
+
+def space_to_depth(x, block_size=2):
+    """tf.space_to_depth on NHWC (the YOLOv2 reorg layer; absent from the reference).  Pure data
+    movement, done with torch views here; the batch engine folds it into the producer's store address instead."""
+    assert block_size == 2
+    n, h, w, c = x.shape
+    return x.reshape(n, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 4 * c).contiguous()
+
+
 def darknet19_core(inputs, num_classes=None, is_training=True, global_pool=True, output_stride=None, reuse=None,
-                   scope='darknet19'):
+                   scope='darknet19', return_passthrough=False):
     """darknet.py:126-179.  `num_classes`, `global_pool`, `output_stride` are accepted and ignored,
-    exactly like the reference.  Fully convolutional: 224 -> 7x7, 416 -> 13x13, 608 -> 19x19."""
+    exactly like the reference.  Fully convolutional: 224 -> 7x7, 416 -> 13x13, 608 -> 19x19.
+
+    return_passthrough=True (extension; default reproduces the reference) also returns the un-pooled 26x26x512
+    output of layer 13 (darknet.py:170), the source of the YOLOv2 passthrough branch: -> (net, passthrough)."""
     net = inputs
+    pt = None
     with _variable_scope(scope, reuse=reuse):
-        for (k, cin, cout, pool) in CORE_PLAN:
-            net = conv_bn_layer(net, k, cin, cout, 1, is_training, _pool=pool)
-    return net
+        for li, (k, cin, cout, pool) in enumerate(CORE_PLAN):
+            if return_passthrough and li == PASSTHROUGH_LAYER:
+                pt = conv_bn_layer(net, k, cin, cout, 1, is_training)
+                net = ops.maxpool2x2_bf16(pt) if pt.dtype == torch.bfloat16 else max_pool(pt, 2, 2)
+            else:
+                net = conv_bn_layer(net, k, cin, cout, 1, is_training, _pool=pool)
+    return (net, pt) if return_passthrough else net
 
 
-def darknet19_detection(net, output_filter, is_training=True, scope='darknet19_detection', reuse=None):
+def darknet19_detection(net, output_filter, is_training=True, scope='darknet19_detection', reuse=None,
+                        passthrough=None, passthrough_filters=64):
     """darknet.py:182-201: conv1..conv3 (3x3, 1024->1024) + output (1x1 -> output_filter), every
     layer conv+BN+leaky, `is_training` defaulting to True (so the head normalises with batch
-    statistics unless the caller says otherwise -- the reference's scripts never do)."""
+    statistics unless the caller says otherwise -- the reference's scripts never do).
+
+    passthrough (extension; default None = the reference's graph): the 26x26x512 tensor from
+    darknet19_core(return_passthrough=True).  It goes through a 1x1 conv_bn_layer (scope `passthrough`, 512 ->
+    passthrough_filters), space_to_depth(2), and is concatenated after conv2's 1024 channels; conv3 then takes
+    1024 + 4*passthrough_filters input channels."""
     with _variable_scope(scope, reuse=reuse):
         with _variable_scope('conv1'):
             net = conv_bn_layer(net, 3, 1024, 1024, 1, is_training)
         with _variable_scope('conv2'):
             net = conv_bn_layer(net, 3, 1024, 1024, 1, is_training)
+        cat = 1024
+        if passthrough is not None:
+            with _variable_scope('passthrough'):
+                pt = conv_bn_layer(passthrough, 1, int(passthrough.shape[-1]), passthrough_filters, 1, is_training)
+            net = torch.cat([net, space_to_depth(pt.to(net.dtype))], dim=-1)
+            cat += 4 * passthrough_filters
         with _variable_scope('conv3'):
-            net = conv_bn_layer(net, 3, 1024, 1024, 1, is_training)
+            net = conv_bn_layer(net, 3, cat, 1024, 1, is_training)
         with _variable_scope('output'):
             output = conv_bn_layer(net, 1, 1024, output_filter, 1, is_training, _out_f32=True)
     return output

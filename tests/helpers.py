@@ -6,11 +6,11 @@ from tensorflow_yolo2_b200.engine import create_variables
 from tensorflow_yolo2_b200.variables import VariableStore, _to_numpy
 
 
-def make_store(output_filter, seed=0, tame=False):
+def make_store(output_filter, seed=0, tame=False, passthrough=False):
     """Variables in the reference's order/naming.  tame=True rescales W to He-init magnitude
     (sqrt(2/fan_in)) so activations stay O(1) instead of exploding to 1e9+."""
     st = VariableStore(seed=seed)
-    layers = create_variables(st, output_filter)
+    layers = create_variables(st, output_filter, passthrough=passthrough)
     if tame:
         rs = np.random.RandomState(seed + 1)
         for L in layers:
@@ -25,15 +25,19 @@ def make_store(output_filter, seed=0, tame=False):
     return st, layers
 
 
-def oracle_params(st, layers):
-    core, head = [], []
+def oracle_params(st, layers, with_passthrough=False):
+    """-> (core, head) parameter lists for the oracle; with_passthrough=True -> (core, head, passthrough_params)."""
+    core, head, pt = [], [], None
     for L in layers:
         bn = L['bn']
         g = lambda n: torch.tensor(_to_numpy(st[n]))
         p = dict(W=g(L['W']), b=g(L['b']), gamma=g(bn['gamma']), beta=g(bn['beta']), mm=g(bn['moving_mean']),
                  mv=g(bn['moving_variance']))
-        (head if L['head'] else core).append(p)
-    return core, head
+        if L.get('role') == 'passthrough':
+            pt = p
+        else:
+            (head if L['head'] else core).append(p)
+    return (core, head, pt) if with_passthrough else (core, head)
 
 
 def rel_l2(a, b):

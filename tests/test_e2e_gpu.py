@@ -209,3 +209,42 @@ def test_engine_pipelined_submit_equals_infer(fresh):
     torch.cuda.synchronize()
     for (wn, wk), o in zip(want, outs):
         assert torch.equal(wn, o['net']) and torch.equal(wk, o['keep_count'])
+
+
+# ---- passthrough / reorg branch (absent from the reference: SURVEY Appendix A, parity unpinned) ----------------------
+def test_engine_passthrough_vs_oracle_and_builders(fresh):
+    """Engine with passthrough=True (reorg + concat folded into the producers' store addresses) against the oracle's
+    space_to_depth + concat graph on the same weights, and against the eager builders."""
+    from tensorflow_yolo2_b200.engine import Yolo2Engine
+    from tensorflow_yolo2_b200.yolo2_nets.darknet import darknet19_core, darknet19_detection
+    fresh.COMPUTE = 'bf16'
+    st, layers = make_store(125, tame=True, passthrough=True)
+    assert [L['role'] for L in layers if L['head']] == ['conv1', 'conv2', 'passthrough', 'conv3', 'output']
+    assert st[layers[-2]['W']].shape == (3, 3, 1280, 1024)
+    core_p, head_p, pt_p = oracle_params(st, layers, with_passthrough=True)
+    N, IS = 4, 128
+    img = np.random.RandomState(9).randint(0, 256, (N, IS, IS, 3)).astype(np.uint8)
+    x = O.preprocess_u8(img)
+    want = O.darknet19_forward(torch.tensor(x), core_p, head_p, dtype=torch.float64, bf16_operands=True,
+                               params_passthrough=pt_p).numpy()
+    base = O.darknet19_forward(torch.tensor(x), core_p, [head_p[0], head_p[1], dict(head_p[2], W=head_p[2]['W'][:, :, :1024]),
+                                                        head_p[3]], dtype=torch.float64, bf16_operands=True).numpy()
+    assert rel_l2(base, want) > 0.05                       # the branch really contributes to the output
+    for head_training in (True, False):
+        eng = Yolo2Engine(N, IS, 125, store=st, passthrough=True, head_training=head_training, score_thresh=0.05,
+                          use_cuda_graph=False)
+        got = eng.infer(torch.tensor(img))['net'].cpu().numpy()
+        if head_training:
+            e = rel_l2(got, want)
+            print('passthrough engine vs oracle: rel_l2=%.3g' % e)
+            assert e < 6e-2
+        else:
+            w2 = O.darknet19_forward(torch.tensor(x), core_p, head_p, head_training=False, dtype=torch.float64,
+                                     bf16_operands=True, params_passthrough=pt_p).numpy()
+            assert rel_l2(got, w2) < 6e-2
+    # eager builders, same store (generic first layer -> compare by tolerance)
+    _install(st)
+    core, pt = darknet19_core(torch.tensor(x).cuda(), is_training=False, return_passthrough=True)
+    assert tuple(pt.shape) == (N, IS // 16, IS // 16, 512)
+    out = darknet19_detection(core, 125, passthrough=pt)
+    assert rel_l2(out.cpu().numpy(), want) < 6e-2

@@ -103,6 +103,37 @@ def test_affine_leaky_pool(ops, C, pool, bf16):
     np.testing.assert_allclose(got, y.numpy(), rtol=1e-2 if bf16 else 1e-5, atol=1e-2 if bf16 else 1e-5)
 
 
+def test_affine_space_to_depth_into_concat_slice(ops):
+    """Passthrough / reorg folded into the store address: the 26x26x64 branch lands space-to-depth in channels
+    [1024, 1280) of a [N,13,13,1280] tensor whose first 1024 channels belong to another producer."""
+    rs = np.random.RandomState(11)
+    N, H, W, C = 2, 26, 26, 64
+    x = rs.randn(N * H * W, C).astype(np.float32)
+    scale, shift = rs.uniform(0.5, 1.5, C).astype(np.float32), rs.randn(C).astype(np.float32)
+    cat = torch.full((N, H // 2, W // 2, 1280), 7.0, dtype=torch.bfloat16, device='cuda')
+    ops.affine_leaky_pool(cu(x), N, H, W, C, scale=cu(scale), shift=cu(shift), leaky=True, out_bf16=True, out=cat,
+                          ldo=1280, out_col=1024, space_to_depth=True)
+    y = torch.tensor(x).double().reshape(N, H, W, C) * torch.tensor(scale).double() + torch.tensor(shift).double()
+    y = torch.maximum(O.ALPHA * y, y)
+    want = O.space_to_depth2(y).to(torch.bfloat16).float().numpy()
+    got = cat.float().cpu().numpy()
+    assert np.all(got[..., :1024] == 7.0)                                 # the other producer's slice is untouched
+    np.testing.assert_allclose(got[..., 1024:], want, rtol=1e-2, atol=1e-2)
+    # dense slice with a row stride (conv2's share of the same tensor)
+    x2 = rs.randn(N * 13 * 13, 1024).astype(np.float32)
+    ops.affine_leaky_pool(cu(x2), N, 13, 13, 1024, leaky=False, out_bf16=True, out=cat, ldo=1280, out_col=0)
+    got = cat.float().cpu().numpy()
+    np.testing.assert_array_equal(got[..., :1024], torch.tensor(x2).to(torch.bfloat16).float().numpy().reshape(N, 13, 13, 1024))
+    np.testing.assert_allclose(got[..., 1024:], want, rtol=1e-2, atol=1e-2)
+
+
+def test_maxpool2x2_bf16(ops):
+    x = torch.randn((3, 26, 26, 512), generator=torch.Generator().manual_seed(5)).to(torch.bfloat16)
+    got = ops.maxpool2x2_bf16(x.cuda()).float().cpu()
+    want = O.max_pool_2x2(x.float())
+    assert torch.equal(got, want)                                         # max of bf16 values: exact
+
+
 def test_bn_fold_and_moving(ops):
     rs = np.random.RandomState(4)
     C = 50

@@ -171,3 +171,18 @@ def test_region_decode_shapes():
     assert boxes.shape == (2, 845, 4) and s.shape == (2, 845, 20)
     assert np.all(s.sum(-1) <= 1.0 + 1e-6)
     assert np.all((sthr == 0) | (sthr > 0.3))
+
+
+def test_space_to_depth_matches_definition():
+    """Appendix A reorg: out[n,i,j,(di*2+dj)*C + c] = x[n,2i+di,2j+dj,c] (tf.space_to_depth, block 2)."""
+    import torch
+    x = torch.arange(2 * 4 * 6 * 3, dtype=torch.float64).reshape(2, 4, 6, 3)
+    y = O.space_to_depth2(x)
+    assert y.shape == (2, 2, 3, 12)
+    for n in range(2):
+        for i in range(2):
+            for j in range(3):
+                for di in range(2):
+                    for dj in range(2):
+                        for c in range(3):
+                            assert y[n, i, j, (di * 2 + dj) * 3 + c] == x[n, 2 * i + di, 2 * j + dj, c]
