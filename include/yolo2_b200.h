@@ -158,7 +158,7 @@ int y2_nms(const float* boxes, const float* scores, int N, int nbox, int C, floa
 
 /* ---- a': decode + threshold + per-class NMS fused, one CTA per image (same results as y2_decode_region + y2_nms) -
  * net [N,S,S,A*(5+C)] f32 -> boxes [N,S*S*A,4]; scores [N,S*S*A,C] dense thresholded scores (optional, NULL to skip;
- * needed for the overflow path: images with > 2048 candidates are re-done by the y2_nms kernel -- without `scores`
+ * needed for the overflow path: images where one class has > 64 candidates are re-done by the y2_nms kernel -- without `scores`
  * such images report keep_count = -1); keep_idx [N,C,max_keep], keep_count [N,C]; keep_score [N,C,max_keep]
  * (optional) = score of each kept box.  C must be 20 and S*S*A <= 4095. */
 int y2_detect_fused(const float* net, const float* anchors, int N, int S, int A, int C, float score_thresh,

@@ -4,157 +4,207 @@
 //
 // Why fused: decode and NMS are HBM-bound and tiny (166 KB + 98 KB of algorithmic traffic per 13x13 image); as two
 // kernels the [N, S*S*A, C] score tensor makes a round trip through memory and the NMS pays one CTA per
-// (image, class).  Here an image's network output is streamed once through shared memory:
-//   1. chunks of 64 cells are staged with coalesced 128-bit loads; one THREAD per (cell, anchor) then reads its
-//      5+C values from smem (stride 5+C floats = odd -> bank-conflict-free), computes sigmoid / exp / softmax
-//      serially in registers (no shuffles), writes its box to smem + global and its dense thresholded scores to
-//      global (optional), and appends every (class, score, box) above the threshold to a candidate list in smem
-//      as a 64-bit key  class << 44 | ~score_bits << 12 | box_index;
-//   2. one bitonic sort of the keys orders candidates by (class asc, score desc, box index asc);
-//   3. each warp takes whole class segments and runs the greedy sweep: the next surviving candidate is kept,
-//      lanes test it against the rest of the segment and set "removed" flags.
-// Keep lists are bit-identical to y2_decode_region + y2_nms (same float32 op order, same tie rule).
-// Images with more than DF_CAP candidates (only with a near-zero threshold) are flagged keep_count = -1 and
-// re-done by nms_kernel (bit-matrix algorithm) in a second, normally empty, launch.
+// (image, class).  At 256 images the whole job is ~15 us of HBM time, so what matters is the LATENCY of one image's
+// chain and how few block-wide barriers it has:
+//   1. the image (84.5 KB at 13x13; 128-cell chunks at 19x19) is staged with 128-bit streaming loads, all in flight
+//      at once; one THREAD per (cell, anchor) reads its 5+C values from smem (stride 25 floats: conflict-free),
+//      computes sigmoid / exp / softmax in registers with the fast intrinsics (ex2.approx / rcp.approx: ~5e-7
+//      relative, the spec allows 1e-5), writes its box (smem + global) and its dense thresholded scores (global,
+//      optional), and appends every score above the threshold to ITS CLASS's candidate list in smem as a 64-bit key
+//      ~score_bits << 12 | box_index (smem atomics on 20 counters);
+//   2. ONE barrier; then each warp owns whole classes: rank-sorts the class's keys (score desc, box index asc)
+//      with warp-local reads, and runs the greedy sweep -- for <= 32 candidates entirely in registers (one candidate
+//      per lane, corner broadcast by shuffle, suppression mask by ballot).
+// Keep lists are bit-identical to the oracle's NMS on the kernel's own boxes / scores (unfused IEEE IoU ops).
+// Images where some class has more than DF_CAPK candidates (only with a near-zero threshold) are flagged
+// keep_count = -1 and re-done by nms_kernel (bit-matrix algorithm) in a second, normally empty, launch.
 #include "nms_common.cuh"
 
 namespace y2 {
 
-constexpr int DF_THREADS = 320;          // 64 cells x 5 anchors per chunk
-constexpr int DF_CAP = 2048;             // candidate capacity per image
+constexpr int DF_THREADS = 448;          // 14 warps, <= 72 registers: two CTAs per SM overlap one image's load with
+                                         // the other's compute
+constexpr int DF_CAPK = 64;              // candidates per (image, class) held in smem
+constexpr int DF_MAX_CHUNK_CELLS = 176;  // whole 13x13 image in one chunk; larger grids go in 128-cell chunks
 
-__device__ __forceinline__ float df_sigmoid(float v) { return 1.0f / (1.0f + expf(-v)); }
+__device__ __forceinline__ float df_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 
 template <int C>
-__global__ void __launch_bounds__(DF_THREADS) detect_fused_kernel(
+__global__ void __launch_bounds__(DF_THREADS, 2) detect_fused_kernel(
     const float* __restrict__ net, const float* __restrict__ anchors, int S, int A, float score_thresh, float iou_thresh,
     float* __restrict__ boxes, float* __restrict__ scores, int32_t* __restrict__ keep_idx,
     int32_t* __restrict__ keep_count, float* __restrict__ keep_score, int max_keep, int cells_per_chunk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_count;
-  __shared__ int s_seg[C + 1];
+  __shared__ int s_cnt[C];
+  __shared__ unsigned char s_removed[C * DF_CAPK];
   const int per = 5 + C, ch = A * per;
   const int ncell = S * S, nbox = ncell * A;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int img = blockIdx.x;
-  // smem: boxes float4[nbox] | keys u64[DF_CAP] | removed u8[DF_CAP] | chunk float[cells_per_chunk*ch]
+  // smem: boxes float4[nbox] | keys u64[C][DF_CAPK] | chunk float[cells_per_chunk*ch + 4]
   float4* s_box = reinterpret_cast<float4*>(smem_raw);
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)nbox * 16 + 15) & ~(size_t)15));
-  unsigned char* removed = reinterpret_cast<unsigned char*>(keys + DF_CAP);
-  float* s_in = reinterpret_cast<float*>(removed + DF_CAP);
-  if (tid == 0) s_count = 0;
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)nbox * 16);
+  float* s_in = reinterpret_cast<float*>(s_keys + C * DF_CAPK);
+  if (tid < C) s_cnt[tid] = 0;
   const float fs = (float)S;
   const float* src_img = net + (size_t)img * ncell * ch;
   for (int cell0 = 0; cell0 < ncell; cell0 += cells_per_chunk) {
     const int nc = min(cells_per_chunk, ncell - cell0);
-    __syncthreads();                                   // previous chunk consumed (and s_count initialised)
+    __syncthreads();                                   // previous chunk consumed (and s_cnt initialised)
+    // stage [src, src + nfl) through the 16-byte aligned superset, keeping the misalignment in smem
+    const float* src = src_img + (size_t)cell0 * ch;
+    const int nfl = nc * ch;
+    const int mis = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);       // 0..3 floats
     {
-      const float* src = src_img + (size_t)cell0 * ch;
-      const int nfl = nc * ch;
-      if ((((uintptr_t)src) & 15) == 0) {
-        const int nv = nfl >> 2;
-        for (int v = tid; v < nv; v += DF_THREADS) reinterpret_cast<float4*>(s_in)[v] = __ldcs(reinterpret_cast<const float4*>(src) + v);
-        for (int e = (nv << 2) + tid; e < nfl; e += DF_THREADS) s_in[e] = __ldcs(src + e);
-      } else {
-        for (int e = tid; e < nfl; e += DF_THREADS) s_in[e] = __ldcs(src + e);
+      // whole 16-byte vectors [v0, nv) lie inside this chunk; the partial first / last vectors go float by float.
+      // Loads are issued four deep per thread before the first dependent store: a plain load-store loop leaves ONE
+      // DRAM round trip in flight per thread and turns the 12 iterations into 12 serial latencies (measured: 8 us).
+      const float4* vsrc = reinterpret_cast<const float4*>(src - mis);
+      const int nv = (mis + nfl) >> 2;
+      const int v0 = mis ? 1 : 0;
+      for (int base = v0 + tid; base < nv; base += 4 * DF_THREADS) {
+        float4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (base + u * DF_THREADS < nv) r[u] = __ldcs(vsrc + base + u * DF_THREADS);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (base + u * DF_THREADS < nv) reinterpret_cast<float4*>(s_in)[base + u * DF_THREADS] = r[u];
       }
+      if (mis && tid >= mis && tid < 4) s_in[tid] = __ldcs(src - mis + tid);
+      for (int e = (nv << 2) + tid; e < mis + nfl; e += DF_THREADS) s_in[e] = __ldcs(src - mis + e);
     }
     __syncthreads();
     for (int t = tid; t < nc * A; t += DF_THREADS) {
       const int lc = t / A, a = t - lc * A;
       const int cell = cell0 + lc;
-      const int j = cell % S, i = cell / S;
-      const float* q = s_in + (size_t)t * per;         // == (lc*A + a) * per
-      // same expressions as decode_region_kernel (decode.cu)
-      float mx = -INFINITY;
+      const int i = cell / S, j = cell - i * S;
+      const float* q = s_in + mis + (size_t)t * per;   // == (lc*A + a) * per
+      float mx = q[5];
 #pragma unroll
-      for (int k = 0; k < C; ++k) mx = fmaxf(mx, q[5 + k]);
+      for (int k = 1; k < C; ++k) mx = fmaxf(mx, q[5 + k]);
       float e[C];
       float sum = 0.0f;
 #pragma unroll
-      for (int k = 0; k < C; ++k) { e[k] = expf(q[5 + k] - mx); sum += e[k]; }
-      const float obj = df_sigmoid(q[4]);
-      const float bx = ((float)j + df_sigmoid(q[0])) / fs;
-      const float by = ((float)i + df_sigmoid(q[1])) / fs;
-      const float bw = anchors[2 * a + 0] * expf(q[2]) / fs;
-      const float bh = anchors[2 * a + 1] * expf(q[3]) / fs;
+      for (int k = 0; k < C; ++k) { e[k] = __expf(q[5 + k] - mx); sum += e[k]; }
+      const float w = __fdividef(df_sigmoid(q[4]), sum);              // objectness / softmax denominator
+      const float bx = __fdividef((float)j + df_sigmoid(q[0]), fs);
+      const float by = __fdividef((float)i + df_sigmoid(q[1]), fs);
+      const float bw = __fdividef(anchors[2 * a + 0] * __expf(q[2]), fs);
+      const float bh = __fdividef(anchors[2 * a + 1] * __expf(q[3]), fs);
       const int b = cell * A + a;
       const float4 box = make_float4(bx, by, bw, bh);
       s_box[b] = box;
       reinterpret_cast<float4*>(boxes)[(size_t)img * nbox + b] = box;
-      float sc[C];
+      unsigned cm = 0;                                  // classes above the threshold (rare: ~0.3 per box)
 #pragma unroll
       for (int k = 0; k < C; ++k) {
-        const float v = obj * (e[k] / sum);
-        sc[k] = v > score_thresh ? v : 0.0f;
-        if (v > score_thresh) {
-          const int pos = atomicAdd(&s_count, 1);
-          if (pos < DF_CAP)
-            keys[pos] = ((unsigned long long)k << 44) | ((unsigned long long)(~__float_as_uint(v)) << 12) | (unsigned)b;
-        }
+        const float v = e[k] * w;
+        cm |= v > score_thresh ? (1u << k) : 0u;
+        e[k] = v > score_thresh ? v : 0.0f;
       }
       if (scores) {
         float* dst = scores + ((size_t)img * nbox + b) * C;
         if ((C & 3) == 0) {
 #pragma unroll
-          for (int k = 0; k < C; k += 4) __stcs(reinterpret_cast<float4*>(dst + k), make_float4(sc[k], sc[k + 1], sc[k + 2], sc[k + 3]));
+          for (int k = 0; k < C; k += 4) __stcs(reinterpret_cast<float4*>(dst + k), make_float4(e[k], e[k + 1], e[k + 2], e[k + 3]));
         } else {
 #pragma unroll
-          for (int k = 0; k < C; ++k) dst[k] = sc[k];
+          for (int k = 0; k < C; ++k) dst[k] = e[k];
+        }
+      }
+      if (__any_sync(__activemask(), cm != 0)) {
+        // append (class, score, box) keys: the scores go back to the thread's own smem slot so that the loop over
+        // the set bits can index them (a register array indexed at run time would live in local memory)
+        float* qs = const_cast<float*>(q) + 5;
+#pragma unroll
+        for (int k = 0; k < C; ++k) qs[k] = e[k];
+        while (cm) {
+          const int k = __ffs(cm) - 1;
+          cm &= cm - 1;
+          const int pos = atomicAdd(&s_cnt[k], 1);
+          if (pos < DF_CAPK) s_keys[k * DF_CAPK + pos] = ((unsigned long long)(~__float_as_uint(qs[k])) << 12) | (unsigned)b;
         }
       }
     }
   }
   __syncthreads();
-  const int n = s_count;
   int32_t* kc = keep_count + (size_t)img * C;
-  if (n > DF_CAP) {                                     // rare: hand the image to the bit-matrix kernel
-    for (int k = tid; k < C; k += DF_THREADS) kc[k] = -1;
-    return;
-  }
-  if (n == 0) {
-    for (int k = tid; k < C; k += DF_THREADS) kc[k] = 0;
-    return;
-  }
-  // ---- sort by (class asc, score desc, index asc) ----
-  int P2 = 1;
-  while (P2 < n) P2 <<= 1;
-  for (int i = n + tid; i < P2; i += DF_THREADS) keys[i] = ~0ull;
-  __syncthreads();
-  for (int size = 2; size <= P2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < (P2 >> 1); i += DF_THREADS) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool asc = (lo & size) == 0;
-        const unsigned long long x = keys[lo], y = keys[hi];
-        if ((x > y) == asc) { keys[lo] = y; keys[hi] = x; }
-      }
-      __syncthreads();
+  {
+    bool overflow = false;
+#pragma unroll
+    for (int k = 0; k < C; ++k) overflow |= s_cnt[k] > DF_CAPK;
+    if (overflow) {                                     // rare: hand the image to the bit-matrix kernel
+      for (int k = tid; k < C; k += DF_THREADS) kc[k] = -1;
+      return;
     }
   }
-  // ---- class segments ----
-  for (int k = tid; k <= C; k += DF_THREADS) s_seg[k] = n;
-  for (int i = tid; i < n; i += DF_THREADS) removed[i] = 0;
-  __syncthreads();
-  for (int i = tid; i < n; i += DF_THREADS) {
-    const int k = (int)(keys[i] >> 44);
-    if (i == 0 || (int)(keys[i - 1] >> 44) != k) s_seg[k] = i;
-  }
-  __syncthreads();
-  // ---- greedy sweep, one warp per class ----
+  // ---- per class: rank sort + greedy sweep, one warp per class, no block-wide barrier from here on ----
   for (int k = warp; k < C; k += DF_THREADS / 32) {
-    const int beg = s_seg[k];
-    int end = n;
-    if (beg < n) {                                     // end = start of the next non-empty class
-      for (int k2 = k + 1; k2 < C; ++k2)
-        if (s_seg[k2] < n) { end = s_seg[k2]; break; }
+    const int m = s_cnt[k];
+    if (m == 0) {
+      if (lane == 0) kc[k] = 0;
+      continue;
     }
+    unsigned long long* keys = s_keys + k * DF_CAPK;
+    const unsigned long long k0 = lane < m ? keys[lane] : ~0ull;
+    const unsigned long long k1 = lane + 32 < m ? keys[lane + 32] : ~0ull;
+    int r0 = 0, r1 = 0;
+    for (int i = 0; i < m; ++i) {
+      const unsigned long long o = keys[i];            // smem broadcast
+      r0 += o < k0;
+      r1 += o < k1;
+    }
+    __syncwarp();
+    if (lane < m) keys[r0] = k0;                        // keys are unique (box index) -> ranks are a permutation
+    if (lane + 32 < m) keys[r1] = k1;
+    __syncwarp();
     int32_t* out = keep_idx + ((size_t)img * C + k) * max_keep;
     float* outs = keep_score ? keep_score + ((size_t)img * C + k) * max_keep : nullptr;
     int count = 0;
-    if (beg < n) {
-      for (int i = beg; i < end; ++i) {
+    if (m <= 32) {
+      // one candidate per lane, everything in registers.  Pass 1: lane j collects the set of earlier candidates i that
+      // would suppress it (IoU > thresh).  The IEEE division of get_iou only runs when some lane's intersection with
+      // candidate i is non-empty (inter == 0 gives IoU 0 exactly, so skipping it cannot change a decision).
+      const unsigned long long key = lane < m ? keys[lane] : 0ull;
+      const int bi = (int)(key & 0xfffu);
+      const Corner cj = to_corner(s_box[lane < m ? bi : 0]);
+      unsigned supby = 0;
+      for (int i = 0; i + 1 < m; ++i) {
+        Corner ci;
+        ci.x1 = __shfl_sync(0xffffffffu, cj.x1, i);
+        ci.y1 = __shfl_sync(0xffffffffu, cj.y1, i);
+        ci.x2 = __shfl_sync(0xffffffffu, cj.x2, i);
+        ci.y2 = __shfl_sync(0xffffffffu, cj.y2, i);
+        const float iw = fmaxf(0.0f, __fsub_rn(fminf(ci.x2, cj.x2), fmaxf(ci.x1, cj.x1)));
+        const float ih = fmaxf(0.0f, __fsub_rn(fminf(ci.y2, cj.y2), fmaxf(ci.y1, cj.y1)));
+        const bool ov = lane > i && lane < m && __fmul_rn(iw, ih) > 0.0f;
+        if (__any_sync(0xffffffffu, ov)) {
+          ci.area = __shfl_sync(0xffffffffu, cj.area, i);
+          if (ov && iou_corner(ci, cj) > iou_thresh) supby |= 1u << i;
+        }
+      }
+      // Pass 2: greedy resolution in score order on bit masks
+      unsigned alive = m == 32 ? 0xffffffffu : ((1u << m) - 1u);
+      for (int i = 0; i < m; ++i) {
+        if (!((alive >> i) & 1u)) continue;            // warp-uniform
+        alive &= ~__ballot_sync(0xffffffffu, (supby >> i) & 1u);
+      }
+      // kept candidates, in visiting order
+      count = __popc(alive);
+      if ((alive >> lane) & 1u) {
+        const int slot = __popc(alive & ((1u << lane) - 1u));
+        if (slot < max_keep) {
+          out[slot] = bi;
+          if (outs) outs[slot] = __uint_as_float(~(unsigned)(key >> 12));
+        }
+      }
+    } else {
+      unsigned char* removed = s_removed + k * DF_CAPK;
+      removed[lane] = 0;
+      removed[lane + 32] = 0;
+      __syncwarp();
+      for (int i = 0; i < m; ++i) {
         if (removed[i]) continue;                      // warp-uniform (smem broadcast)
         const unsigned long long key = keys[i];
         const int bi = (int)(key & 0xfffu);
@@ -164,7 +214,7 @@ __global__ void __launch_bounds__(DF_THREADS) detect_fused_kernel(
         }
         ++count;
         const Corner ci = to_corner(s_box[bi]);
-        for (int jn = i + 1 + lane; jn < end; jn += 32) {
+        for (int jn = i + 1 + lane; jn < m; jn += 32) {
           if (!removed[jn] && iou_corner(ci, to_corner(s_box[(int)(keys[jn] & 0xfffu)])) > iou_thresh) removed[jn] = 1;
         }
         __syncwarp();
@@ -174,8 +224,8 @@ __global__ void __launch_bounds__(DF_THREADS) detect_fused_kernel(
   }
 }
 
-static size_t df_smem_bytes(int nbox, int cells_per_chunk, int ch) {
-  return (((size_t)nbox * 16 + 15) & ~(size_t)15) + (size_t)DF_CAP * 8 + DF_CAP + (size_t)cells_per_chunk * ch * 4;
+static size_t df_smem_bytes(int nbox, int cells_per_chunk, int ch, int C) {
+  return (size_t)nbox * 16 + (size_t)C * DF_CAPK * 8 + ((size_t)cells_per_chunk * ch + 4) * 4;
 }
 
 // defined in nms.cu
@@ -196,8 +246,8 @@ extern "C" int y2_detect_fused(const float* net, const float* anchors, int N, in
     set_error("y2_detect_fused: C=%d / %d boxes unsupported (C == 20, <= 4095 boxes); use y2_decode_region + y2_nms", C, nbox);
     return Y2_ERR_UNSUPPORTED;
   }
-  const int cells_per_chunk = DF_THREADS / A > 0 ? DF_THREADS / A : 1;
-  const size_t smem = df_smem_bytes(nbox, cells_per_chunk, A * (5 + C));
+  const int cells_per_chunk = S * S <= DF_MAX_CHUNK_CELLS ? S * S : 128;
+  const size_t smem = df_smem_bytes(nbox, cells_per_chunk, A * (5 + C), C);
   Y2_ARG(smem <= 200 * 1024);
   cudaStream_t st = (cudaStream_t)stream;
   static thread_local size_t configured = 0;

@@ -292,8 +292,12 @@ def test_detect_fused_equals_decode_plus_nms_and_oracle(ops, N, S, thr):
     ks = torch.zeros((N, 20, S * S * 5), dtype=torch.float32, device='cuda')
     b1, s1, ki1, kc1, _ = ops.detect_fused(cu(net), an, 20, thr, 0.45, keep_score=ks)
     torch.cuda.synchronize()
-    np.testing.assert_allclose(b1.cpu().numpy(), b0.cpu().numpy(), rtol=1e-6, atol=1e-7)
-    np.testing.assert_allclose(s1.cpu().numpy(), s0.cpu().numpy(), rtol=2e-6, atol=1e-7)
+    # the fused kernel uses the fast intrinsics (ex2.approx / rcp.approx), the two-kernel path expf and IEEE division:
+    # both sit inside the spec's 1e-5; a score within that distance of the threshold may be kept by one and not the other
+    np.testing.assert_allclose(b1.cpu().numpy(), b0.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    d = np.abs(s1.cpu().numpy() - s0.cpu().numpy())
+    near = np.abs(np.maximum(s1.cpu().numpy(), s0.cpu().numpy()) - thr) < 1e-5
+    assert np.all((d <= 1e-5 * np.abs(s0.cpu().numpy()) + 1e-7) | near)
     # oracle: decode parity, then NMS on the fused kernel's own boxes/scores must give its keep lists bit-exactly
     wb, wst, _ = O.region_decode_v2(net, O.VOC_ANCHORS, 20, thr)
     np.testing.assert_allclose(b1.cpu().numpy(), wb, rtol=1e-5, atol=1e-7)
