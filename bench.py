@@ -51,6 +51,28 @@ def conv_flops_per_image(image_size, output_filter):
     return total, per
 
 
+def make_config(world, extra=None):
+    """config of the bench line -- the reference arm prints the same one (it is the driver's join key)."""
+    cfg = dict(workload='Darknet19-YOLO2 416x416 inference, fwd + region decode + per-class NMS, synthetic uint8 batch '
+                        '%d per GPU (BASELINE.json configs[1])' % BATCH_PER_GPU,
+               global_batch=world * BATCH_PER_GPU, image_size=IMAGE_SIZE, output_filter=OUTPUT_FILTER,
+               score_thresh=SCORE_THRESH, iou_thresh=IOU_THRESH, head_bn='batch statistics',
+               l2='flushed (256 MiB memset) between timed steps', parallelism='batch sharding x%d' % world)
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def load_traffic():
+    """DRAM bytes (read + write) of the 22 conv launches of one step, from the committed ncu launch list of this same
+    command (profiles/r1b_traffic.json; ncu numbers are never taken live inside a timed run)."""
+    p = os.path.join(ROOT, 'profiles', 'r1b_traffic.json')
+    try:
+        return float(json.load(open(p))['conv_dram_bytes_per_step'])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -157,8 +179,7 @@ def run_reference(args):
     line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * total / len(timed), higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload='Darknet19-YOLO2 416x416 inference, fwd + region decode + NMS, batch 64/GPU '
-                                     '(reference arm: CPU restatement of the reference, sample batch %d)' % sample_batch),
+                config=make_config(max(args.gpus, 1)),
                 cpu_baseline=dict(value=value, unit='images/s', cores=threads, kind='port', sample=sample),
                 e2e=dict(value=value, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -215,7 +236,9 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    n_launch0 = ops.launch_count()
     evs = [one_step(i, True) for i in range(args.steps)]
+    eager_launches = ops.launch_count() - n_launch0          # 0 under CUDA-graph replay (counted at capture)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     t_ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -257,7 +280,7 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel (conv_tc_kernel), timed live per launch ----
-    launches_per_step = eng.launches_per_step if not args.no_graph else None
+    launches_per_step = eng.launches_per_step if not args.no_graph else eager_launches // max(args.steps, 1)
     eng.use_cuda_graph = False
     conv_ms = conv_kernel_times(eng, ops, iters=max(3, min(args.steps, 10)))
     flops_img, per_layer = conv_flops_per_image(IMAGE_SIZE, OUTPUT_FILTER)
@@ -265,7 +288,8 @@ def run_ours(args):
     conv_total_ms = sum(conv_ms)
     achieved = N * flops_img / (conv_total_ms * 1e-3) / 1e12
     roofline = dict(bound='tensor', achieved=achieved, peak=peaks['sustained'], unit='TFLOP/s',
-                    frac=achieved / peaks['sustained'], traffic=None, peak_source=peaks['which'] + ' sustained bf16',
+                    frac=achieved / peaks['sustained'], traffic=load_traffic(),
+                    algorithmic_bytes=N * 35.0e6, traffic_source='profiles/r1b_traffic.json (ncu launch list of this command)', peak_source=peaks['which'] + ' sustained bf16',
                     kernel='conv_tc_kernel x21 + conv1_u8_pool_kernel (22 conv launches/step)', conv_ms_per_step=conv_total_ms,
                     per_layer_tflops=[round(N * f / (ms * 1e-3) / 1e12, 1) for f, ms in zip(per_layer, conv_ms)])
 
@@ -282,14 +306,9 @@ def run_ours(args):
     line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=t_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
                 data='synthetic',
-                config=dict(workload='Darknet19-YOLO2 416x416 inference, fwd + region decode + per-class NMS, '
-                                     'synthetic uint8 batch %d per GPU (BASELINE.json configs[1])' % N,
-                            global_batch=world * N, image_size=IMAGE_SIZE, output_filter=OUTPUT_FILTER,
-                            score_thresh=SCORE_THRESH, iou_thresh=IOU_THRESH, head_bn='batch statistics',
-                            l2='flushed (256 MiB memset) between timed steps', parallelism='batch sharding x%d' % world,
-                            nms_candidates=cand, nms_kept=kept),
+                config=make_config(world, dict(nms_candidates=cand, nms_kept=kept)),
                 e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                gpu_launches=int((launches_per_step or 41) * args.steps), launches_per_step=int(launches_per_step or 41),
+                gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step),
                 roofline=roofline, cpu_baseline=cpu, clocks=clocks)
     print(json.dumps(line), flush=True)
     if world > 1:
