@@ -697,6 +697,8 @@ static int launch_conv(int block_n, const CUtensorMap& tmA, const CUtensorMap& t
   }
 }
 
+int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled);   // conv_streamk_tcgen05.cu
+
 }  // namespace y2
 
 using namespace y2;
@@ -710,6 +712,12 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   if (pool) Y2_ARG(p->H % 2 == 0 && p->W % 2 == 0);
   int rc = load_driver_entry_points();
   if (rc != Y2_OK) return rc;
+  {
+    // float32 pre-BN rows of a deep 3x3 layer on a small map: 256x256 stream-K tiles (conv_streamk_tcgen05.cu)
+    int handled = 0;
+    rc = conv_streamk_try(p, (cudaStream_t)stream, &handled);
+    if (rc != Y2_OK || handled) return rc;
+  }
 
   ConvArgs a;
   memset(&a, 0, sizeof(a));

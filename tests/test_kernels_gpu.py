@@ -76,6 +76,35 @@ def test_conv_f32_vs_oracle(ops, N, H, W, Cin, Cout, k):
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())   # fp32 path: 1e-5
 
 
+# ---------------------------------------------------------------------------------- a1 stream-K 256x256 path
+@pytest.mark.parametrize('N,S,Cin,Cout,k', [(16, 13, 512, 512, 3), (9, 13, 1024, 256, 3), (6, 19, 1024, 256, 3)])
+def test_conv_streamk_vs_generic_and_oracle(ops, monkeypatch, N, S, Cin, Cout, k):
+    """float32 pre-BN rows of a deep 3x3 layer: the 256x256 stream-K kernel (partial K ranges combined with
+    red.global.add) against the generic tcgen05 kernel and the oracle; and bit-identical across repeated runs
+    (at most two additions per element -> order-independent)."""
+    rs = np.random.RandomState(S + Cout)
+    x = rs.randn(N, S, S, Cin).astype(np.float32)
+    w = (rs.randn(k, k, Cin, Cout) * 0.05).astype(np.float32)
+    b = rs.randn(Cout).astype(np.float32)
+    xb = cu(x, torch.bfloat16)
+    wp = ops.pack_weights_bf16(cu(w))
+    monkeypatch.setenv('Y2_CONV_NO_STREAMK', '1')
+    n0 = ops.launch_count()
+    ref = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, scale=None, shift=cu(b), leaky=False, out_f32=True).cpu().numpy()
+    assert ops.launch_count() - n0 == 1
+    monkeypatch.delenv('Y2_CONV_NO_STREAMK')
+    monkeypatch.setenv('Y2_CONV_FORCE_STREAMK', '1')           # small test shapes have fewer tiles than the auto rule wants
+    got1 = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, scale=None, shift=cu(b), leaky=False, out_f32=True)
+    got2 = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, scale=None, shift=cu(b), leaky=False, out_f32=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got1, got2)
+    got = got1.cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=2e-4, atol=2e-4 * np.abs(ref).max())     # fp32 accumulation order differs
+    want = (O.conv2d_same(O.bf16_round(torch.tensor(x)).double(), O.bf16_round(torch.tensor(w)).double(), torch.float64)
+            + torch.tensor(b).double()).numpy().reshape(-1, Cout)
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
+
+
 # ---------------------------------------------------------------------------------- a2 / a3
 def test_bn_stats_large_mean(ops):
     rs = np.random.RandomState(2)

@@ -35,6 +35,8 @@ def main():
         shift = torch.zeros(cout, device='cuda')
         ld = (cout + 31) // 32 * 32
         kw = dict(scale=scale, shift=shift, leaky=not head, pool=pool, out_f32=head, ldy=ld if head else None)
+        if '--raw' in sys.argv:        # float32 conv + bias rows (batch-statistics BN path)
+            kw = dict(scale=None, shift=shift, leaky=False, pool=False, out_f32=True, ldy=ld)
         y = ops.conv_fwd_bf16(x, wp, k, cin, cout, **kw)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
