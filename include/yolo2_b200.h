@@ -89,6 +89,14 @@ size_t y2_conv_packed_weight_elems(int ksize, int Cin, int Cout);
 int y2_pack_weights_bf16(const float* w_hwio, void* w_packed, int ksize, int Cin, int Cout, y2_stream_t stream);
 int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream);
 
+/* Scratch for the stream-K variant of y2_conv_fwd_bf16 (256x256 tiles whose K range is split between two CTAs: the
+ * partial accumulators travel through this buffer).  Register a device buffer of y2_conv_workspace_bytes() bytes
+ * (256-byte aligned) per calling thread; convolutions issued concurrently on different streams need different
+ * buffers.  Without a workspace (or with NULL) every layer runs on the 128-row-tile kernel -- same results up to the
+ * float32 summation order. */
+size_t y2_conv_workspace_bytes(void);
+int y2_conv_set_workspace(void* workspace, size_t bytes);
+
 /* ---- a10+a1+a2+a3 fused for the FIRST layer (inference-mode BN): uint8 image -> pooled bf16 activation ---------
  * pascal_voc.py:62-64 (x/255*2-1) + darknet.py:150-151 (conv 3x3 3->32, +bias, BN, leaky, 2x2 max-pool) in one
  * kernel; the padded bf16 input is never materialised.  img uint8 [N,H,W,3] (H % 32 == 0, W % 16 == 0, 16-byte

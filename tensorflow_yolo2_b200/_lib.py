@@ -34,6 +34,8 @@ _SIGNATURES = {
     'y2_conv_packed_weight_elems': (_sz, [_i, _i, _i]),
     'y2_pack_weights_bf16': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'y2_conv_fwd_bf16': (_i, [C.POINTER(ConvParams), _vp]),
+    'y2_conv_workspace_bytes': (_sz, []),
+    'y2_conv_set_workspace': (_i, [_vp, _sz]),
     'y2_conv1_u8_packed_weight_elems': (_sz, []),
     'y2_pack_weights_conv1_u8': (_i, [_vp, _vp, _vp, _vp]),
     'y2_conv1_u8_pool_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),

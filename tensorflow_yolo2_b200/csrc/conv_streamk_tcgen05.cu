@@ -1,5 +1,4 @@
-// conv_streamk_tcgen05.cu -- a1 (+bias) for the 13x13 / 19x19 3x3 layers whose output is the float32 pre-BN tensor
-// (the detection head, darknet.py:189-197, whose BN runs on batch statistics; and every such layer in training):
+// conv_streamk_tcgen05.cu -- a1 + a2 (scale/shift, leaky) for the deep 3x3 layers on the small maps (26x26 and below):
 // the same implicit GEMM as conv_tcgen05.cu with 256 x 256 CTA tiles and a stream-K work split.
 //
 // Why.  conv_tc_kernel on these layers is bound by the operand bytes the L2 can deliver into the SMs -- measured
@@ -8,15 +7,21 @@
 // needs 64 KB for twice the flops = 128 flop/B, i.e. 1.5x fewer bytes for the same layer.  With K = 9 * 1024 the
 // accumulator (2 x 128 x 256 fp32 = all 512 TMEM columns, single-buffered) is drained once per ~150 k clk, so the
 // un-overlapped epilogue costs ~2 %.  But 256 x 256 tiles leave only 172 tiles for 148 SMs, so instead of whole
-// tiles each CTA takes an equal, contiguous range of (tile, K-step) units ("stream-K"): a CTA's range covers the
-// tail of one tile, possibly a whole tile, and the head of the next.  A segment that covers a tile's whole K range
-// stores its result; partial segments add theirs into the zero-initialised output with red.global.add.v4.f32.
-// Every CTA's range is at least one tile long, so a tile is shared by at most TWO CTAs and each output element
-// receives at most two additions onto zero -- which is order-independent, so results stay bit-reproducible.
+// tiles each CTA takes an equal, contiguous range of (tile, K-step) units ("stream-K"): a CTA's range is the TAIL of
+// one tile (its first segment), whole tiles, and the HEAD of the next tile (its last segment).  Every range is at
+// least one tile long, so a tile is shared by at most two CTAs, c (head, done LAST in c's range) and c + 1 (tail,
+// done FIRST in c + 1's range):
+//   tail  -> the float32 partial goes to slot c + 1 of a workspace, then flag[c + 1] is released;
+//   head  -> CTA c waits for flag[c + 1] (in practice set ~150 k clk earlier), adds the partial to its own
+//            accumulator and runs the full epilogue (scale/shift, leaky, float32 or bf16 store) -- the owner
+//            finalises, so the fused epilogue survives the K split, there are no atomics and no zero-fill, and the
+//            result is bit-reproducible (fixed order: head + tail).
+// No circular wait: a tail segment depends on nothing, and all CTAs are co-resident (grid <= #SMs, 1 CTA/SM).
 //
-// Scope: ksize 1 or 3, stride 1, SAME; Cin % 64 == 0; Cout % 256 == 0; flags == Y2_CONV_OUT_F32 (no scale, no leaky,
-// no pool: the raw conv + bias rows that y2_bn_stats / y2_affine_leaky_pool consume).  Anything else stays on
-// conv_tc_kernel; y2_conv_fwd_bf16 chooses (env Y2_CONV_NO_STREAMK=1 disables this path).
+// Scope: ksize 1 or 3, stride 1, SAME; Cin % 64 == 0; Cout % 256 == 0; no fused pool; maps smaller than 64x64;
+// >= 32 K steps.  Needs the workspace registered with y2_conv_set_workspace (y2_conv_workspace_bytes() bytes, one per
+// stream); without it, or for any other layer, y2_conv_fwd_bf16 stays on conv_tc_kernel.  Env Y2_CONV_NO_STREAMK=1
+// disables the path.
 #include "tc_common.cuh"
 
 namespace y2 {
@@ -27,8 +32,13 @@ constexpr uint32_t SK_A_HALF = 128 * 128, SK_B_BYTES = 256 * 128, SK_STAGE = 2 *
 constexpr int SK_MAX_UNITS = 192;
 
 struct SkArgs {
-  const float* bias;
-  float* y;
+  const float* scale;
+  const float* shift;
+  void* y;
+  float* ws_partial;                // [grid][2][128][256] float32 partial accumulators (slot = the tail CTA)
+  int* ws_flags;                    // [grid], zeroed before the launch
+  float alpha;
+  int leaky, out_f32;
   long long M;
   int H, W, ldy, pad;
   int cin_p, cchunks, ksteps;       // K steps per tile = taps * cchunks
@@ -37,18 +47,14 @@ struct SkArgs {
   uint32_t fd_nt_mul, fd_nt_shr, fd_w_mul, fd_w_shr, fd_h_mul, fd_h_shr, fd_ks_mul, fd_ks_shr;
 };
 
-struct SkUnit { int a_c0, kw, kh, b_k; };
-
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
+constexpr uint32_t SK_STG_WARP = 32 * 128;     // per-warp store staging: 32 rows x 32 floats (or bf16), 128B-swizzled
 
 __global__ void __launch_bounds__(SK_THREADS, 1)
 conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SkArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[SK_STAGES], empty_bar[SK_STAGES], tmem_full, tmem_empty;
   __shared__ uint32_t s_tmem_base;
-  __shared__ SkUnit s_units[SK_MAX_UNITS];
+  __shared__ uint8_t s_unit_tap[SK_MAX_UNITS], s_unit_cc[SK_MAX_UNITS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
@@ -65,11 +71,9 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       fence_barrier_init();
     }
     for (int u = lane; u < a.ksteps; u += 32) {
-      SkUnit d;
-      const int tap = u / a.cchunks, cc = u - tap * a.cchunks;
-      const int ks = 2 * a.pad + 1;
-      d.a_c0 = cc * 64; d.kh = tap / ks; d.kw = tap - d.kh * ks; d.b_k = tap * a.cin_p + d.a_c0;
-      s_units[u] = d;
+      const int tap = u / a.cchunks;
+      s_unit_tap[u] = (uint8_t)tap;
+      s_unit_cc[u] = (uint8_t)(u - tap * a.cchunks);
     }
   }
   if (warp == 9) {
@@ -108,13 +112,13 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int k = k0; k < k1; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_expect_tx(&full_bar[stage], SK_STAGE);
-          const SkUnit d = s_units[k];
+          const int tap = s_unit_tap[k], a_c0 = s_unit_cc[k] * 64;
+          const int kh = a.pad ? (tap * 11) >> 5 : 0, kw = tap - kh * 3;       // tap / 3 for tap < 9 (1x1: tap == 0)
           const uint32_t sA = smem_base + stage * SK_STAGE;
           const uint32_t bar = smem_u32(&full_bar[stage]);
-          tma_load_im2col_4d(sA, &tmA, bar, d.a_c0, w0[0] - a.pad, h0[0] - a.pad, n0[0], (uint16_t)d.kw, (uint16_t)d.kh);
-          tma_load_im2col_4d(sA + SK_A_HALF, &tmA, bar, d.a_c0, w0[1] - a.pad, h0[1] - a.pad, n0[1], (uint16_t)d.kw,
-                             (uint16_t)d.kh);
-          tma_load_2d(sA + 2 * SK_A_HALF, &tmB, bar, d.b_k, nrow0);
+          tma_load_im2col_4d(sA, &tmA, bar, a_c0, w0[0] - a.pad, h0[0] - a.pad, n0[0], (uint16_t)kw, (uint16_t)kh);
+          tma_load_im2col_4d(sA + SK_A_HALF, &tmA, bar, a_c0, w0[1] - a.pad, h0[1] - a.pad, n0[1], (uint16_t)kw, (uint16_t)kh);
+          tma_load_2d(sA + 2 * SK_A_HALF, &tmB, bar, tap * a.cin_p + a_c0, nrow0);
           if (++stage == SK_STAGES) { stage = 0; phase ^= 1u; }
         }
         u += k1 - k0;
@@ -161,48 +165,135 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ++seg;
     }
   } else {
-    // =========================== epilogue: +bias, store (whole K range) or red.add (partial) ===========================
+    // =========================== epilogue ===========================
     const int q = warp & 3, chalf = warp >> 2;                 // TMEM lane quarter, column half of each accumulator
+    const int et = threadIdx.x;                                // 0..255
     uint32_t seg = 0;
     long long u = u_begin;
     while (u < u_end) {
       const uint32_t tile = (uint32_t)fdiv((uint32_t)u, a.fd_ks_mul, a.fd_ks_shr);
       const int k0 = (int)(u - (long long)tile * a.ksteps);
       const int k1 = (int)min((long long)a.ksteps, k0 + (u_end - u));
-      const bool whole = k0 == 0 && k1 == a.ksteps;
+      const bool tail = k0 > 0;                                // partial -> workspace slot blockIdx.x
+      const bool head = k0 == 0 && k1 < a.ksteps;              // owner: add the partial of CTA blockIdx.x + 1, finalise
       const uint32_t mt = fdiv(tile, a.fd_nt_mul, a.fd_nt_shr);
       const int col0 = (int)(tile - mt * (uint32_t)a.n_tiles) * 256 + chalf * 128;
+      if (head) {
+        if (et == 0) {
+          const int* f = a.ws_flags + blockIdx.x + 1;
+          int v;
+          long long t0 = clock64();
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (!v) {
+              __nanosleep(200);
+              if (clock64() - t0 > 6000000000ll) { printf("y2 conv_streamk: partial of CTA %d never arrived\n", blockIdx.x + 1); __trap(); }
+            }
+          } while (!v);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
+      }
       mbar_wait(&tmem_full, seg & 1u);
       tc_fence_after();
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const long long row = (long long)mt * 256 + h * 128 + q * 32 + lane;
-        float* dst = a.y + (size_t)row * a.ldy + col0;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + chalf * 128);
-#pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)c, v);
-          tmem_ld_wait();
-          if (h == 1 && c == 96) {                             // my last chunk is in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty);
-          }
-          if (row < a.M) {
+      // Partials use a lane-major layout (float4 #i of lane l at [i * 32 + l]) so that both the tail's stores and the
+      // head's loads are fully coalesced; the final rows go through a per-warp 128B-swizzled smem tile so that one store
+      // instruction covers whole 128-byte (float32) / 64-byte (bf16) row segments instead of 32 scattered 16-byte pieces.
+      const uint32_t stg = smem_base + SK_STAGES * SK_STAGE + (uint32_t)warp * SK_STG_WARP;
+      float4* part = reinterpret_cast<float4*>(a.ws_partial + (size_t)(tail ? blockIdx.x : blockIdx.x + 1) * 65536) +
+                     (size_t)warp * 2048 + lane;                  // + (h * 4 + c/32) * 256 + i * 32
+      float4 pv[8];
+      if (head) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float f0 = __uint_as_float(v[i]), f1 = __uint_as_float(v[i + 1]), f2 = __uint_as_float(v[i + 2]),
-                    f3 = __uint_as_float(v[i + 3]);
-              if (k0 == 0 && a.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + c + i));
-                f0 += b.x; f1 += b.y; f2 += b.z; f3 += b.w;
-              }
-              if (whole) *reinterpret_cast<float4*>(dst + c + i) = make_float4(f0, f1, f2, f3);
-              else red_add_v4(dst + c + i, f0, f1, f2, f3);
-            }
+        for (int i = 0; i < 8; ++i) pv[i] = __ldcg(part + i * 32);
+      }
+#pragma unroll 1
+      for (int hc = 0; hc < 8; ++hc) {
+        const int h = hc >> 2, c = (hc & 3) * 32;
+        const int row0 = h * 128 + q * 32;                        // first tile row of this warp's 32-row slab
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + chalf * 128 + c);
+        uint32_t v[32];
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        if (hc == 7) {                                         // my last chunk is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty);
+        }
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            __stcg(part + hc * 256 + i * 32, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+          continue;
+        }
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.scale) sc = __ldg(reinterpret_cast<const float4*>(a.scale + col0 + c) + i);
+          if (a.shift) sh = __ldg(reinterpret_cast<const float4*>(a.shift + col0 + c) + i);
+          const float4 p4 = head ? pv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          f[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]) + p4.x, sc.x, sh.x);
+          f[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]) + p4.y, sc.y, sh.y);
+          f[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]) + p4.z, sc.z, sh.z);
+          f[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]) + p4.w, sc.w, sh.w);
+        }
+        if (head && hc < 7) {                                  // prefetch the next chunk's partial behind this chunk's stores
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[i] = __ldcg(part + (hc + 1) * 256 + i * 32);
+        }
+        if (a.leaky) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], a.alpha * f[i]);
+        }
+        const long long grow0 = (long long)mt * 256 + row0;       // global row of slab row 0
+        if (a.out_f32) {
+          // lane = slab row: 8 x 16-byte units, unit j of row r at (j ^ (r & 7))
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((j ^ (lane & 7)) << 4)), "f"(f[4 * j]),
+                         "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                         : "memory");
+          __syncwarp();
+          float* dst = reinterpret_cast<float*>(a.y) + col0 + c;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int r = t * 4 + (lane >> 3), j = lane & 7;
+            float4 o;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                         : "r"(stg + r * 128 + ((j ^ (r & 7)) << 4)));
+            if (grow0 + r < a.M) *reinterpret_cast<float4*>(dst + (size_t)(grow0 + r) * a.ldy + j * 4) = o;
+          }
+        } else {
+          // bf16: 64-byte rows, 4 units, unit j of row r at (j ^ ((r >> 1) & 3))
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
+                         : "memory");
           }
           __syncwarp();
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + col0 + c;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int r = t * 8 + (lane >> 2), j = lane & 3;
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                         : "r"(stg + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)));
+            if (grow0 + r < a.M) *reinterpret_cast<uint4*>(dst + (size_t)(grow0 + r) * a.ldy + j * 8) = o;
+          }
+        }
+        __syncwarp();                                           // staging tile free for the next chunk
+      }
+      if (tail) {
+        __threadfence();                                       // my partial is visible device-wide ...
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // ... and so is everybody else's
+        if (et == 0) {
+          int one = 1;
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.ws_flags + blockIdx.x), "r"(one) : "memory");
         }
       }
       u += k1 - k0;
@@ -219,24 +310,36 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+static thread_local void* g_sk_ws = nullptr;
+static thread_local size_t g_sk_ws_bytes = 0;
+constexpr size_t SK_FLAG_BYTES = 4096;
+
+static size_t sk_workspace_bytes(int sms) { return SK_FLAG_BYTES + (size_t)sms * 256 * 256 * sizeof(float); }
+
 // returns Y2_OK and sets *handled = 1 when the layer was issued on this path
 int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   *handled = 0;
-  if (getenv("Y2_CONV_NO_STREAMK")) return Y2_OK;
-  if (p->flags != Y2_CONV_OUT_F32 || p->scale != nullptr) return Y2_OK;
+  if (getenv("Y2_CONV_NO_STREAMK") || g_sk_ws == nullptr) return Y2_OK;
+  if ((p->flags & Y2_CONV_POOL2) != 0) return Y2_OK;
   if (!(p->ksize == 1 || p->ksize == 3) || p->Cin % 64 != 0 || p->Cout % 256 != 0) return Y2_OK;
   if (p->H >= 64 && p->W >= 64) return Y2_OK;                   // large maps: the halo-patch mode of conv_tc_kernel wins
+  const bool out_f32 = (p->flags & Y2_CONV_OUT_F32) != 0;
   const int ldy = p->ldy > 0 ? p->ldy : p->Cout;
-  if (ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(p->y) & 15) != 0) return Y2_OK;
-  if (p->shift && (reinterpret_cast<uintptr_t>(p->shift) & 15) != 0) return Y2_OK;
+  if (ldy % (out_f32 ? 4 : 8) != 0 || (reinterpret_cast<uintptr_t>(p->y) & 15) != 0) return Y2_OK;
+  if ((p->shift && (reinterpret_cast<uintptr_t>(p->shift) & 15) != 0) || (p->scale && (reinterpret_cast<uintptr_t>(p->scale) & 15) != 0))
+    return Y2_OK;
   const int taps = p->ksize * p->ksize, cchunks = p->Cin / 64, ksteps = taps * cchunks;
-  if (ksteps < 64 || ksteps > SK_MAX_UNITS) return Y2_OK;       // short K: the un-overlapped epilogue would show
+  if (ksteps < 32 || ksteps > SK_MAX_UNITS) return Y2_OK;       // short K: the un-overlapped epilogue would show
   int rc = load_driver_entry_points();
   if (rc != Y2_OK) return rc;
   SkArgs a;
   memset(&a, 0, sizeof(a));
-  a.bias = p->shift;
-  a.y = reinterpret_cast<float*>(p->y);
+  a.scale = p->scale;
+  a.shift = p->shift;
+  a.y = p->y;
+  a.alpha = p->alpha;
+  a.leaky = (p->flags & Y2_CONV_LEAKY) != 0;
+  a.out_f32 = out_f32;
   a.M = (long long)p->N * p->H * p->W;
   a.H = p->H; a.W = p->W; a.ldy = ldy; a.pad = p->ksize / 2;
   a.cin_p = p->Cin; a.cchunks = cchunks; a.ksteps = ksteps;
@@ -245,12 +348,15 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   a.tiles = (int)(m_tiles * a.n_tiles);
   a.units = (long long)a.tiles * ksteps;
   if ((a.tiles < g_num_sms / 2 && !getenv("Y2_CONV_FORCE_STREAMK")) || a.units >= (1ll << 31) || a.M + 256 >= (1ll << 31)) return Y2_OK;
+  // every CTA's range must be at least one tile long (a tile is then shared by at most two CTAs)
+  const int grid = a.tiles < g_num_sms ? a.tiles : g_num_sms;
+  if (g_sk_ws_bytes < sk_workspace_bytes(grid)) return Y2_OK;
+  a.ws_flags = reinterpret_cast<int*>(g_sk_ws);
+  a.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_sk_ws) + SK_FLAG_BYTES);
   fastdiv_init((uint32_t)a.n_tiles, &a.fd_nt_mul, &a.fd_nt_shr);
   fastdiv_init((uint32_t)p->W, &a.fd_w_mul, &a.fd_w_shr);
   fastdiv_init((uint32_t)p->H, &a.fd_h_mul, &a.fd_h_shr);
   fastdiv_init((uint32_t)ksteps, &a.fd_ks_mul, &a.fd_ks_shr);
-  // every CTA's range must be at least one tile long (<= 2 CTAs per tile -> order-independent additions)
-  const int grid = a.tiles < g_num_sms ? a.tiles : g_num_sms;
 
   CUtensorMap tmA, tmB;
   {
@@ -281,14 +387,9 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
       return Y2_ERR_DRIVER;
     }
   }
-  const size_t smem = (size_t)SK_STAGES * SK_STAGE + 1024;
+  const size_t smem = (size_t)SK_STAGES * SK_STAGE + 8 * SK_STG_WARP + 1024;
   Y2_CUDA(cudaFuncSetAttribute(conv_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // partial segments add into the output: zero the rows first (the columns [Cout, ldy) padding is left alone)
-  if (ldy == p->Cout) {
-    Y2_CUDA(cudaMemsetAsync(p->y, 0, (size_t)a.M * ldy * sizeof(float), st));
-  } else {
-    Y2_CUDA(cudaMemset2DAsync(p->y, (size_t)ldy * sizeof(float), 0, (size_t)p->Cout * sizeof(float), (size_t)a.M, st));
-  }
+  Y2_CUDA(cudaMemsetAsync(a.ws_flags, 0, (size_t)(grid + 1) * sizeof(int), st));
   conv_streamk_kernel<<<grid, SK_THREADS, smem, st>>>(tmA, tmB, a);
   Y2_LAUNCHED();
   *handled = 1;
@@ -296,3 +397,17 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
 }
 
 }  // namespace y2
+
+using namespace y2;
+
+extern "C" size_t y2_conv_workspace_bytes(void) {
+  if (load_driver_entry_points() != Y2_OK) return 0;
+  return sk_workspace_bytes(g_num_sms);
+}
+
+extern "C" int y2_conv_set_workspace(void* workspace, size_t bytes) {
+  Y2_ARG(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  g_sk_ws = workspace;
+  g_sk_ws_bytes = workspace ? bytes : 0;
+  return Y2_OK;
+}

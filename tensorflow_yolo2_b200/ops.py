@@ -93,6 +93,7 @@ def conv_fwd_bf16(x, w_packed, ksize, cin, cout, scale=None, shift=None, leaky=T
     """x bf16 [N,H,W,Cin_p]; returns bf16 [N,Ho,Wo,Cout] or (out_f32) f32 [N*H*W, ldy]."""
     N, H, W, cin_p = x.shape
     assert cin_p == conv_cin_padded(cin), (cin_p, cin)
+    _ensure_conv_workspace(x.device)
     flags = (Y2_CONV_LEAKY if leaky else 0) | (Y2_CONV_POOL2 if pool else 0) | (Y2_CONV_OUT_F32 if out_f32 else 0)
     ld = int(ldy) if ldy else cout
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
@@ -107,6 +108,38 @@ def conv_fwd_bf16(x, w_packed, ksize, cin, cout, scale=None, shift=None, leaky=T
                      flags=flags, alpha=alpha, ldy=ld, reserved=0)
     check(_lib.load().y2_conv_fwd_bf16(C.byref(prm), _stream()), 'y2_conv_fwd_bf16')
     return out
+
+
+_conv_ws = {}
+
+
+def conv_workspace(device=None):
+    """Allocate (once per device) and register the stream-K scratch of y2_conv_fwd_bf16 for the calling thread."""
+    device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+    ws = _conv_ws.get(device)
+    if ws is None:
+        with torch.cuda.device(device):
+            ws = torch.empty((int(_lib.load().y2_conv_workspace_bytes()),), dtype=torch.uint8, device=device)
+        _conv_ws[device] = ws
+    check(_lib.load().y2_conv_set_workspace(_p(ws), ws.numel()), 'y2_conv_set_workspace')
+    return ws
+
+
+def conv_clear_workspace():
+    _tls.conv_ws_device = None
+    check(_lib.load().y2_conv_set_workspace(None, 0), 'y2_conv_set_workspace')
+
+
+import threading as _threading
+
+_tls = _threading.local()
+
+
+def _ensure_conv_workspace(device):
+    """The C ABI keeps the registered scratch per calling thread: register this device's buffer once per thread."""
+    if getattr(_tls, 'conv_ws_device', None) != device:
+        conv_workspace(device)
+        _tls.conv_ws_device = device
 
 
 def pack_weights_conv1_u8(w_hwio, scale=None, out=None):

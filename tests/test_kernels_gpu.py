@@ -77,32 +77,41 @@ def test_conv_f32_vs_oracle(ops, N, H, W, Cin, Cout, k):
 
 
 # ---------------------------------------------------------------------------------- a1 stream-K 256x256 path
-@pytest.mark.parametrize('N,S,Cin,Cout,k', [(16, 13, 512, 512, 3), (9, 13, 1024, 256, 3), (6, 19, 1024, 256, 3)])
-def test_conv_streamk_vs_generic_and_oracle(ops, monkeypatch, N, S, Cin, Cout, k):
-    """float32 pre-BN rows of a deep 3x3 layer: the 256x256 stream-K kernel (partial K ranges combined with
-    red.global.add) against the generic tcgen05 kernel and the oracle; and bit-identical across repeated runs
-    (at most two additions per element -> order-independent)."""
+@pytest.mark.parametrize('N,S,Cin,Cout,k,out_f32', [(16, 13, 512, 512, 3, True), (9, 13, 1024, 256, 3, False),
+                                                    (6, 19, 1024, 256, 3, True), (8, 26, 256, 512, 3, False)])
+def test_conv_streamk_vs_generic_and_oracle(ops, monkeypatch, N, S, Cin, Cout, k, out_f32):
+    """Deep 3x3 layer on a small map: the 256x256 stream-K kernel (a tile's K range split between two CTAs, the partial
+    travels through the workspace and the owner runs the fused epilogue) against the generic tcgen05 kernel and the
+    oracle, for the float32 pre-BN output and for the fused scale/shift/leaky bf16 output; bit-identical across runs."""
     rs = np.random.RandomState(S + Cout)
     x = rs.randn(N, S, S, Cin).astype(np.float32)
     w = (rs.randn(k, k, Cin, Cout) * 0.05).astype(np.float32)
     b = rs.randn(Cout).astype(np.float32)
+    sc = None if out_f32 else (rs.uniform(0.5, 1.5, Cout) * np.where(rs.rand(Cout) < 0.3, -1, 1)).astype(np.float32)
     xb = cu(x, torch.bfloat16)
     wp = ops.pack_weights_bf16(cu(w))
+    kw = dict(scale=None if sc is None else cu(sc), shift=cu(b), leaky=not out_f32, out_f32=out_f32)
     monkeypatch.setenv('Y2_CONV_NO_STREAMK', '1')
-    n0 = ops.launch_count()
-    ref = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, scale=None, shift=cu(b), leaky=False, out_f32=True).cpu().numpy()
-    assert ops.launch_count() - n0 == 1
+    ref = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw).float().cpu().numpy().reshape(-1, Cout)
     monkeypatch.delenv('Y2_CONV_NO_STREAMK')
     monkeypatch.setenv('Y2_CONV_FORCE_STREAMK', '1')           # small test shapes have fewer tiles than the auto rule wants
-    got1 = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, scale=None, shift=cu(b), leaky=False, out_f32=True)
-    got2 = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, scale=None, shift=cu(b), leaky=False, out_f32=True)
+    got1 = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw)
+    got2 = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw)
     torch.cuda.synchronize()
     assert torch.equal(got1, got2)
-    got = got1.cpu().numpy()
-    np.testing.assert_allclose(got, ref, rtol=2e-4, atol=2e-4 * np.abs(ref).max())     # fp32 accumulation order differs
-    want = (O.conv2d_same(O.bf16_round(torch.tensor(x)).double(), O.bf16_round(torch.tensor(w)).double(), torch.float64)
-            + torch.tensor(b).double()).numpy().reshape(-1, Cout)
-    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
+    got = got1.float().cpu().numpy().reshape(-1, Cout)
+    tol = 2e-4 if out_f32 else 1e-2                             # fp32 accumulation order / one bf16 ulp
+    np.testing.assert_allclose(got, ref, rtol=tol, atol=tol * np.abs(ref).max())
+    want = O.conv2d_same(O.bf16_round(torch.tensor(x)).double(), O.bf16_round(torch.tensor(w)).double(), torch.float64)
+    if sc is not None:
+        want = want * torch.tensor(sc).double()
+    want = want + torch.tensor(b).double()
+    if not out_f32:
+        want = torch.maximum(O.ALPHA * want, want)
+    want = want.numpy().reshape(-1, Cout)
+    tol = 1e-3 if out_f32 else 1e-2
+    np.testing.assert_allclose(got, want, rtol=tol, atol=tol * np.abs(want).max())
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < (1e-4 if out_f32 else 4e-3)
 
 
 # ---------------------------------------------------------------------------------- a2 / a3
