@@ -223,6 +223,63 @@ __device__ __forceinline__ void epilogue_chunk(const ConvArgs& a, const uint32_t
   }
 }
 
+// Pooled bf16 epilogue, 32 accumulator columns of one row per lane -> 8 output columns of one POOLED pixel per lane.
+//   max-pool commutes with any increasing map, and x -> leaky(s*x + b) is increasing in sign(s)*x.  So the 2x2 max runs
+//   first, on the raw accumulators with the sign of the channel's scale folded in, and the affine + leaky + convert run
+//   on the pooled quarter only.  The pooling itself is a recursive halving instead of a butterfly: in each of the two
+//   exchange steps a lane hands half of its columns to the partner and keeps the max over the other half, so that the
+//   four lanes of a window end up with DIFFERENT 8-column slices of the result (16 B each, 64 contiguous bytes per
+//   window) and every lane does useful work in the affine / store phase.  ~2x fewer instructions than
+//   affine+leaky on all four pixels followed by a butterfly max -- the layers with few input channels (Cin = 32)
+//   are bound by exactly these epilogue instructions (63 M warp instructions for layer 2 in the profile).
+__device__ __forceinline__ void epilogue_chunk_pooled_bf16(const ConvArgs& a, const uint32_t* v, const float* s_scale,
+                                                           const float* s_shift, int cc, int c0, bool valid_px, long long orow,
+                                                           bool leaky_on, int lane) {
+  float t[32];
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const uint4 sb = *reinterpret_cast<const uint4*>(&s_scale[cc + i]);     // smem broadcast
+    t[i + 0] = __uint_as_float(v[i + 0] ^ (sb.x & 0x80000000u));
+    t[i + 1] = __uint_as_float(v[i + 1] ^ (sb.y & 0x80000000u));
+    t[i + 2] = __uint_as_float(v[i + 2] ^ (sb.z & 0x80000000u));
+    t[i + 3] = __uint_as_float(v[i + 3] ^ (sb.w & 0x80000000u));
+  }
+  const bool up1 = (lane & 1) != 0;                       // horizontal partner: lane ^ 1 (tile width >= 2)
+  float m16[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float send = up1 ? t[i] : t[16 + i];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    m16[i] = fmaxf(up1 ? t[16 + i] : t[i], recv);
+  }
+  const bool up2 = ((lane >> a.tw_log2) & 1) != 0;        // vertical partner: lane ^ TW
+  float m8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = up2 ? m16[i] : m16[8 + i];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 1 << a.tw_log2);
+    m8[i] = fmaxf(up2 ? m16[8 + i] : m16[i], recv);
+  }
+  const int cb = (up1 ? 16 : 0) + (up2 ? 8 : 0);          // my 8 columns of the chunk
+  const float4 sa = *reinterpret_cast<const float4*>(&s_scale[cc + cb]), sb4 = *reinterpret_cast<const float4*>(&s_scale[cc + cb + 4]);
+  const float4 ha = *reinterpret_cast<const float4*>(&s_shift[cc + cb]), hb4 = *reinterpret_cast<const float4*>(&s_shift[cc + cb + 4]);
+  const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb4.x, sb4.y, sb4.z, sb4.w};
+  const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb4.x, hb4.y, hb4.z, hb4.w};
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    f[i] = fmaf(m8[i], fabsf(sc[i]), sh[i]);
+    if (leaky_on) f[i] = fmaxf(f[i], a.alpha * f[i]);
+  }
+  if (valid_px) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)orow * a.ldy + c0 + cb;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+  }
+}
+
 // KIND: 0 = first layer (Cin 3 -> 8, un-swizzled 16-byte rows), 1 = 64-byte rows (Cin 32), 2 = 128-byte rows
 template <int BLOCK_N, int A_MODE, int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -550,7 +607,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         staged_ntile = t.n_tile;
       }
       // ---- where does my row go? ----
-      bool valid;
+      bool valid, valid_px = false;
       long long orow;     // output pixel row index
       if constexpr (A_MODE == 0) {
         const long long m = t.m0 + r;
@@ -558,7 +615,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         orow = m;
       } else {
         const int n = t.n0 + r_nb, h = t.h0 + r_th, w = t.w0 + r_tw;
-        valid = n < a.N && h < a.H && w < a.W && (!pool || r_even);
+        valid_px = n < a.N && h < a.H && w < a.W;
+        valid = valid_px && (!pool || r_even);
         orow = (long long)((n * Ho + (pool ? h >> 1 : h)) * Wo + (pool ? w >> 1 : w));   // < 2^31 (host-checked)
       }
       mbar_wait(&tmem_full_bar[buf], ((uint32_t)it / NBUF) & 1u);
@@ -576,7 +634,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
         const int c0 = nbase + cc;
-        if (c0 < a.ldy) epilogue_chunk<32>(a, v, my_scale, my_shift, cc, c0, valid, orow, pool, leaky_on, out_f32);
+        if (A_MODE != 0 && pool && !out_f32 && c0 + 32 <= a.Cout && (a.ldy & 7) == 0) {
+          epilogue_chunk_pooled_bf16(a, v, my_scale, my_shift, cc, c0, valid_px, orow, leaky_on, lane);
+        } else if (c0 < a.ldy) {
+          epilogue_chunk<32>(a, v, my_scale, my_shift, cc, c0, valid, orow, pool, leaky_on, out_f32);
+        }
         __syncwarp();                               // reconverge before the next .sync.aligned TMEM load
       }
     }
