@@ -16,9 +16,9 @@
 //      with warp-local reads, and runs the greedy sweep -- for <= 32 candidates entirely in registers (one candidate
 //      per lane, corner broadcast by shuffle, suppression mask by ballot).
 // Keep lists are bit-identical to the oracle's NMS on the kernel's own boxes / scores (unfused IEEE IoU ops).
-// Images where some class has more than DF_CAPK candidates (only with a near-zero threshold) are flagged
-// keep_count = -1 and re-done by nms_kernel (bit-matrix algorithm) in a second, normally empty, launch.
-#include "nms_common.cuh"
+// Images where some class has more than DF_CAPK candidates (only with a near-zero threshold) are redone in place by
+// the same CTA with the general algorithm of nms.cu (nms_body.cuh) on the dense scores it has just written.
+#include "nms_body.cuh"
 
 namespace y2 {
 
@@ -33,7 +33,7 @@ template <int C>
 __global__ void __launch_bounds__(DF_THREADS, 2) detect_fused_kernel(
     const float* __restrict__ net, const float* __restrict__ anchors, int S, int A, float score_thresh, float iou_thresh,
     float* __restrict__ boxes, float* __restrict__ scores, int32_t* __restrict__ keep_idx,
-    int32_t* __restrict__ keep_count, float* __restrict__ keep_score, int max_keep, int cells_per_chunk) {
+    int32_t* __restrict__ keep_count, float* __restrict__ keep_score, int max_keep, int cells_per_chunk, size_t smem_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_cnt[C];
   __shared__ unsigned char s_removed[C * DF_CAPK];
@@ -134,8 +134,15 @@ __global__ void __launch_bounds__(DF_THREADS, 2) detect_fused_kernel(
     bool overflow = false;
 #pragma unroll
     for (int k = 0; k < C; ++k) overflow |= s_cnt[k] > DF_CAPK;
-    if (overflow) {                                     // rare: hand the image to the bit-matrix kernel
-      for (int k = tid; k < C; k += DF_THREADS) kc[k] = -1;
+    if (overflow) {
+      // rare (near-zero threshold): redo the image in place with the general bit-matrix algorithm of nms.cu on the
+      // dense scores this CTA has just written (visible to the whole block after the barrier above)
+      if (scores == nullptr) {
+        for (int k = tid; k < C; k += DF_THREADS) kc[k] = -1;         // reported, not silently dropped
+        return;
+      }
+      nms_image_fallback<DF_THREADS>(smem_raw, smem_bytes, boxes, scores, img, nbox, C, score_thresh, iou_thresh, keep_idx,
+                                     keep_count, keep_score, max_keep);
       return;
     }
   }
@@ -228,10 +235,6 @@ static size_t df_smem_bytes(int nbox, int cells_per_chunk, int ch, int C) {
   return (size_t)nbox * 16 + (size_t)C * DF_CAPK * 8 + ((size_t)cells_per_chunk * ch + 4) * 4;
 }
 
-// defined in nms.cu
-int launch_nms_flagged(const float* boxes, const float* scores, int N, int nbox, int C, float score_thresh, float iou_thresh,
-                       int32_t* keep_idx, int32_t* keep_count, float* keep_score, int max_keep, cudaStream_t st);
-
 }  // namespace y2
 
 using namespace y2;
@@ -256,9 +259,7 @@ extern "C" int y2_detect_fused(const float* net, const float* anchors, int N, in
     configured = smem;
   }
   detect_fused_kernel<20><<<N, DF_THREADS, smem, st>>>(net, anchors, S, A, score_thresh, iou_thresh, boxes, scores, keep_idx,
-                                                       keep_count, keep_score, max_keep, cells_per_chunk);
+                                                       keep_count, keep_score, max_keep, cells_per_chunk, smem);
   Y2_LAUNCHED();
-  if (scores) return launch_nms_flagged(boxes, scores, N, nbox, C, score_thresh, iou_thresh, keep_idx, keep_count, keep_score, max_keep,
-                                        st);
   return Y2_OK;
 }
