@@ -56,6 +56,7 @@ struct ConvArgs {
   int b_stationary;       // whole B operand resident in smem for the CTA's lifetime (n_tiles == 1, small B)
   uint32_t b_total_bytes;
   int sps;                // (tap, channel-chunk) sub-blocks per pipeline stage
+  int kw_merge;           // mode 2: the three horizontally shifted patches share one stage (stationary B, one chunk)
   int stages_per_tile;    // kblocks / sps
   uint32_t a_sub_bytes, b_sub_bytes;
   uint32_t tx_bytes;      // A bytes the TMA reports per stage
@@ -368,7 +369,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =========================== TMA producer ===========================
     // The whole warp runs the loop; lane 0 owns the barrier handshake and the stage's TMA loads are issued
     // by different lanes in the same instruction slot.
-    int stage = 0;
     uint32_t phase = 0;
     const int sps = a.sps;
     if (a.b_stationary) {
@@ -387,18 +387,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       __syncwarp();
     }
+    const uint32_t full0 = opaque(smem_u32(&full_bar[0])), empty0 = opaque(smem_u32(&empty_bar[0]));
+    const uint32_t nstages = opaque((uint32_t)a.stages);
+    const int spt = (int)opaque((uint32_t)a.stages_per_tile);
+    uint32_t ustage = 0, soffb = 0;                      // stage index and its byte offset
     for (int tile = sched_first; tile < total_tiles; tile += sched_step) {
       const TileCoord t = decode_tile(a, tile, crank);
       const int nrow0 = t.n_tile * BLOCK_N;
-      for (int st = 0; st < a.stages_per_tile; ++st) {
+      for (int st = 0; st < spt; ++st) {
+        const uint32_t bar = full0 + 8u * ustage;
         if (lane == 0) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          mbar_wait_a(empty0 + 8u * ustage, phase ^ 1u);
+          mbar_expect_tx_a(bar, tx_bytes);
         }
         __syncwarp();
-        const uint32_t sA = smem_base + stage * stage_bytes;
+        const uint32_t sA = smem_base + soffb;
         const uint32_t sB = sA + a.a_stage_bytes;
-        const uint32_t bar = smem_u32(&full_bar[stage]);
         if constexpr (FIRST && A_MODE == 2) {
           // halo patch: ONE 18-row x 10-pixel x 16-byte load serves all 9 taps (shifted UMMA descriptors)
           if (lane == 0) tma_load_3d(sA, &tmA, bar, (t.w0 - 1) * 8, t.h0 - 1, t.n0);
@@ -417,17 +421,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_3d(sB, &tmB, bar, 0, nrow0, 0);
           }
         } else if constexpr (A_MODE == 2) {
-          // one horizontally shifted (16+2)-row patch serves the three taps kh = 0..2 of this kw
-          const UnitDesc d = s_units[st];
-          if (lane == 0) {
-            tma_load_4d(sA, &tmA, bar, d.a_c0, t.w0 + d.kw - 1, t.h0 - 1, t.n0);
-          } else if (lane < 4 && !a.b_stationary) {
-            const int kh = lane - 1;
-            if (CS > 1)
-              tma_load_2d_mc(sB + kh * a.b_sub_bytes + crank * (a.b_sub_bytes / CS), &tmB, bar, d.b_k + kh * 3 * a.cin_p,
-                             nrow0 + (int)crank * (BLOCK_N / CS), mc_mask);
-            else
-              tma_load_2d(sB + kh * a.b_sub_bytes, &tmB, bar, d.b_k + kh * 3 * a.cin_p, nrow0);
+          if (a.kw_merge) {
+            // the three horizontally shifted (16+2)-row patches of the single channel chunk, one lane each
+            if (lane < 3) tma_load_4d(sA + (uint32_t)lane * a.a_sub_bytes, &tmA, bar, 0, t.w0 + lane - 1, t.h0 - 1, t.n0);
+          } else {
+            // one horizontally shifted (16+2)-row patch serves the three taps kh = 0..2 of this kw
+            const UnitDesc d = s_units[st];
+            if (lane == 0) {
+              tma_load_4d(sA, &tmA, bar, d.a_c0, t.w0 + d.kw - 1, t.h0 - 1, t.n0);
+            } else if (lane < 4 && !a.b_stationary) {
+              const int kh = lane - 1;
+              if (CS > 1)
+                tma_load_2d_mc(sB + kh * a.b_sub_bytes + crank * (a.b_sub_bytes / CS), &tmB, bar, d.b_k + kh * 3 * a.cin_p,
+                               nrow0 + (int)crank * (BLOCK_N / CS), mc_mask);
+              else
+                tma_load_2d(sB + kh * a.b_sub_bytes, &tmB, bar, d.b_k + kh * 3 * a.cin_p, nrow0);
+            }
           }
         } else {
 #if Y2_PRODUCER_SINGLE
@@ -469,13 +478,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
         }
         __syncwarp();
-        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        ++ustage;
+        soffb += stage_bytes;
+        if (ustage == nstages) { ustage = 0; soffb = 0; phase ^= 1u; }
       }
     }
   } else if (warp == WARP_MMA) {
     // =========================== MMA issuer ===========================
     // The whole warp walks the loop with warp-uniform values (so descriptors live in uniform registers and
     // an MMA costs a handful of instructions); one elected lane issues tcgen05.mma / tcgen05.commit.
+    // This warp is the critical path of every layer whose stages hold few MMAs (profile of layer 2: ~140 dependent
+    // instructions = ~800 clk per stage against 192 clk of tensor work), so the loop carries everything as running
+    // 32-bit values -- barrier addresses, stage offsets, the stationary-B cursor -- instead of recomputing them from
+    // pointers, selects and the unit table each stage.
     uint32_t is_leader;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(is_leader));
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N, M=128
@@ -496,19 +511,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t khshift16 = FIRST ? 0u : (8u * ROW_BYTES) >> 4;          // mode 2: one patch row = one swizzle atom
     const int subs = FIRST ? 1 : a.sps;
     const bool bstat = a.b_stationary != 0;
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
+    const uint32_t full0 = opaque(smem_u32(&full_bar[0])), empty0 = opaque(smem_u32(&empty_bar[0]));
+    const uint32_t tfull0 = opaque(smem_u32(&tmem_full_bar[0])), tempty0 = opaque(smem_u32(&tmem_empty_bar[0]));
+    const uint32_t nstages = opaque((uint32_t)a.stages);
+    const int spt = (int)opaque((uint32_t)a.stages_per_tile);
+    // B descriptor offset: streamed B lives in the stage (stage * stage16); stationary B is addressed by a cursor
+    // that runs through the resident filter bank once per tile (modes 0/1) or by the unit's tap index (mode 2)
+    const uint32_t b_stage_inc = bstat ? 0u : stage16;
+    const uint32_t b_cursor_inc = bstat ? (uint32_t)subs * b_sub16 : 0u;
+    const uint32_t b_unit_mul = bstat ? b_sub16 : 0u;                                   // mode 2
+    const uint32_t b_kh_mul = bstat ? (uint32_t)(3 * a.cchunks) * b_sub16 : b_sub16;    // mode 2
+    uint32_t stage = 0, phase = 0, soff = 0, bsoff = 0;
+    uint32_t it = 0;
     for (int tile = sched_first; tile < total_tiles; tile += sched_step, ++it) {
-      const int buf = it % NBUF;
-      mbar_wait(&tmem_empty_bar[buf], (((uint32_t)it / NBUF) & 1u) ^ 1u);
+      const uint32_t buf = it % NBUF;
+      mbar_wait_a(tempty0 + 8u * buf, ((it / NBUF) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BLOCK_N);
+      const uint32_t tmem_d = tmem_base + buf * (uint32_t)BLOCK_N;
       uint32_t accum = 0;
-      for (int st = 0; st < a.stages_per_tile; ++st) {
-        mbar_wait(&full_bar[stage], phase);
+      uint32_t bcur = 0;
+      for (int st = 0; st < spt; ++st) {
+        uint32_t bidx0 = 0;
+        if constexpr (A_MODE == 2 && !FIRST) {
+          if (!a.kw_merge) bidx0 = (uint32_t)s_units[st].kh;   // mode 2: kh field carries the stationary B index of kh = 0
+        }
+        // descriptors of this stage are ready before the barrier is: after the wait only the MMAs issue
+        const uint64_t ad_s = adesc0 + soff;
+        const uint64_t bd_s = bdesc0 + bsoff + ((A_MODE == 2 && !FIRST) ? bidx0 * b_unit_mul : bcur);
+        const uint32_t empty_addr = empty0 + 8u * stage;
+        mbar_wait_a(full0 + 8u * stage, phase);
         tc_fence_after();
-        const uint32_t soff = (uint32_t)stage * stage16;
         if constexpr (FIRST && A_MODE == 2) {
           // patch [18][10 px][8 ch]: pixel = 16 B, 8 consecutive pixels = one un-swizzled core matrix.
           // MMA p multiplies k-groups (2p, 2p+1): A start = first tap's pixel shift, LBO = distance to the
@@ -521,48 +553,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int t0 = pr < 4 ? 2 * pr : 7, t1 = pr < 4 ? 2 * pr + 1 : 8;
               const int o0 = ((t0 / 3) * 10 + (t0 % 3)) * 16, o1 = ((t1 / 3) * 10 + (t1 % 3)) * 16;
               const uint64_t ad = make_smem_desc(sA + o0, (uint32_t)(o1 - o0), 160u, 0u);
-              const uint64_t bd = (bstat ? bdesc0 : bdesc0 + soff) + (uint32_t)pr * b_kstep;
+              const uint64_t bd = bdesc0 + bsoff + (uint32_t)pr * b_kstep;
               umma_bf16(tmem_d, ad, bd, idesc, accum);
               accum = 1;
             }
           }
         } else if constexpr (A_MODE == 2) {
-          const UnitDesc d = s_units[st];
-          const uint32_t bidx0 = (uint32_t)d.kh;            // mode 2: kh field carries the stationary B index of kh = 0
           if (is_leader) {
+            if (a.kw_merge) {
+              // all three horizontally shifted patches in one stage, stationary B indexed by tap = kh * 3 + kw
+              // (one channel chunk): 9 * KSTEPS MMAs behind a single barrier round trip, every offset a constant
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              const uint64_t ad = adesc0 + soff + (uint32_t)kh * khshift16;      // rows of tap (kh,kw) = patch rows + kh
-              const uint64_t bd = bstat ? bdesc0 + (bidx0 + (uint32_t)(kh * 3 * a.cchunks)) * b_sub16
-                                        : bdesc0 + soff + (uint32_t)kh * b_sub16;
+              for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-              for (int ks = 0; ks < KSTEPS; ++ks) {
-                umma_bf16(tmem_d, ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep, idesc, accum);
-                accum = 1;
+                for (int kh = 0; kh < 3; ++kh) {
+                  const uint64_t ad = ad_s + (uint32_t)kw * a_sub16 + (uint32_t)kh * khshift16;
+                  const uint64_t bd = bd_s + (uint32_t)(kh * 3 + kw) * b_sub16;     // (bd_s == bdesc0: stationary, bidx0 = 0)
+#pragma unroll
+                  for (int ks = 0; ks < KSTEPS; ++ks) {
+                    umma_bf16(tmem_d, ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep, idesc, accum);
+                    accum = 1;
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+                const uint64_t ad = ad_s + (uint32_t)kh * khshift16;           // rows of tap (kh,kw) = patch rows + kh
+                const uint64_t bd = bd_s + (uint32_t)kh * b_kh_mul;
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                  umma_bf16(tmem_d, ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep, idesc, accum);
+                  accum = 1;
+                }
               }
             }
           }
         } else {
           if (is_leader) {
+            uint64_t ad = ad_s;
+            uint64_t bd = bd_s;
+#pragma unroll 1
             for (int j = 0; j < subs; ++j) {
-              const uint64_t ad = adesc0 + soff + (uint32_t)j * a_sub16;
-              const uint64_t bd = bstat ? bdesc0 + (uint32_t)(st * subs + j) * b_sub16 : bdesc0 + soff + (uint32_t)j * b_sub16;
 #pragma unroll
               for (int ks = 0; ks < KSTEPS; ++ks) {
                 umma_bf16(tmem_d, ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep, idesc, accum);
                 accum = 1;
               }
+              ad += a_sub16;
+              bd += b_sub16;
             }
           }
+          bcur += b_cursor_inc;
         }
         if (is_leader) {
-          if (CS > 1) umma_commit_mc(&empty_bar[stage], mc_mask);   // release the stage in every CTA of the cluster
-          else umma_commit(&empty_bar[stage]);                      // frees the smem stage when these MMAs retire
+          if (CS > 1) umma_commit_mc_a(empty_addr, mc_mask);   // release the stage in every CTA of the cluster
+          else umma_commit_a(empty_addr);                      // frees the smem stage when these MMAs retire
         }
         __syncwarp();
-        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        ++stage;
+        soff += stage16;
+        bsoff += b_stage_inc;
+        if (stage == nstages) { stage = 0; phase ^= 1u; soff = 0; bsoff = 0; }
       }
-      if (is_leader) umma_commit(&tmem_full_bar[buf]);               // accumulator complete -> epilogue
+      if (is_leader) umma_commit_a(tfull0 + 8u * buf);               // accumulator complete -> epilogue
       __syncwarp();
     }
   } else {
@@ -901,6 +955,16 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   const size_t SMEM_BUDGET = 218 * 1024;           // dynamic smem for operands (static smem + slack stay below 227 KB)
   a.b_stationary = (a.n_tiles == 1 && a.b_total_bytes + 4 * (size_t)a.a_stage_bytes <= SMEM_BUDGET &&
                     !getenv("Y2_CONV_NO_BSTAT")) ? 1 : 0;
+  // halo-patch mode with a resident filter bank and a single channel chunk (layer 2: Cin = 32): the three
+  // horizontally shifted patches share ONE stage, so the MMA warp issues all 9 taps behind one barrier round trip.
+  // With one patch per stage that warp's ~800 clk of per-stage bookkeeping hid 192 clk of tensor work (ncu, r1c).
+  if (a.a_mode == 2 && !a.first_layer && a.b_stationary && a.cchunks == 1 &&
+      a.b_total_bytes + 3 * (size_t)(3 * a.a_sub_bytes) <= SMEM_BUDGET && !getenv("Y2_CONV_NO_KWMERGE")) {
+    a.kw_merge = 1;
+    a.a_stage_bytes = 3 * a.a_sub_bytes;
+    a.stages_per_tile = 1;
+    a.tx_bytes = a.a_stage_bytes;
+  }
   // CTA pairs with B multicast (opt-in, Y2_CONV_CLUSTER=1): each CTA fetches half of the B tile for both.
   // Measured on B200 it is ~15% SLOWER than independent CTAs: the kernel is bound by bytes delivered into
   // each SM (~49 B/clk/SM), which multicast does not reduce -- see DESIGN.md.
