@@ -310,6 +310,284 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2).  Why: with cta_group::1 every MMA fetches its whole A (128 x 16) and B
+// (N x 16) slice from the issuing SM's shared memory, and that operand path moves ~64 B/clk: 12 KB = 192 clk for a
+// 128 x 256 x 16 MMA whose arithmetic takes 128 clk.  ncu on the single-CTA kernels (profiles/r1c): 101 / 146 / 192 clk
+// per MMA at N = 64 / 128 / 256, i.e. (4096 + 32 N) / 64 -- the tensor pipe tops out at 67 % however the loop is
+// written.  A CTA pair computes one 256 x 256 tile with M = 256 MMAs: each SM supplies its own 128 rows of A and HALF
+// of the B rows (8 KB per MMA = the 128 clk of arithmetic) and accumulates its 128 rows in its own TMEM.
+//   * both CTAs run a TMA producer (own A half, own B half) that signals the LEADER's full barrier (cta_group::2 loads,
+//     leader-mapped barrier address); the leader alone expects the 64 KB of both;
+//   * the leader's MMA warp issues tcgen05.mma.cta_group::2 and commits with a multicast arrive to the empty / tmem_full
+//     barriers of both CTAs; the follower's MMA warp only allocates / frees TMEM;
+//   * each CTA's 8 epilogue warps drain their own 128 x 256 accumulator and arrive on the leader's tmem_empty.
+// The accumulator is 256 of the 512 TMEM columns, so segments alternate between two buffers and the epilogue of one
+// segment overlaps the MMAs of the next.  Stream-K split, partial hand-over and epilogue as above, per CTA pair:
+// pair c's head waits for the partials of pair c + 1 (same rank: same rows), slots / flags indexed by blockIdx.x.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SK2_STAGES = 6;                  // 32 KB each per CTA: A 128 px x 128 B, B 128 filters x 128 B
+constexpr uint32_t SK2_A_BYTES = 128 * 128, SK2_STAGE = 2 * 128 * 128;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SK_THREADS, 1)
+conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SkArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[SK2_STAGES], empty_bar[SK2_STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ uint8_t s_unit_tap[SK_MAX_UNITS], s_unit_cc[SK_MAX_UNITS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t rank = cluster_ctarank();                      // 0 = leader (issues the MMAs)
+  const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+
+  // the pair's contiguous range of (tile, K-step) units
+  const long long u_begin = a.units * pair / npairs, u_end = a.units * (pair + 1) / npairs;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      for (int s = 0; s < SK2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 16); }   // 8 warps x 2 CTAs
+      fence_barrier_init();
+    }
+    for (int u = lane; u < a.ksteps; u += 32) {
+      const int tap = u / a.cchunks;
+      s_unit_tap[u] = (uint8_t)tap;
+      s_unit_cc[u] = (uint8_t)(u - tap * a.cchunks);
+    }
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                           // the partner's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 8) {
+    // =========================== TMA producer (both CTAs) ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long u = u_begin;
+      while (u < u_end) {
+        const uint32_t tile = (uint32_t)fdiv((uint32_t)u, a.fd_ks_mul, a.fd_ks_shr);       // units < 2^31 (host-checked)
+        const int k0 = (int)(u - (long long)tile * a.ksteps);
+        const int k1 = (int)min((long long)a.ksteps, k0 + (u_end - u));
+        const uint32_t mt = fdiv(tile, a.fd_nt_mul, a.fd_nt_shr);
+        const int nrow0 = (int)(tile - mt * (uint32_t)a.n_tiles) * 256 + (int)rank * 128;   // my half of the filters
+        uint32_t m = mt * 256u + rank * 128u;                                               // my half of the pixels
+        if ((long long)m >= a.M) m = 0;                        // half tile entirely past the end: load valid pixels, rows are masked
+        const uint32_t row = fdiv(m, a.fd_w_mul, a.fd_w_shr);
+        const int w0 = (int)(m - row * (uint32_t)a.W);
+        const uint32_t img = fdiv(row, a.fd_h_mul, a.fd_h_shr);
+        const int h0 = (int)(row - img * (uint32_t)a.H), n0 = (int)img;
+        for (int k = k0; k < k1; ++k) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);             // my own copy: the leader's commit arrives on both
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * SK2_STAGE);
+          const int tap = s_unit_tap[k], a_c0 = s_unit_cc[k] * 64;
+          const int kh = a.pad ? (tap * 11) >> 5 : 0, kw = tap - kh * 3;       // tap / 3 for tap < 9 (1x1: tap == 0)
+          const uint32_t sA = smem_base + stage * SK2_STAGE;
+          const uint32_t bar = smem_u32(&full_bar[stage]) & PEER_BIT_MASK;      // the leader's barrier
+          tma_load_im2col_4d_2sm(sA, &tmA, bar, a_c0, w0 - a.pad, h0 - a.pad, n0, (uint16_t)kw, (uint16_t)kh);
+          tma_load_2d_2sm(sA + SK2_A_BYTES, &tmB, bar, tap * a.cin_p + a_c0, nrow0);
+          if (++stage == SK2_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        u += k1 - k0;
+      }
+    }
+  } else if (warp == 9) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    if (rank == 0) {
+      uint32_t is_leader;
+      asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(is_leader));
+      // D=f32, A=B=bf16, K-major both, N = 256, M = 256 (the pair)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint64_t adesc0 = make_smem_desc(smem_base, 16u, 8u * 128u, 2u);                    // SWIZZLE_128B, K-major
+      const uint64_t bdesc0 = make_smem_desc(smem_base + SK2_A_BYTES, 16u, 8u * 128u, 2u);
+      const uint32_t empty0 = smem_u32(&empty_bar[0]), tfull0 = smem_u32(&tmem_full[0]);
+      int stage = 0;
+      uint32_t phase = 0, seg = 0;
+      long long u = u_begin;
+      while (u < u_end) {
+        const uint32_t tile = (uint32_t)fdiv((uint32_t)u, a.fd_ks_mul, a.fd_ks_shr);
+        const int k0 = (int)(u - (long long)tile * a.ksteps);
+        const int k1 = (int)min((long long)a.ksteps, k0 + (u_end - u));
+        const uint32_t buf = seg & 1u;
+        mbar_wait(&tmem_empty[buf], ((seg >> 1) & 1u) ^ 1u);     // both CTAs drained this buffer's previous segment
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * 256u;
+        uint32_t accum = 0;
+        for (int k = k0; k < k1; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (is_leader) {
+            const uint32_t soff = (uint32_t)(stage * SK2_STAGE) >> 4;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_bf16_2sm(tmem_d, adesc0 + soff + (uint32_t)(ks * 2), bdesc0 + soff + (uint32_t)(ks * 2), idesc, accum);
+              accum = 1;
+            }
+            umma_commit_2sm_mc(empty0 + 8u * (uint32_t)stage, (uint16_t)3);
+          }
+          __syncwarp();
+          if (++stage == SK2_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (is_leader) umma_commit_2sm_mc(tfull0 + 8u * buf, (uint16_t)3);
+        __syncwarp();
+        u += k1 - k0;
+        ++seg;
+      }
+    }
+  } else {
+    // =========================== epilogue (both CTAs, own 128 rows) ===========================
+    const int q = warp & 3, chalf = warp >> 2;                 // TMEM lane quarter, column half of the accumulator
+    const int et = threadIdx.x;                                // 0..255
+    uint32_t seg = 0;
+    long long u = u_begin;
+    while (u < u_end) {
+      const uint32_t tile = (uint32_t)fdiv((uint32_t)u, a.fd_ks_mul, a.fd_ks_shr);
+      const int k0 = (int)(u - (long long)tile * a.ksteps);
+      const int k1 = (int)min((long long)a.ksteps, k0 + (u_end - u));
+      const bool tail = k0 > 0;                                // partial -> workspace slot blockIdx.x
+      const bool head = k0 == 0 && k1 < a.ksteps;              // owner: add the partial of CTA blockIdx.x + 2, finalise
+      const uint32_t mt = fdiv(tile, a.fd_nt_mul, a.fd_nt_shr);
+      const int col0 = (int)(tile - mt * (uint32_t)a.n_tiles) * 256 + chalf * 128;
+      const uint32_t buf = seg & 1u;
+      if (head) {
+        if (et == 0) {
+          const int* f = a.ws_flags + blockIdx.x + 2;
+          int v;
+          long long t0 = clock64();
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (!v) {
+              __nanosleep(200);
+              if (clock64() - t0 > 6000000000ll) { printf("y2 conv_streamk2: partial of CTA %d never arrived\n", blockIdx.x + 2); __trap(); }
+            }
+          } while (!v);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
+      }
+      mbar_wait(&tmem_full[buf], (seg >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t stg = smem_base + SK2_STAGES * SK2_STAGE + (uint32_t)warp * SK_STG_WARP;
+      float4* part = reinterpret_cast<float4*>(a.ws_partial + (size_t)(tail ? blockIdx.x : blockIdx.x + 2) * 32768) +
+                     (size_t)warp * 1024 + lane;                  // + hc * 256 + i * 32
+      float4 pv[8];
+      if (head) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pv[i] = __ldcg(part + i * 32);
+      }
+#pragma unroll 1
+      for (int hc = 0; hc < 4; ++hc) {
+        const int c = hc * 32;
+        const int row0 = (int)rank * 128 + q * 32;                // first tile row of this warp's 32-row slab
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)(chalf * 128 + c);
+        uint32_t v[32];
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        if (hc == 3) {                                         // my last chunk is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty[buf]) & PEER_BIT_MASK);
+        }
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            __stcg(part + hc * 256 + i * 32, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+          continue;
+        }
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.scale) sc = __ldg(reinterpret_cast<const float4*>(a.scale + col0 + c) + i);
+          if (a.shift) sh = __ldg(reinterpret_cast<const float4*>(a.shift + col0 + c) + i);
+          const float4 p4 = head ? pv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          f[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]) + p4.x, sc.x, sh.x);
+          f[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]) + p4.y, sc.y, sh.y);
+          f[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]) + p4.z, sc.z, sh.z);
+          f[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]) + p4.w, sc.w, sh.w);
+        }
+        if (head && hc < 3) {                                  // prefetch the next chunk's partial behind this chunk's stores
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[i] = __ldcg(part + (hc + 1) * 256 + i * 32);
+        }
+        if (a.leaky) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], a.alpha * f[i]);
+        }
+        const long long grow0 = (long long)mt * 256 + row0;       // global row of slab row 0
+        if (a.out_f32) {
+          // lane = slab row: 8 x 16-byte units, unit j of row r at (j ^ (r & 7))
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((j ^ (lane & 7)) << 4)), "f"(f[4 * j]),
+                         "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                         : "memory");
+          __syncwarp();
+          float* dst = reinterpret_cast<float*>(a.y) + col0 + c;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int r = t * 4 + (lane >> 3), j = lane & 7;
+            float4 o;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                         : "r"(stg + r * 128 + ((j ^ (r & 7)) << 4)));
+            if (grow0 + r < a.M) *reinterpret_cast<float4*>(dst + (size_t)(grow0 + r) * a.ldy + j * 4) = o;
+          }
+        } else {
+          // bf16: 64-byte rows, 4 units, unit j of row r at (j ^ ((r >> 1) & 3))
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
+                         : "memory");
+          }
+          __syncwarp();
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + col0 + c;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int r = t * 8 + (lane >> 2), j = lane & 3;
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                         : "r"(stg + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)));
+            if (grow0 + r < a.M) *reinterpret_cast<uint4*>(dst + (size_t)(grow0 + r) * a.ldy + j * 8) = o;
+          }
+        }
+        __syncwarp();                                           // staging tile free for the next chunk
+      }
+      if (tail) {
+        __threadfence();                                       // my partial is visible device-wide ...
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // ... and so is everybody else's
+        if (et == 0) {
+          int one = 1;
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.ws_flags + blockIdx.x), "r"(one) : "memory");
+        }
+      }
+      u += k1 - k0;
+      ++seg;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                           // nobody frees TMEM / exits while the partner's MMAs or arrives are in flight
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 static thread_local void* g_sk_ws = nullptr;
 static thread_local size_t g_sk_ws_bytes = 0;
 constexpr size_t SK_FLAG_BYTES = 4096;
@@ -349,8 +627,11 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   a.units = (long long)a.tiles * ksteps;
   if ((a.tiles < g_num_sms / 2 && !getenv("Y2_CONV_FORCE_STREAMK")) || a.units >= (1ll << 31) || a.M + 256 >= (1ll << 31)) return Y2_OK;
   // every CTA's range must be at least one tile long (a tile is then shared by at most two CTAs)
-  const int grid = a.tiles < g_num_sms ? a.tiles : g_num_sms;
-  if (g_sk_ws_bytes < sk_workspace_bytes(grid)) return Y2_OK;
+  // CTA-pair kernel (cta_group::2) unless disabled: 74 pairs, every pair's range at least one tile long
+  const bool two_cta = !getenv("Y2_CONV_STREAMK_1CTA") && g_num_sms >= 2;
+  const int npairs = a.tiles < g_num_sms / 2 ? a.tiles : g_num_sms / 2;
+  const int grid = two_cta ? 2 * npairs : (a.tiles < g_num_sms ? a.tiles : g_num_sms);
+  if (g_sk_ws_bytes < sk_workspace_bytes(g_num_sms)) return Y2_OK;
   a.ws_flags = reinterpret_cast<int*>(g_sk_ws);
   a.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_sk_ws) + SK_FLAG_BYTES);
   fastdiv_init((uint32_t)a.n_tiles, &a.fd_nt_mul, &a.fd_nt_shr);
@@ -377,7 +658,7 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
     const int Kp = taps * p->Cin;
     cuuint64_t bdims[2] = {(cuuint64_t)Kp, (cuuint64_t)p->Cout};
     cuuint64_t bstrides[1] = {(cuuint64_t)Kp * 2};
-    cuuint32_t bbox[2] = {64, 256};
+    cuuint32_t bbox[2] = {64, two_cta ? 128u : 256u};          // pair kernel: each CTA loads its half of the filters
     cuuint32_t bestr[2] = {1, 1};
     r = g_encodeTiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->w_packed), bdims, bstrides, bbox, bestr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -387,10 +668,16 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
       return Y2_ERR_DRIVER;
     }
   }
-  const size_t smem = (size_t)SK_STAGES * SK_STAGE + 8 * SK_STG_WARP + 1024;
-  Y2_CUDA(cudaFuncSetAttribute(conv_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  Y2_CUDA(cudaMemsetAsync(a.ws_flags, 0, (size_t)(grid + 1) * sizeof(int), st));
-  conv_streamk_kernel<<<grid, SK_THREADS, smem, st>>>(tmA, tmB, a);
+  Y2_CUDA(cudaMemsetAsync(a.ws_flags, 0, (size_t)(grid + 2) * sizeof(int), st));
+  if (two_cta) {
+    const size_t smem = (size_t)SK2_STAGES * SK2_STAGE + 8 * SK_STG_WARP + 1024;
+    Y2_CUDA(cudaFuncSetAttribute(conv_streamk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_streamk2_kernel<<<grid, SK_THREADS, smem, st>>>(tmA, tmB, a);
+  } else {
+    const size_t smem = (size_t)SK_STAGES * SK_STAGE + 8 * SK_STG_WARP + 1024;
+    Y2_CUDA(cudaFuncSetAttribute(conv_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_streamk_kernel<<<grid, SK_THREADS, smem, st>>>(tmA, tmB, a);
+  }
   Y2_LAUNCHED();
   *handled = 1;
   return Y2_OK;
