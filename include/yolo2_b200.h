@@ -115,6 +115,12 @@ int y2_conv1_u8_pool_fwd(const uint8_t* img, const void* w_packed, const float* 
 size_t y2_bn_stats_workspace_bytes(int M, int C);
 int y2_bn_stats(const float* x, int M, int C, int ld, float* mean, float* var,
                 void* workspace, size_t workspace_bytes, y2_stream_t stream);
+/* y2_bn_stats plus, in the same finalising kernel, the folded affine of the centred form
+ * y = (x - mean) * scale + shift: scale = gamma * rsqrt(var + eps), shift = beta (what y2_bn_fold
+ * gives for mean = 0, bias = NULL) -- the training=True branch of darknet.py:42-44 in two launches. */
+int y2_bn_stats_fold(const float* x, int M, int C, int ld, float* mean, float* var, const float* gamma,
+                     const float* beta, float eps, float* scale, float* shift,
+                     void* workspace, size_t workspace_bytes, y2_stream_t stream);
 /* scale = gamma * rsqrt(var + eps); shift = beta + (bias_or_0 - mean) * scale.
  * Pass conv_bias when the scale/shift is applied to a bias-free accumulator (fused epilogue),
  * NULL when it is applied to h = conv + b. */

@@ -36,7 +36,7 @@ struct SkArgs {
   const float* shift;
   void* y;
   float* ws_partial;                // [grid][2][128][256] float32 partial accumulators (slot = the tail CTA)
-  int* ws_flags;                    // [grid], zeroed before the launch
+  int* ws_flags;                    // [grid + 2], all zero between launches (a head resets the flag it consumed)
   float alpha;
   int leaky, out_f32;
   long long M;
@@ -190,6 +190,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (clock64() - t0 > 6000000000ll) { printf("y2 conv_streamk: partial of CTA %d never arrived\n", blockIdx.x + 1); __trap(); }
             }
           } while (!v);
+          *const_cast<int*>(f) = 0;                             // consumed: the flags are all zero again when the kernel ends
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
       }
@@ -470,6 +471,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               if (clock64() - t0 > 6000000000ll) { printf("y2 conv_streamk2: partial of CTA %d never arrived\n", blockIdx.x + 2); __trap(); }
             }
           } while (!v);
+          *const_cast<int*>(f) = 0;                             // consumed: the flags are all zero again when the kernel ends
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
       }
@@ -589,6 +591,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 static thread_local void* g_sk_ws = nullptr;
+static thread_local bool g_sk_flags_zeroed = false;             // first launch after registration clears the flags once
 static thread_local size_t g_sk_ws_bytes = 0;
 constexpr size_t SK_FLAG_BYTES = 4096;
 
@@ -607,7 +610,9 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   if ((p->shift && (reinterpret_cast<uintptr_t>(p->shift) & 15) != 0) || (p->scale && (reinterpret_cast<uintptr_t>(p->scale) & 15) != 0))
     return Y2_OK;
   const int taps = p->ksize * p->ksize, cchunks = p->Cin / 64, ksteps = taps * cchunks;
-  if (ksteps < 32 || ksteps > SK_MAX_UNITS) return Y2_OK;       // short K: the un-overlapped epilogue would show
+  int min_ksteps = 18;                                          // short K: the epilogue starts to show
+  if (const char* e = getenv("Y2_CONV_STREAMK_MIN_KSTEPS")) min_ksteps = atoi(e);
+  if (ksteps < min_ksteps || ksteps > SK_MAX_UNITS) return Y2_OK;
   int rc = load_driver_entry_points();
   if (rc != Y2_OK) return rc;
   SkArgs a;
@@ -668,7 +673,11 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
       return Y2_ERR_DRIVER;
     }
   }
-  Y2_CUDA(cudaMemsetAsync(a.ws_flags, 0, (size_t)(grid + 2) * sizeof(int), st));
+  if (!g_sk_flags_zeroed) {
+    // once per registered workspace: afterwards every launch leaves the flags zero (no memset node per layer)
+    Y2_CUDA(cudaMemsetAsync(a.ws_flags, 0, SK_FLAG_BYTES, st));
+    g_sk_flags_zeroed = true;
+  }
   if (two_cta) {
     const size_t smem = (size_t)SK2_STAGES * SK2_STAGE + 8 * SK_STG_WARP + 1024;
     Y2_CUDA(cudaFuncSetAttribute(conv_streamk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -696,5 +705,6 @@ extern "C" int y2_conv_set_workspace(void* workspace, size_t bytes) {
   Y2_ARG(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
   g_sk_ws = workspace;
   g_sk_ws_bytes = workspace ? bytes : 0;
+  g_sk_flags_zeroed = false;
   return Y2_OK;
 }

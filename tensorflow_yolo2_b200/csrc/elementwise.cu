@@ -167,8 +167,12 @@ __global__ void __launch_bounds__(256) bn_stats_partial_v4_kernel(const float* _
 
 // grid ceil(C/32), block (32, 8): the 8 thread rows fold interleaved subsets of the splits (fixed order ->
 // deterministic), then one row folds the 8 partials.
+// With gamma / beta the same thread also writes the folded affine of the CENTRED form y = (x - mean) * scale + shift
+// (scale = gamma * rsqrt(var + eps), shift = beta) -- one launch less per batch-statistics layer.
 __global__ void bn_stats_final_kernel(const float* __restrict__ x, const double* __restrict__ part, int splits, int M,
-                                      int C, float* __restrict__ mean, float* __restrict__ var) {
+                                      int C, float* __restrict__ mean, float* __restrict__ var,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
   __shared__ double s1[8][33], s2[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double a1 = 0.0, a2 = 0.0;
@@ -187,7 +191,12 @@ __global__ void bn_stats_final_kernel(const float* __restrict__ x, const double*
   double v = a2 / (double)M - md * md;
   if (v < 0.0) v = 0.0;
   mean[c] = (float)((double)x[c] + md);
-  var[c] = (float)v;
+  const float vf = (float)v;
+  var[c] = vf;
+  if (scale) {
+    scale[c] = gamma[c] * rsqrtf(vf + eps);                    // bit-identical to bn_fold_kernel on (mean = 0, bias = 0)
+    shift[c] = beta[c];
+  }
 }
 
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -391,8 +400,8 @@ static int bn_splits(int M) {
 
 size_t y2_bn_stats_workspace_bytes(int M, int C) { return (size_t)bn_splits(M) * C * 2 * sizeof(double); }
 
-int y2_bn_stats(const float* x, int M, int C, int ld, float* mean, float* var, void* workspace, size_t workspace_bytes,
-                y2_stream_t stream) {
+static int bn_stats_impl(const float* x, int M, int C, int ld, float* mean, float* var, const float* gamma, const float* beta,
+                         float eps, float* scale, float* shift, void* workspace, size_t workspace_bytes, y2_stream_t stream) {
   Y2_ARG(x && mean && var && M > 0 && C > 0 && ld >= C);
   if (!workspace || workspace_bytes < y2_bn_stats_workspace_bytes(M, C)) {
     set_error("y2_bn_stats: workspace too small (%zu < %zu)", workspace_bytes, y2_bn_stats_workspace_bytes(M, C));
@@ -413,9 +422,21 @@ int y2_bn_stats(const float* x, int M, int C, int ld, float* mean, float* var, v
     bn_stats_partial_kernel<<<grid, block, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
   }
   Y2_LAUNCHED();
-  bn_stats_final_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(x, (const double*)workspace, splits, M, C, mean, var);
+  bn_stats_final_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(x, (const double*)workspace, splits, M, C, mean, var, gamma, beta,
+                                                               eps, scale, shift);
   Y2_LAUNCHED();
   return Y2_OK;
+}
+
+int y2_bn_stats(const float* x, int M, int C, int ld, float* mean, float* var, void* workspace, size_t workspace_bytes,
+                y2_stream_t stream) {
+  return bn_stats_impl(x, M, C, ld, mean, var, nullptr, nullptr, 0.0f, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+int y2_bn_stats_fold(const float* x, int M, int C, int ld, float* mean, float* var, const float* gamma, const float* beta,
+                     float eps, float* scale, float* shift, void* workspace, size_t workspace_bytes, y2_stream_t stream) {
+  Y2_ARG(gamma && beta && scale && shift);
+  return bn_stats_impl(x, M, C, ld, mean, var, gamma, beta, eps, scale, shift, workspace, workspace_bytes, stream);
 }
 
 int y2_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias,

@@ -201,8 +201,8 @@ class Yolo2Engine:
                 bn = L['bn']
                 ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], scale=None, shift=st[L['b']],
                                   leaky=False, pool=False, out_f32=True, ldy=raw.shape[1], out=raw)
-                ops.bn_stats(raw, L['cout'], ld=raw.shape[1], workspace=self.ws, mean=mean, var=var)
-                ops.bn_fold(st[bn['gamma']], st[bn['beta']], zeros, var, None, scale=scale, shift=shift)
+                ops.bn_stats_fold(raw, L['cout'], st[bn['gamma']], st[bn['beta']], ld=raw.shape[1], workspace=self.ws,
+                                  mean=mean, var=var, scale=scale, shift=shift)
                 ops.affine_leaky_pool(raw, self.N, Hl, Hl, L['cout'], ldx=raw.shape[1], sub=mean, scale=scale, shift=shift,
                                       leaky=True, pool=pool, out_bf16=not last, out=out, ldo=ldo, out_col=col,
                                       space_to_depth=s2d)

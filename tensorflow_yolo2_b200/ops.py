@@ -198,6 +198,25 @@ def bn_stats(x2d, C_, ld=None, workspace=None, mean=None, var=None):
     return mean, var
 
 
+def bn_stats_fold(x2d, C_, gamma, beta, ld=None, workspace=None, mean=None, var=None, scale=None, shift=None, eps=BN_EPS):
+    """bn_stats + the folded affine of the centred form y = (x - mean) * scale + shift, in the same two launches.
+    Returns (mean, var, scale, shift)."""
+    M = x2d.shape[0]
+    ld = ld or x2d.shape[1]
+    lib = _lib.load()
+    need = int(lib.y2_bn_stats_workspace_bytes(M, C_))
+    ws = workspace if workspace is not None else _workspace(need, x2d.device)
+    new = lambda: torch.empty((C_,), dtype=torch.float32, device=x2d.device)
+    mean = new() if mean is None else mean
+    var = new() if var is None else var
+    scale = new() if scale is None else scale
+    shift = new() if shift is None else shift
+    check(lib.y2_bn_stats_fold(_p(x2d, torch.float32), M, C_, ld, _p(mean), _p(var), _p(gamma, torch.float32),
+                               _p(beta, torch.float32), eps, _p(scale), _p(shift), _p(ws), ws.numel(), _stream()),
+          'y2_bn_stats_fold')
+    return mean, var, scale, shift
+
+
 def bn_fold(gamma, beta, mean, var, conv_bias=None, eps=BN_EPS, scale=None, shift=None):
     C_ = gamma.numel()
     if scale is None:

@@ -120,6 +120,19 @@ def test_conv_streamk_vs_generic_and_oracle(ops, monkeypatch, N, S, Cin, Cout, k
 
 
 # ---------------------------------------------------------------------------------- a2 / a3
+def test_bn_stats_fold_matches_two_step(ops):
+    """y2_bn_stats_fold == y2_bn_stats followed by y2_bn_fold(mean=0, bias=None), bit for bit."""
+    rs = np.random.RandomState(5)
+    M, C = 5 * 13 * 13, 96
+    x = cu((rs.randn(M, C) * rs.uniform(0.5, 3, C) + rs.randn(C) * 10).astype(np.float32))
+    gamma, beta = cu(rs.uniform(0.5, 1.5, C).astype(np.float32)), cu(rs.randn(C).astype(np.float32))
+    mean, var = ops.bn_stats(x, C)
+    sc, sh = ops.bn_fold(gamma, beta, torch.zeros_like(mean), var, None)
+    m2, v2, sc2, sh2 = ops.bn_stats_fold(x, C, gamma, beta)
+    torch.cuda.synchronize()
+    assert torch.equal(mean, m2) and torch.equal(var, v2) and torch.equal(sc, sc2) and torch.equal(sh, sh2)
+
+
 def test_bn_stats_large_mean(ops):
     rs = np.random.RandomState(2)
     M, C = 3 * 13 * 13, 70
