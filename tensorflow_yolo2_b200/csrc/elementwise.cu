@@ -165,19 +165,21 @@ __global__ void __launch_bounds__(256) bn_stats_partial_v4_kernel(const float* _
   }
 }
 
-// grid ceil(C/32), block (32, 8): the 8 thread rows fold interleaved subsets of the splits (fixed order ->
-// deterministic), then one row folds the 8 partials.
+// grid ceil(C/32), block (32, FIN_TY): the thread rows fold interleaved subsets of the splits (fixed order ->
+// deterministic), then one row folds the FIN_TY partials.  32 rows: with 8 each thread walked ~11 dependent L2 round
+// trips (8 us for 1.4 MB, ncu r1c).
+constexpr int FIN_TY = 32;
 // With gamma / beta the same thread also writes the folded affine of the CENTRED form y = (x - mean) * scale + shift
 // (scale = gamma * rsqrt(var + eps), shift = beta) -- one launch less per batch-statistics layer.
-__global__ void bn_stats_final_kernel(const float* __restrict__ x, const double* __restrict__ part, int splits, int M,
+__global__ void __launch_bounds__(32 * FIN_TY) bn_stats_final_kernel(const float* __restrict__ x, const double* __restrict__ part, int splits, int M,
                                       int C, float* __restrict__ mean, float* __restrict__ var,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                       float* __restrict__ scale, float* __restrict__ shift) {
-  __shared__ double s1[8][33], s2[8][33];
+  __shared__ double s1[FIN_TY][33], s2[FIN_TY][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double a1 = 0.0, a2 = 0.0;
   if (c < C)
-    for (int s = threadIdx.y; s < splits; s += 8) {
+    for (int s = threadIdx.y; s < splits; s += FIN_TY) {
       const double2 p = *reinterpret_cast<const double2*>(part + ((size_t)s * C + c) * 2);
       a1 += p.x;
       a2 += p.y;
@@ -186,7 +188,7 @@ __global__ void bn_stats_final_kernel(const float* __restrict__ x, const double*
   s2[threadIdx.y][threadIdx.x] = a2;
   __syncthreads();
   if (threadIdx.y != 0 || c >= C) return;
-  for (int y = 1; y < 8; ++y) { a1 += s1[y][threadIdx.x]; a2 += s2[y][threadIdx.x]; }
+  for (int y = 1; y < FIN_TY; ++y) { a1 += s1[y][threadIdx.x]; a2 += s2[y][threadIdx.x]; }
   double md = a1 / (double)M;
   double v = a2 / (double)M - md * md;
   if (v < 0.0) v = 0.0;
@@ -293,6 +295,57 @@ __global__ void affine_leaky_pool_kernel(const float* __restrict__ x, int ldx, c
   }
 }
 
+// Fast path of the above for the batch-statistics head layers (no pool, dense rows, C % 8 == 0, bf16 out): the generic
+// kernel spends its time in 64-bit div/mod per element (30 us for 66 MB, ncu r1c).  Here a thread owns 8 channels --
+// their sub / scale / shift live in registers -- and walks rows, four rows of 2 x 16-byte streaming loads in flight,
+// one 16-byte store per row.  block = (C/8 rounded to a warp, up to 128) x rows-per-block lanes.
+__global__ void __launch_bounds__(256) affine_leaky_rows_bf16_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ sub,
+                                                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                     float alpha, int leaky_on, __nv_bfloat16* __restrict__ out, int ldo,
+                                                                     int M, int C8) {
+  const int cx = blockIdx.y * blockDim.x + threadIdx.x;          // channel group
+  if (cx >= C8) return;
+  const int c0 = cx * 8;
+  float sb[8], sc[8], sh[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    sb[v] = sub ? sub[c0 + v] : 0.0f;
+    sc[v] = scale ? scale[c0 + v] : 1.0f;
+    sh[v] = shift ? shift[c0 + v] : 0.0f;
+  }
+  const int rstep = gridDim.x * blockDim.y;
+  for (int r0 = blockIdx.x * blockDim.y + threadIdx.y; r0 < M; r0 += 4 * rstep) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + j * rstep;
+      if (r < M) {
+        const float4* px = reinterpret_cast<const float4*>(x + (size_t)r * ldx + c0);
+        a[j] = __ldcs(px);
+        b[j] = __ldcs(px + 1);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + j * rstep;
+      if (r >= M) continue;
+      const float t[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
+      float y[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        y[v] = (t[v] - sb[v]) * sc[v] + sh[v];                   // same expression as the generic kernel
+        if (leaky_on) y[v] = leaky(y[v], alpha);
+      }
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(y[0], y[1]), h1 = __floats2bfloat162_rn(y[2], y[3]);
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[4], y[5]), h3 = __floats2bfloat162_rn(y[6], y[7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(out + (size_t)r * ldo + c0) = pk;
+    }
+  }
+}
+
 // a3  tf.nn.max_pool 2x2/2 (darknet.py:24-25) on a bf16 NHWC tensor, 8 channels (16 B) per thread.  Used when a layer's
 // un-pooled output is needed as well (the passthrough source, darknet.py:170) so the pool cannot live in the conv epilogue.
 __global__ void maxpool2x2_bf16_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int CV) {
@@ -331,6 +384,17 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     v[i] = vi;
     p[i] -= lr_t * mi / (sqrtf(vi) + eps);
   }
+}
+
+static int g_sms_elementwise() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
 }
 
 static int grid_for(size_t n, int block) {
@@ -422,7 +486,7 @@ static int bn_stats_impl(const float* x, int M, int C, int ld, float* mean, floa
     bn_stats_partial_kernel<<<grid, block, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
   }
   Y2_LAUNCHED();
-  bn_stats_final_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(x, (const double*)workspace, splits, M, C, mean, var, gamma, beta,
+  bn_stats_final_kernel<<<(C + 31) / 32, dim3(32, FIN_TY), 0, st>>>(x, (const double*)workspace, splits, M, C, mean, var, gamma, beta,
                                                                eps, scale, shift);
   Y2_LAUNCHED();
   return Y2_OK;
@@ -467,6 +531,20 @@ int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const flo
   else Y2_ARG(ldo >= C);
   cudaStream_t st = (cudaStream_t)stream;
   int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  if (!pool && !space_to_depth && out_dtype == 1 && C % 8 == 0 && ldx % 4 == 0 && ldo % 8 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0 &&
+      (long long)N * H * W < (1ll << 30) && !getenv("Y2_AFFINE_GENERIC")) {
+    const int M = N * H * W, C8 = C / 8;
+    const int bx = C8 >= 128 ? 128 : ((C8 + 31) / 32) * 32;       // channel-group lanes per block (whole warps)
+    const int by = 256 / bx;                                      // row lanes per block
+    int gx = g_sms_elementwise() * 8 / ((C8 + bx - 1) / bx);
+    const int need = (M + by - 1) / by;
+    if (gx > need) gx = need;
+    if (gx < 1) gx = 1;
+    affine_leaky_rows_bf16_kernel<<<dim3(gx, (C8 + bx - 1) / bx), dim3(bx, by), 0, st>>>(
+        x, ldx, sub, scale, shift, alpha, leaky_on, reinterpret_cast<__nv_bfloat16*>(out), ldo, M, C8);
+    Y2_LAUNCHED();
+    return Y2_OK;
+  }
   bool vec4 = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)out & 15) == 0);
   size_t total = (size_t)N * Ho * Wo * (vec4 ? C / 4 : C);
   int g = grid_for(total, 256);

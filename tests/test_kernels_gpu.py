@@ -133,6 +133,30 @@ def test_bn_stats_fold_matches_two_step(ops):
     assert torch.equal(mean, m2) and torch.equal(var, v2) and torch.equal(sc, sc2) and torch.equal(sh, sh2)
 
 
+@pytest.mark.parametrize('C,ld,ldo,col', [(1024, 1024, None, 0), (72, 96, 160, 8)])
+def test_affine_rows_fast_path_equals_generic(ops, monkeypatch, C, ld, ldo, col):
+    """The row-walking bf16 kernel of the batch-statistics head layers == the generic kernel, bit for bit (dense rows and
+    a channel slice of a wider tensor)."""
+    rs = np.random.RandomState(6)
+    N, S = 3, 13
+    x = cu((rs.randn(N * S * S, ld) * 3).astype(np.float32))
+    sub, sc, sh = (cu(rs.randn(C).astype(np.float32)) for _ in range(3))
+    outs = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv('Y2_AFFINE_GENERIC', '1')
+        out = torch.zeros((N, S, S, ldo or C), dtype=torch.bfloat16, device='cuda')
+        ops.affine_leaky_pool(x, N, S, S, C, ldx=ld, sub=sub, scale=sc, shift=sh, leaky=True, out_bf16=True, out=out,
+                              ldo=ldo, out_col=col)
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    want = (x[:, :C] - sub) * sc + sh
+    want = torch.maximum(want, 0.1 * want).to(torch.bfloat16).float().reshape(N, S, S, C)
+    got = outs[0][..., col:col + C].float()
+    assert (got - want).abs().max() <= 2e-2 * want.abs().max()
+
+
 def test_bn_stats_large_mean(ops):
     rs = np.random.RandomState(2)
     M, C = 3 * 13 * 13, 70
