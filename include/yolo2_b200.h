@@ -179,6 +179,16 @@ int y2_detect_fused(const float* net, const float* anchors, int N, int S, int A,
                     float iou_thresh, float* boxes, float* scores, int32_t* keep_idx, int32_t* keep_count,
                     float* keep_score, int max_keep, y2_stream_t stream);
 
+/* Same contract and results as y2_detect_fused, as two launches sized for the HBM roofline (detect_split.cu): a decode
+ * kernel over 32-cell chunks of the whole batch (bulk-copy staged, candidates appended to per-(image, class) lists in the
+ * workspace) and a per-image NMS kernel over those lists.  workspace: y2_detect_workspace_bytes(N, C) bytes, 256-byte
+ * aligned, ZERO-FILLED once before its first use (every call leaves it zero-filled again).  C == 20, A == 5,
+ * S*S*A <= 4095, net / scores 16-byte aligned. */
+size_t y2_detect_workspace_bytes(int N, int C);
+int y2_detect_split(const float* net, const float* anchors, int N, int S, int A, int C, float score_thresh,
+                    float iou_thresh, float* boxes, float* scores, int32_t* keep_idx, int32_t* keep_count,
+                    float* keep_score, int max_keep, void* workspace, size_t workspace_bytes, y2_stream_t stream);
+
 /* ---- a7: IoU of n box pairs (yolo2_nets/net_utils.py:222-260 get_iou) ------------------------
  * boxes1/boxes2 [n,4] (cx,cy,w,h) f32 -> iou [n]; float32 in the reference's op order. */
 int y2_iou(const float* boxes1, const float* boxes2, float* iou, size_t n, y2_stream_t stream);

@@ -52,6 +52,8 @@ _SIGNATURES = {
     'y2_nms_workspace_bytes': (_sz, [_i, _i, _i]),
     'y2_nms': (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _i, _vp, _sz, _vp]),
     'y2_detect_fused': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'y2_detect_workspace_bytes': (_sz, [_i, _i]),
+    'y2_detect_split': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     'y2_iou': (_i, [_vp, _vp, _vp, _sz, _vp]),
     'y2_loss_v1_workspace_bytes': (_sz, [_i, _i]),
     'y2_loss_v1_fwd_bwd': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

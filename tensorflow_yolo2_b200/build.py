@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libyolo2_b200.so')
-SOURCES = ['api.cu', 'elementwise.cu', 'conv_simt.cu', 'conv_tcgen05.cu', 'conv_streamk_tcgen05.cu', 'conv1_fused.cu', 'decode.cu', 'nms.cu', 'detect_fused.cu', 'loss.cu', 'region_loss.cu', 'backward.cu',
+SOURCES = ['api.cu', 'elementwise.cu', 'conv_simt.cu', 'conv_tcgen05.cu', 'conv_streamk_tcgen05.cu', 'conv1_fused.cu', 'decode.cu', 'nms.cu', 'detect_fused.cu', 'detect_split.cu', 'loss.cu', 'region_loss.cu', 'backward.cu',
            'conv_wgrad_tcgen05.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']

@@ -337,6 +337,51 @@ def detect_fused(net, anchors, C_=20, score_thresh=0.3, iou_thresh=0.45, max_kee
     return boxes, scores, keep_idx, keep_count, keep_score
 
 
+_detect_ws = {}
+
+
+def detect_workspace_bytes(N, C_):
+    return int(_lib.load().y2_detect_workspace_bytes(N, C_))
+
+
+def detect_workspace(N, C_, device):
+    """Zero-filled candidate-list workspace of y2_detect_split for (N, C) on `device` (cached: every call leaves it
+    zero-filled again, so one buffer per shape and device serves all calls on a stream)."""
+    key = (str(device), int(N), int(C_))
+    ws = _detect_ws.get(key)
+    if ws is None:
+        need = int(_lib.load().y2_detect_workspace_bytes(N, C_))
+        ws = torch.zeros((need,), dtype=torch.uint8, device=device)
+        _detect_ws[key] = ws
+    return ws
+
+
+def detect_split(net, anchors, C_=20, score_thresh=0.3, iou_thresh=0.45, max_keep=None, boxes=None, scores=None,
+                 keep_idx=None, keep_count=None, keep_score=None, want_scores=True, workspace=None):
+    """Region decode + per-class NMS as two launches (chunked bulk-copy decode over the whole batch, per-image NMS over
+    candidate lists) -- same results as detect_fused.  Returns (boxes, scores or None, keep_idx, keep_count, keep_score)."""
+    N, S = net.shape[0], net.shape[1]
+    A = anchors.shape[0]
+    nbox = S * S * A
+    assert net.numel() == N * nbox * (5 + C_)
+    max_keep = max_keep or nbox
+    dev = net.device
+    if boxes is None:
+        boxes = torch.empty((N, nbox, 4), dtype=torch.float32, device=dev)
+    if scores is None and want_scores:
+        scores = torch.empty((N, nbox, C_), dtype=torch.float32, device=dev)
+    if keep_idx is None:
+        keep_idx = torch.full((N, C_, max_keep), -1, dtype=torch.int32, device=dev)
+    if keep_count is None:
+        keep_count = torch.empty((N, C_), dtype=torch.int32, device=dev)
+    ws = workspace if workspace is not None else detect_workspace(N, C_, dev)
+    check(_lib.load().y2_detect_split(_p(net, torch.float32), _p(anchors, torch.float32), N, S, A, C_, score_thresh,
+                                      iou_thresh, _p(boxes, torch.float32), _p(scores, torch.float32),
+                                      _p(keep_idx, torch.int32), _p(keep_count, torch.int32), _p(keep_score, torch.float32),
+                                      max_keep, _p(ws), ws.numel(), _stream()), 'y2_detect_split')
+    return boxes, scores, keep_idx, keep_count, keep_score
+
+
 # ---- a6 / a7 -------------------------------------------------------------------------------
 def iou(boxes1, boxes2):
     """[..., 4] x [..., 4] (cx,cy,w,h) f32 -> [...] IoU (net_utils.get_iou arithmetic)."""

@@ -362,15 +362,23 @@ def test_adam_step(ops):
 
 
 # ---- fused decode + NMS ---------------------------------------------------------------------------
-@pytest.mark.parametrize('N,S,thr', [(7, 13, 0.3), (3, 19, 0.2), (2, 13, 0.01), (2, 7, 0.3)])
-def test_detect_fused_equals_decode_plus_nms_and_oracle(ops, N, S, thr):
+@pytest.mark.parametrize('impl', ['detect_fused', 'detect_split'])
+@pytest.mark.parametrize('N,S,thr', [(7, 13, 0.3), (3, 19, 0.2), (2, 13, 0.01), (2, 7, 0.3), (64, 13, 0.1)])
+def test_detect_fused_equals_decode_plus_nms_and_oracle(ops, impl, N, S, thr):
+    detect = getattr(ops, impl)          # one CTA per image / chunked decode + per-image NMS over candidate lists
     rs = np.random.RandomState(S * 10 + N)
     net = (2.0 * rs.randn(N, S, S, 125)).astype(np.float32)
     an = cu(O.VOC_ANCHORS)
     b0, s0 = ops.decode_region(cu(net), an, 20, thr)
     ki0, kc0 = ops.nms(b0, s0, thr, 0.45)
     ks = torch.zeros((N, 20, S * S * 5), dtype=torch.float32, device='cuda')
-    b1, s1, ki1, kc1, _ = ops.detect_fused(cu(net), an, 20, thr, 0.45, keep_score=ks)
+    b1, s1, ki1, kc1, _ = detect(cu(net), an, 20, thr, 0.45, keep_score=ks)
+    if impl == 'detect_split':           # second call on the same (self-resetting) workspace must agree with the first
+        ks2 = torch.zeros_like(ks)
+        b2, s2, ki2, kc2, _ = detect(cu(net), an, 20, thr, 0.45, keep_score=ks2)
+        torch.cuda.synchronize()
+        assert torch.equal(kc1, kc2) and torch.equal(s1, s2) and torch.equal(b1, b2) and torch.equal(ks, ks2)
+        assert int(ops.detect_workspace(N, 20, b1.device)[:N * 20 * 4].view(torch.int32).abs().sum()) == 0
     torch.cuda.synchronize()
     # the fused kernel uses the fast intrinsics (ex2.approx / rcp.approx), the two-kernel path expf and IEEE division:
     # both sit inside the spec's 1e-5; a score within that distance of the threshold may be kept by one and not the other
@@ -397,13 +405,15 @@ def test_detect_fused_equals_decode_plus_nms_and_oracle(ops, N, S, thr):
         assert torch.equal(kc0, kc1)
 
 
-def test_detect_fused_overflow_falls_back_to_bitmatrix_kernel(ops):
+@pytest.mark.parametrize('impl', ['detect_fused', 'detect_split'])
+def test_detect_fused_overflow_falls_back_to_bitmatrix_kernel(ops, impl):
     """threshold 0: all 845 x 20 candidates (> 2048) -> image flagged and re-done by nms_kernel; and a mixed batch."""
+    detect = getattr(ops, impl)
     rs = np.random.RandomState(77)
     net = (1.0 * rs.randn(3, 13, 13, 125)).astype(np.float32)
     net[1, ..., 4::25] = -30.0                       # image 1: objectness ~ 0 -> scores underflow below any threshold
     an = cu(O.VOC_ANCHORS)
-    b1, s1, ki1, kc1, _ = ops.detect_fused(cu(net), an, 20, 1e-12, 0.45, max_keep=845)
+    b1, s1, ki1, kc1, _ = detect(cu(net), an, 20, 1e-12, 0.45, max_keep=845)
     torch.cuda.synchronize()
     boxes, scores = b1.cpu().numpy(), s1.cpu().numpy()
     ki, kc = ki1.cpu().numpy(), kc1.cpu().numpy()
@@ -414,6 +424,6 @@ def test_detect_fused_overflow_falls_back_to_bitmatrix_kernel(ops):
             assert kc[n, k] == len(keeps[k])
             np.testing.assert_array_equal(ki[n, k, :kc[n, k]], keeps[k])
     # without a scores buffer the overflowed images are reported, not silently dropped
-    _, _, _, kc2, _ = ops.detect_fused(cu(net), an, 20, 1e-12, 0.45, max_keep=845, want_scores=False)
+    _, _, _, kc2, _ = detect(cu(net), an, 20, 1e-12, 0.45, max_keep=845, want_scores=False)
     torch.cuda.synchronize()
     assert (kc2.cpu().numpy()[0] == -1).all()

@@ -42,11 +42,14 @@ def main():
             ops.nms(boxes, scores, thr, 0.45, 64, keep_idx=ki, keep_count=kc)
         def fused():
             ops.detect_fused(net, an, 20, thr, 0.45, 64, boxes=boxes, scores=scores, keep_idx=ki, keep_count=kc)
-        t2, tf = timeit(two), timeit(fused)
+        def split():
+            ops.detect_split(net, an, 20, thr, 0.45, 64, boxes=boxes, scores=scores, keep_idx=ki, keep_count=kc)
+        t2, tf, ts = timeit(two), timeit(fused), timeit(split)
         cand = int((scores > 0).sum())
         print(json.dumps(dict(workload='decode+NMS microbench %dx%dx5x25, batch %d, score_thresh %g' % (S, S, N, thr),
                               candidates=cand, kept=int(kc.clamp(min=0).sum()), algorithmic_bytes=alg,
-                              two_kernels_us=round(t2 * 1e3, 1), fused_us=round(tf * 1e3, 1),
+                              two_kernels_us=round(t2 * 1e3, 1), fused_us=round(tf * 1e3, 1), split_us=round(ts * 1e3, 1),
+                              split_gbs=round(alg / ts / 1e6, 1), split_frac_of_hbm_peak=round(alg / ts / 1e6 / peak, 3),
                               two_kernels_gbs=round(alg / t2 / 1e6, 1), fused_gbs=round(alg / tf / 1e6, 1),
                               hbm_peak_gbs=peak, fused_frac_of_hbm_peak=round(alg / tf / 1e6 / peak, 3),
                               images_per_s_fused=round(N / tf * 1e3))), flush=True)
