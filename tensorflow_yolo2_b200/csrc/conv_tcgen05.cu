@@ -56,6 +56,7 @@ struct ConvArgs {
   int b_stationary;       // whole B operand resident in smem for the CTA's lifetime (n_tiles == 1, small B)
   uint32_t b_total_bytes;
   int sps;                // (tap, channel-chunk) sub-blocks per pipeline stage
+  int cta2;               // mode 2, stationary B: CTA pair, tcgen05 cta_group::2 MMAs (M = 256, each CTA holds half of the filters)
   int kw_merge;           // mode 2: the three horizontally shifted patches share one stage (stationary B, one chunk)
   int stages_per_tile;    // kblocks / sps
   uint32_t a_sub_bytes, b_sub_bytes;
@@ -282,7 +283,9 @@ __device__ __forceinline__ void epilogue_chunk_pooled_bf16(const ConvArgs& a, co
 }
 
 // KIND: 0 = first layer (Cin 3 -> 8, un-swizzled 16-byte rows), 1 = 64-byte rows (Cin 32), 2 = 128-byte rows
-template <int BLOCK_N, int A_MODE, int KIND>
+// CTA2: CTA-pair variant (tcgen05 cta_group::2).  A template parameter, not a run-time flag: a kernel that merely CONTAINS
+// cta_group::2 instructions can only be launched with an even cluster size (launch error "cluster misconfiguration").
+template <int BLOCK_N, int A_MODE, int KIND, bool CTA2 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
   constexpr bool FIRST = KIND == 0;
@@ -315,6 +318,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // "super tiles" (two consecutive M tiles x one N tile); each CTA loads half of the B tile and multicasts
   // it to both, which removes a third of the L2->SM operand traffic the kernel is bound by.
   const int CS = a.cluster;
+  // CTA pair on one M = 256 MMA (see conv_streamk2_kernel for the why: the 64 B/clk smem operand path).  Each CTA keeps
+  // its own 128-pixel tile and HALF of the resident filter bank; the leader (rank 0) issues, both run producer + epilogue.
+  constexpr bool cta2 = CTA2;
+  static_assert(!CTA2 || (A_MODE == 2 && !FIRST), "the CTA-pair variant exists for the halo-patch mode only");
   const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
   const int sched_first = CS > 1 ? (int)(blockIdx.x / CS) : (int)blockIdx.x;
   const int sched_step = CS > 1 ? (int)(gridDim.x / CS) : (int)gridDim.x;
@@ -328,11 +335,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
       for (int s = 0; s < a.stages; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], CS);                   // every CTA of the cluster must release the stage
+        mbar_init(&empty_bar[s], cta2 ? 1 : CS);        // every CTA of the cluster must release the stage (pair: one multicast commit)
       }
       for (int b = 0; b < NBUF; ++b) {
         mbar_init(&tmem_full_bar[b], 1);
-        mbar_init(&tmem_empty_bar[b], 4 * CP);          // the warps of the CP groups that drain this buffer
+        mbar_init(&tmem_empty_bar[b], 4 * CP * (cta2 ? 2 : 1));   // the warps of the CP groups that drain this buffer (pair: of both CTAs)
       }
       mbar_init(&bfull_bar, 1);
       fence_barrier_init();
@@ -354,10 +361,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   if (warp == WARP_MMA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (cta2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -373,16 +387,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int sps = a.sps;
     if (a.b_stationary) {
       // weights of this layer fit in smem: fetch them once per CTA instead of once per tile
-      if (lane == 0) mbar_expect_tx(&bfull_bar, a.b_total_bytes);
+      // pair: both CTAs' halves are counted on the LEADER's barrier (the issuer needs both resident)
+      if (lane == 0 && (!cta2 || crank == 0)) mbar_expect_tx(&bfull_bar, cta2 ? 2u * a.b_total_bytes : a.b_total_bytes);
       __syncwarp();
-      const uint32_t bar = smem_u32(&bfull_bar);
+      const uint32_t bar = cta2 ? (smem_u32(&bfull_bar) & PEER_BIT_MASK) : smem_u32(&bfull_bar);
       if constexpr (FIRST) {
         if (lane == 0) tma_load_3d(smem_b_stat, &tmB, bar, 0, 0, 0);
       } else {
         // stationary order = packed K order: index = tap * cchunks + cc
         for (int sub = lane; sub < a.kblocks; sub += 32) {
           const int tap = sub / a.cchunks, cc = sub - tap * a.cchunks;
-          tma_load_2d(smem_b_stat + sub * a.b_sub_bytes, &tmB, bar, tap * a.cin_p + cc * a.kchunk, 0);
+          if constexpr (cta2) tma_load_2d_2sm(smem_b_stat + sub * a.b_sub_bytes, &tmB, bar, tap * a.cin_p + cc * a.kchunk, (int)crank * (BLOCK_N / 2));
+          else tma_load_2d(smem_b_stat + sub * a.b_sub_bytes, &tmB, bar, tap * a.cin_p + cc * a.kchunk, 0);
         }
       }
       __syncwarp();
@@ -395,10 +411,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const TileCoord t = decode_tile(a, tile, crank);
       const int nrow0 = t.n_tile * BLOCK_N;
       for (int st = 0; st < spt; ++st) {
-        const uint32_t bar = full0 + 8u * ustage;
+        const uint32_t bar = cta2 ? ((full0 + 8u * ustage) & PEER_BIT_MASK) : full0 + 8u * ustage;   // pair: the leader's barrier
         if (lane == 0) {
           mbar_wait_a(empty0 + 8u * ustage, phase ^ 1u);
-          mbar_expect_tx_a(bar, tx_bytes);
+          if (!cta2) mbar_expect_tx_a(bar, tx_bytes);
+          else if (crank == 0) mbar_expect_tx_a(bar, 2u * tx_bytes);      // both CTAs' patches
         }
         __syncwarp();
         const uint32_t sA = smem_base + soffb;
@@ -423,12 +440,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else if constexpr (A_MODE == 2) {
           if (a.kw_merge) {
             // the three horizontally shifted (16+2)-row patches of the single channel chunk, one lane each
-            if (lane < 3) tma_load_4d(sA + (uint32_t)lane * a.a_sub_bytes, &tmA, bar, 0, t.w0 + lane - 1, t.h0 - 1, t.n0);
+            if (lane < 3) {
+              if constexpr (cta2) tma_load_4d_2sm(sA + (uint32_t)lane * a.a_sub_bytes, &tmA, bar, 0, t.w0 + lane - 1, t.h0 - 1, t.n0);
+              else tma_load_4d(sA + (uint32_t)lane * a.a_sub_bytes, &tmA, bar, 0, t.w0 + lane - 1, t.h0 - 1, t.n0);
+            }
           } else {
             // one horizontally shifted (16+2)-row patch serves the three taps kh = 0..2 of this kw
             const UnitDesc d = s_units[st];
             if (lane == 0) {
-              tma_load_4d(sA, &tmA, bar, d.a_c0, t.w0 + d.kw - 1, t.h0 - 1, t.n0);
+              if constexpr (cta2) tma_load_4d_2sm(sA, &tmA, bar, d.a_c0, t.w0 + d.kw - 1, t.h0 - 1, t.n0);
+              else tma_load_4d(sA, &tmA, bar, d.a_c0, t.w0 + d.kw - 1, t.h0 - 1, t.n0);
             } else if (lane < 4 && !a.b_stationary) {
               const int kh = lane - 1;
               if (CS > 1)
@@ -500,7 +521,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint64_t adesc0 = make_smem_desc(smem_base, a.a_lbo, a.a_sbo, a.layout_type);
     const uint64_t bdesc0 = make_smem_desc(a.b_stationary ? smem_b_stat : smem_base + a.a_stage_bytes, a.b_lbo, a.b_sbo,
                                            a.layout_type);
-    if (a.b_stationary) {
+    // pair: only the leader CTA issues (M = 256 MMAs that read both CTAs' smem and write both CTAs' TMEM); the follower's
+    // MMA warp owns nothing but its TMEM allocation
+    const bool issuer = !cta2 || crank == 0;
+    constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    if (a.b_stationary && issuer) {
       mbar_wait(&bfull_bar, 0);
       tc_fence_after();
     }
@@ -523,7 +548,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t b_kh_mul = bstat ? (uint32_t)(3 * a.cchunks) * b_sub16 : b_sub16;    // mode 2
     uint32_t stage = 0, phase = 0, soff = 0, bsoff = 0;
     uint32_t it = 0;
-    for (int tile = sched_first; tile < total_tiles; tile += sched_step, ++it) {
+    for (int tile = sched_first; tile < (issuer ? total_tiles : 0); tile += sched_step, ++it) {
       const uint32_t buf = it % NBUF;
       mbar_wait_a(tempty0 + 8u * buf, ((it / NBUF) & 1u) ^ 1u);
       tc_fence_after();
@@ -559,7 +584,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else if constexpr (A_MODE == 2) {
-          if (is_leader) {
+          // one body for both MMA flavours (the branch on the flavour stays outside the unrolled loops)
+          auto issue = [&](auto two_tag) {
+            constexpr bool TWO = decltype(two_tag)::value;
+            auto mma = [&](uint64_t ad, uint64_t bd) {
+              if constexpr (TWO) umma_bf16_2sm(tmem_d, ad, bd, idesc2, accum);
+              else umma_bf16(tmem_d, ad, bd, idesc, accum);
+              accum = 1;
+            };
             if (a.kw_merge) {
               // all three horizontally shifted patches in one stage, stationary B indexed by tap = kh * 3 + kw
               // (one channel chunk): 9 * KSTEPS MMAs behind a single barrier round trip, every offset a constant
@@ -570,10 +602,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const uint64_t ad = ad_s + (uint32_t)kw * a_sub16 + (uint32_t)kh * khshift16;
                   const uint64_t bd = bd_s + (uint32_t)(kh * 3 + kw) * b_sub16;     // (bd_s == bdesc0: stationary, bidx0 = 0)
 #pragma unroll
-                  for (int ks = 0; ks < KSTEPS; ++ks) {
-                    umma_bf16(tmem_d, ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep, idesc, accum);
-                    accum = 1;
-                  }
+                  for (int ks = 0; ks < KSTEPS; ++ks) mma(ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep);
                 }
               }
             } else {
@@ -582,12 +611,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint64_t ad = ad_s + (uint32_t)kh * khshift16;           // rows of tap (kh,kw) = patch rows + kh
                 const uint64_t bd = bd_s + (uint32_t)kh * b_kh_mul;
 #pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                  umma_bf16(tmem_d, ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep, idesc, accum);
-                  accum = 1;
-                }
+                for (int ks = 0; ks < KSTEPS; ++ks) mma(ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep);
               }
             }
+          };
+          if (is_leader) {
+            issue(std::integral_constant<bool, cta2>{});
           }
         } else {
           if (is_leader) {
@@ -607,8 +636,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           bcur += b_cursor_inc;
         }
         if (is_leader) {
-          if (CS > 1) umma_commit_mc_a(empty_addr, mc_mask);   // release the stage in every CTA of the cluster
-          else umma_commit_a(empty_addr);                      // frees the smem stage when these MMAs retire
+          if constexpr (cta2) umma_commit_2sm_mc(empty_addr, (uint16_t)3);    // the pair's MMAs retired: both CTAs' copies of the stage are free
+          else if (CS > 1) umma_commit_mc_a(empty_addr, mc_mask);   // release the stage in every CTA of the cluster
+          else umma_commit_a(empty_addr);                           // frees the smem stage when these MMAs retire
         }
         __syncwarp();
         ++stage;
@@ -616,7 +646,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bsoff += b_stage_inc;
         if (stage == nstages) { stage = 0; phase ^= 1u; soff = 0; bsoff = 0; }
       }
-      if (is_leader) umma_commit_a(tfull0 + 8u * buf);               // accumulator complete -> epilogue
+      if (is_leader) {                                               // accumulator complete -> epilogue (pair: of both CTAs)
+        if constexpr (cta2) umma_commit_2sm_mc(tfull0 + 8u * buf, (uint16_t)3);
+        else umma_commit_a(tfull0 + 8u * buf);
+      }
       __syncwarp();
     }
   } else {
@@ -685,7 +718,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // my last chunk is in registers: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          if (lane == 0) {
+            if constexpr (cta2) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[buf]) & PEER_BIT_MASK);   // the leader's barrier counts both CTAs
+            else mbar_arrive(&tmem_empty_bar[buf]);
+          }
         }
         const int c0 = nbase + cc;
         if (A_MODE != 0 && pool && !out_f32 && c0 + 32 <= a.Cout && (a.ldy & 7) == 0) {
@@ -705,7 +741,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == WARP_MMA) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (cta2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -760,9 +797,9 @@ static void choose_box(int N, int H, int W, bool pool, int* tw, int* th, int* nb
   *tw = btw; *th = bth; *nb = bnb;
 }
 
-template <int BLOCK_N, int A_MODE, int KIND>
+template <int BLOCK_N, int A_MODE, int KIND, bool CTA2 = false>
 static int launch_conv3(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, size_t smem, cudaStream_t st) {
-  Y2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, A_MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  Y2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, A_MODE, KIND, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
   const int CS = a.cluster;
   long long units = (long long)((a.m_tiles + CS - 1) / CS) * a.n_tiles;
@@ -782,7 +819,7 @@ static int launch_conv3(const CUtensorMap& tmA, const CUtensorMap& tmB, const Co
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, A_MODE, KIND>, tmA, tmB, a));
+  Y2_CUDA(cudaLaunchKernelEx(&cfg, (conv_tc_kernel<BLOCK_N, A_MODE, KIND, CTA2>), tmA, tmB, a));
   Y2_LAUNCHED();
   return Y2_OK;
 }
@@ -792,7 +829,11 @@ static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Co
   switch (a.a_mode) {
     case 0: return launch_conv3<BLOCK_N, 0, KIND>(tmA, tmB, a, smem, st);
     case 1: return launch_conv3<BLOCK_N, 1, KIND>(tmA, tmB, a, smem, st);
-    default: return launch_conv3<BLOCK_N, 2, KIND>(tmA, tmB, a, smem, st);
+    default:
+      if constexpr (KIND != 0 && BLOCK_N <= 128) {
+        if (a.cta2) return launch_conv3<BLOCK_N, 2, KIND, true>(tmA, tmB, a, smem, st);
+      }
+      return launch_conv3<BLOCK_N, 2, KIND>(tmA, tmB, a, smem, st);
   }
 }
 
@@ -950,9 +991,22 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   // bytes per pipeline stage that the TMA unit will report on the stage's mbarrier
   a.tx_bytes = (a.a_mode == 2 && a.first_layer ? a.a_sub_bytes : a.a_stage_bytes);
   fastdiv_init((uint32_t)a.cchunks, &a.fd_cch_mul, &a.fd_cch_shr);
+  const size_t SMEM_BUDGET = 218 * 1024;           // dynamic smem for operands (static smem + slack stay below 227 KB)
+  // CTA pair on cta_group::2 MMAs for the halo-patch layers with a single N tile (layers 2-5): a single-CTA MMA fetches
+  // (4096 + 32 N) bytes of operands at ~64 B/clk -- 96 / 128 clk at N = 64 / 128 for 32 / 64 clk of arithmetic; in a
+  // pair each SM fetches its own A rows and HALF of the filters (80 / 96 clk).  Each CTA keeps half of the resident bank.
+  a.cta2 = 0;
+  if (a.a_mode == 2 && !a.first_layer && a.n_tiles == 1 && a.m_tiles >= 2 && block_n >= 64 && block_n <= 128 &&
+      ((block_n / 2) * a.row_bytes) % 1024 == 0 && !getenv("Y2_CONV_NO_CTA2")) {
+    const uint32_t half = (uint32_t)(block_n / 2) * a.row_bytes;
+    if ((size_t)a.kblocks * half + 4 * (size_t)a.a_stage_bytes <= SMEM_BUDGET) {
+      a.cta2 = 1;
+      a.b_sub_bytes = half;
+      a.b_stage_bytes = 3 * half;
+    }
+  }
   // B-stationary: with a single N tile and a small filter bank, every tile of the CTA needs the same B
   a.b_total_bytes = a.first_layer ? a.b_sub_bytes : (uint32_t)a.kblocks * a.b_sub_bytes;
-  const size_t SMEM_BUDGET = 218 * 1024;           // dynamic smem for operands (static smem + slack stay below 227 KB)
   a.b_stationary = (a.n_tiles == 1 && a.b_total_bytes + 4 * (size_t)a.a_stage_bytes <= SMEM_BUDGET &&
                     !getenv("Y2_CONV_NO_BSTAT")) ? 1 : 0;
   // halo-patch mode with a resident filter bank and a single channel chunk (layer 2: Cin = 32): the three
@@ -968,7 +1022,11 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   // CTA pairs with B multicast (opt-in, Y2_CONV_CLUSTER=1): each CTA fetches half of the B tile for both.
   // Measured on B200 it is ~15% SLOWER than independent CTAs: the kernel is bound by bytes delivered into
   // each SM (~49 B/clk/SM), which multicast does not reduce -- see DESIGN.md.
-  a.cluster = 1;
+  a.cluster = a.cta2 ? 2 : 1;
+  if (a.cta2 && !a.b_stationary) {
+    set_error("y2_conv_fwd_bf16: internal: CTA-pair mode without a resident filter bank");
+    return Y2_ERR_UNSUPPORTED;
+  }
   if (!a.first_layer && !a.b_stationary && a.m_tiles >= 2 && (a.b_sub_bytes / 2) % 1024 == 0 && block_n >= 64 &&
       getenv("Y2_CONV_CLUSTER"))
     a.cluster = 2;

@@ -2,6 +2,7 @@
 // tensor-core kernels (conv_tcgen05.cu: forward / dgrad, conv_wgrad_tcgen05.cu: weight gradient).
 #pragma once
 #include <cuda.h>
+#include <type_traits>
 #include <mutex>
 #include <cstring>
 #include <cstdlib>
@@ -152,6 +153,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "l"(TMA_CACHE_HINT_DEFAULT)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(TMA_CACHE_HINT_DEFAULT)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_im2col_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h,
