@@ -53,8 +53,8 @@ def conv_flops_per_image(image_size, output_filter):
 
 def make_config(world, extra=None):
     """config of the bench line -- the reference arm prints the same one (it is the driver's join key)."""
-    cfg = dict(workload='Darknet19-YOLO2 416x416 inference, fwd + region decode + per-class NMS, synthetic uint8 batch '
-                        '%d per GPU (BASELINE.json configs[1])' % BATCH_PER_GPU,
+    cfg = dict(workload='Darknet19-YOLO2 %dx%d inference, fwd + region decode + per-class NMS, synthetic uint8 batch ' % (IMAGE_SIZE, IMAGE_SIZE) +
+                        '%d per GPU (BASELINE.json configs[%d])' % (BATCH_PER_GPU, 1 if IMAGE_SIZE == 416 else 3),
                global_batch=world * BATCH_PER_GPU, image_size=IMAGE_SIZE, output_filter=OUTPUT_FILTER,
                score_thresh=SCORE_THRESH, iou_thresh=IOU_THRESH, head_bn='batch statistics',
                l2='flushed (256 MiB memset) between timed steps', parallelism='batch sharding x%d' % world)
@@ -65,8 +65,8 @@ def make_config(world, extra=None):
 
 def load_traffic():
     """DRAM bytes (read + write) of the 22 conv launches of one step, from the committed ncu launch list of this same
-    command (profiles/r1c_traffic.json; ncu numbers are never taken live inside a timed run)."""
-    p = os.path.join(ROOT, 'profiles', 'r1c_traffic.json')
+    command (profiles/r1d_traffic.json; ncu numbers are never taken live inside a timed run)."""
+    p = os.path.join(ROOT, 'profiles', 'r1d_traffic.json')
     try:
         return float(json.load(open(p))['conv_dram_bytes_per_step'])
     except Exception:  # noqa: BLE001
@@ -175,8 +175,8 @@ def run_reference(args):
     timed = t_all[args.warmup:]
     total = sum(timed)
     value = sample_batch * len(timed) / total
-    sample = 'batch %d of 416x416 per step (bounded sample of the batch-64 workload), torch-CPU fp32' % sample_batch
-    line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+    sample = 'batch %d of %dx%d per step (bounded sample of the batch-64 workload), torch-CPU fp32' % (sample_batch, IMAGE_SIZE, IMAGE_SIZE)
+    line = dict(metric=METRIC.replace('416x416', '%dx%d' % (IMAGE_SIZE, IMAGE_SIZE)), value=value, unit='images/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * total / len(timed), higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='reference',
                 config=make_config(max(args.gpus, 1)),
@@ -295,8 +295,8 @@ def run_ours(args):
         conv_ms_source = 'whole device-timed step (upper bound: the per-launch events of the eager replay summed to more)'
     achieved = N * flops_img / (conv_total_ms * 1e-3) / 1e12
     roofline = dict(bound='tensor', achieved=achieved, peak=peaks['sustained'], unit='TFLOP/s',
-                    frac=achieved / peaks['sustained'], traffic=load_traffic(),
-                    algorithmic_bytes=N * 35.0e6, traffic_source='profiles/r1c_traffic.json (ncu launch list of this command)', peak_source=peaks['which'] + ' sustained bf16',
+                    frac=achieved / peaks['sustained'], traffic=load_traffic() if IMAGE_SIZE == 416 and N == 64 else None,
+                    algorithmic_bytes=N * (35.0e6 if IMAGE_SIZE == 416 else 35.0e6 * IMAGE_SIZE * IMAGE_SIZE / (416.0 * 416.0)), traffic_source='profiles/r1d_traffic.json (ncu launch list of this command)', peak_source=peaks['which'] + ' sustained bf16',
                     kernel='conv_tc_kernel x21 + conv1_u8_pool_kernel (22 conv launches/step)', conv_ms_per_step=conv_total_ms, conv_ms_source=conv_ms_source,
                     per_layer_tflops=[round(N * f / (ms * 1e-3) / 1e12, 1) for f, ms in zip(per_layer, conv_ms)])
 
@@ -310,7 +310,7 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             cpu = dict(value=None, unit='images/s', cores=os.cpu_count(), kind='port', sample='failed: %r' % (e,))
 
-    line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+    line = dict(metric=METRIC.replace('416x416', '%dx%d' % (IMAGE_SIZE, IMAGE_SIZE)), value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=t_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
                 data='synthetic',
                 config=make_config(world, dict(nms_candidates=cand, nms_kept=kept)),
@@ -363,7 +363,14 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches (for ncu launch lists)')
+    ap.add_argument('--image-size', type=int, default=None, help='416 (headline, BASELINE configs[1]) or 608 (configs[3])')
+    ap.add_argument('--batch', type=int, default=None, help='images per GPU (default 64; configs[3] uses 32 at 608)')
     args = ap.parse_args()
+    global IMAGE_SIZE, BATCH_PER_GPU
+    if args.image_size:
+        IMAGE_SIZE = args.image_size
+    if args.batch:
+        BATCH_PER_GPU = args.batch
     if args.impl == 'reference':
         run_reference(args)
     else:

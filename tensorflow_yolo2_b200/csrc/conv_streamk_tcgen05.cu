@@ -327,11 +327,25 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // segment overlaps the MMAs of the next.  Stream-K split, partial hand-over and epilogue as above, per CTA pair:
 // pair c's head waits for the partials of pair c + 1 (same rank: same rows), slots / flags indexed by blockIdx.x.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int SK2_STAGES = 6;                  // 32 KB each per CTA: A 128 px x 128 B, B 128 filters x 128 B
-constexpr uint32_t SK2_A_BYTES = 128 * 128, SK2_STAGE = 2 * 128 * 128;
+// HALVES = 1: 256 x 256 pair tiles, the two accumulator buffers alternate between segments (above).
+// HALVES = 2: 512 x 256 pair tiles -- each CTA carries TWO 128-row halves (two accumulators = all 512 TMEM columns,
+//   single-buffered) that share its half of the filters: 48 KB per K step for twice the flops of 32 KB.  The HALVES = 1
+//   kernel runs at the L2 -> SM delivery limit (ncu: 1.64 GB in 143 us = 11.5 TB/s, tensor pipe 77 % busy, the issuer
+//   waiting on TMA), so fewer delivered bytes per flop is what is left; the price is an un-overlapped epilogue (~150 k clk
+//   of MMAs per drain at K = 9 x 1024, so a few per cent).
+constexpr uint32_t SK2_A_BYTES = 128 * 128;
+template <int HALVES> struct Sk2Cfg {
+  static constexpr uint32_t STAGE = (HALVES + 1) * SK2_A_BYTES;          // per CTA: HALVES x (128 px x 128 B) + 128 filters x 128 B
+  static constexpr int STAGES = HALVES == 1 ? 6 : 4;                     // 192 KB of operands either way
+};
 
+template <int HALVES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SK_THREADS, 1)
 conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SkArgs a) {
+  constexpr int SK2_STAGES = Sk2Cfg<HALVES>::STAGES;
+  constexpr uint32_t SK2_STAGE = Sk2Cfg<HALVES>::STAGE;
+  constexpr int NCHUNK = 4 * HALVES;                           // 32-column chunks per epilogue warp and segment
+  constexpr uint32_t TILE_ROWS = 256u * HALVES;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[SK2_STAGES], empty_bar[SK2_STAGES], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t s_tmem_base;
@@ -381,12 +395,17 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int k1 = (int)min((long long)a.ksteps, k0 + (u_end - u));
         const uint32_t mt = fdiv(tile, a.fd_nt_mul, a.fd_nt_shr);
         const int nrow0 = (int)(tile - mt * (uint32_t)a.n_tiles) * 256 + (int)rank * 128;   // my half of the filters
-        uint32_t m = mt * 256u + rank * 128u;                                               // my half of the pixels
-        if ((long long)m >= a.M) m = 0;                        // half tile entirely past the end: load valid pixels, rows are masked
-        const uint32_t row = fdiv(m, a.fd_w_mul, a.fd_w_shr);
-        const int w0 = (int)(m - row * (uint32_t)a.W);
-        const uint32_t img = fdiv(row, a.fd_h_mul, a.fd_h_shr);
-        const int h0 = (int)(row - img * (uint32_t)a.H), n0 = (int)img;
+        int w0[HALVES], h0[HALVES], n0[HALVES];
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) {
+          uint32_t m = mt * TILE_ROWS + (uint32_t)h * 256u + rank * 128u;                   // my rows of half h
+          if ((long long)m >= a.M) m = 0;                      // entirely past the end: load valid pixels, rows are masked
+          const uint32_t row = fdiv(m, a.fd_w_mul, a.fd_w_shr);
+          w0[h] = (int)(m - row * (uint32_t)a.W);
+          const uint32_t img = fdiv(row, a.fd_h_mul, a.fd_h_shr);
+          h0[h] = (int)(row - img * (uint32_t)a.H);
+          n0[h] = (int)img;
+        }
         for (int k = k0; k < k1; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);             // my own copy: the leader's commit arrives on both
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * SK2_STAGE);
@@ -394,8 +413,11 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int kh = a.pad ? (tap * 11) >> 5 : 0, kw = tap - kh * 3;       // tap / 3 for tap < 9 (1x1: tap == 0)
           const uint32_t sA = smem_base + stage * SK2_STAGE;
           const uint32_t bar = smem_u32(&full_bar[stage]) & PEER_BIT_MASK;      // the leader's barrier
-          tma_load_im2col_4d_2sm(sA, &tmA, bar, a_c0, w0 - a.pad, h0 - a.pad, n0, (uint16_t)kw, (uint16_t)kh);
-          tma_load_2d_2sm(sA + SK2_A_BYTES, &tmB, bar, tap * a.cin_p + a_c0, nrow0);
+#pragma unroll
+          for (int h = 0; h < HALVES; ++h)
+            tma_load_im2col_4d_2sm(sA + (uint32_t)h * SK2_A_BYTES, &tmA, bar, a_c0, w0[h] - a.pad, h0[h] - a.pad, n0[h], (uint16_t)kw,
+                                   (uint16_t)kh);
+          tma_load_2d_2sm(sA + HALVES * SK2_A_BYTES, &tmB, bar, tap * a.cin_p + a_c0, nrow0);
           if (++stage == SK2_STAGES) { stage = 0; phase ^= 1u; }
         }
         u += k1 - k0;
@@ -409,7 +431,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // D=f32, A=B=bf16, K-major both, N = 256, M = 256 (the pair)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint64_t adesc0 = make_smem_desc(smem_base, 16u, 8u * 128u, 2u);                    // SWIZZLE_128B, K-major
-      const uint64_t bdesc0 = make_smem_desc(smem_base + SK2_A_BYTES, 16u, 8u * 128u, 2u);
+      const uint64_t bdesc0 = make_smem_desc(smem_base + HALVES * SK2_A_BYTES, 16u, 8u * 128u, 2u);
       const uint32_t empty0 = smem_u32(&empty_bar[0]), tfull0 = smem_u32(&tmem_full[0]);
       int stage = 0;
       uint32_t phase = 0, seg = 0;
@@ -418,8 +440,9 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t tile = (uint32_t)fdiv((uint32_t)u, a.fd_ks_mul, a.fd_ks_shr);
         const int k0 = (int)(u - (long long)tile * a.ksteps);
         const int k1 = (int)min((long long)a.ksteps, k0 + (u_end - u));
-        const uint32_t buf = seg & 1u;
-        mbar_wait(&tmem_empty[buf], ((seg >> 1) & 1u) ^ 1u);     // both CTAs drained this buffer's previous segment
+        const uint32_t buf = HALVES == 1 ? (seg & 1u) : 0u;
+        const uint32_t par = HALVES == 1 ? ((seg >> 1) & 1u) : (seg & 1u);
+        mbar_wait(&tmem_empty[buf], par ^ 1u);                   // both CTAs drained this buffer's previous segment
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * 256u;
         uint32_t accum = 0;
@@ -430,7 +453,10 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t soff = (uint32_t)(stage * SK2_STAGE) >> 4;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16_2sm(tmem_d, adesc0 + soff + (uint32_t)(ks * 2), bdesc0 + soff + (uint32_t)(ks * 2), idesc, accum);
+#pragma unroll
+              for (int h = 0; h < HALVES; ++h)
+                umma_bf16_2sm(tmem_d + (uint32_t)(h * 256), adesc0 + soff + (uint32_t)(h * (SK2_A_BYTES >> 4)) + (uint32_t)(ks * 2),
+                              bdesc0 + soff + (uint32_t)(ks * 2), idesc, accum);
               accum = 1;
             }
             umma_commit_2sm_mc(empty0 + 8u * (uint32_t)stage, (uint16_t)3);
@@ -458,7 +484,8 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const bool head = k0 == 0 && k1 < a.ksteps;              // owner: add the partial of CTA blockIdx.x + 2, finalise
       const uint32_t mt = fdiv(tile, a.fd_nt_mul, a.fd_nt_shr);
       const int col0 = (int)(tile - mt * (uint32_t)a.n_tiles) * 256 + chalf * 128;
-      const uint32_t buf = seg & 1u;
+      const uint32_t buf = HALVES == 1 ? (seg & 1u) : 0u;
+      const uint32_t par = HALVES == 1 ? ((seg >> 1) & 1u) : (seg & 1u);
       if (head) {
         if (et == 0) {
           const int* f = a.ws_flags + blockIdx.x + 2;
@@ -475,25 +502,26 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
       }
-      mbar_wait(&tmem_full[buf], (seg >> 1) & 1u);
+      mbar_wait(&tmem_full[buf], par);
       tc_fence_after();
       const uint32_t stg = smem_base + SK2_STAGES * SK2_STAGE + (uint32_t)warp * SK_STG_WARP;
-      float4* part = reinterpret_cast<float4*>(a.ws_partial + (size_t)(tail ? blockIdx.x : blockIdx.x + 2) * 32768) +
-                     (size_t)warp * 1024 + lane;                  // + hc * 256 + i * 32
+      float4* part = reinterpret_cast<float4*>(a.ws_partial + (size_t)(tail ? blockIdx.x : blockIdx.x + 2) * (32768 * HALVES)) +
+                     (size_t)warp * (1024 * HALVES) + lane;        // + hc * 256 + i * 32
       float4 pv[8];
       if (head) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) pv[i] = __ldcg(part + i * 32);
       }
 #pragma unroll 1
-      for (int hc = 0; hc < 4; ++hc) {
-        const int c = hc * 32;
-        const int row0 = (int)rank * 128 + q * 32;                // first tile row of this warp's 32-row slab
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)(chalf * 128 + c);
+      for (int hc = 0; hc < NCHUNK; ++hc) {
+        const int h = hc >> 2, c = (hc & 3) * 32;
+        const int row0 = h * 256 + (int)rank * 128 + q * 32;      // first tile row of this warp's 32-row slab
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (HALVES == 1 ? buf * 256u : (uint32_t)(h * 256)) +
+                               (uint32_t)(chalf * 128 + c);
         uint32_t v[32];
         tmem_ld32(taddr, v);
         tmem_ld_wait();
-        if (hc == 3) {                                         // my last chunk is in registers
+        if (hc == NCHUNK - 1) {                                // my last chunk is in registers
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty[buf]) & PEER_BIT_MASK);
@@ -517,7 +545,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           f[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]) + p4.z, sc.z, sh.z);
           f[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]) + p4.w, sc.w, sh.w);
         }
-        if (head && hc < 3) {                                  // prefetch the next chunk's partial behind this chunk's stores
+        if (head && hc < NCHUNK - 1) {                         // prefetch the next chunk's partial behind this chunk's stores
 #pragma unroll
           for (int i = 0; i < 8; ++i) pv[i] = __ldcg(part + (hc + 1) * 256 + i * 32);
         }
@@ -525,7 +553,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], a.alpha * f[i]);
         }
-        const long long grow0 = (long long)mt * 256 + row0;       // global row of slab row 0
+        const long long grow0 = (long long)mt * TILE_ROWS + row0; // global row of slab row 0
         if (a.out_f32) {
           // lane = slab row: 8 x 16-byte units, unit j of row r at (j ^ (r & 7))
 #pragma unroll
@@ -627,13 +655,18 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   a.H = p->H; a.W = p->W; a.ldy = ldy; a.pad = p->ksize / 2;
   a.cin_p = p->Cin; a.cchunks = cchunks; a.ksteps = ksteps;
   a.n_tiles = p->Cout / 256;
-  const long long m_tiles = (a.M + 255) / 256;
+  // CTA-pair kernel (cta_group::2) unless disabled; 512-row pair tiles (two halves per CTA) unless disabled or too few tiles
+  const bool two_cta = !getenv("Y2_CONV_STREAMK_1CTA") && g_num_sms >= 2;
+  int halves = 1;
+  if (two_cta && !getenv("Y2_CONV_STREAMK_256") &&
+      (((a.M + 511) / 512) * a.n_tiles >= g_num_sms / 2 || getenv("Y2_CONV_STREAMK_512")))
+    halves = 2;
+  const long long m_tiles = (a.M + 256 * halves - 1) / (256 * halves);
   a.tiles = (int)(m_tiles * a.n_tiles);
   a.units = (long long)a.tiles * ksteps;
   if ((a.tiles < g_num_sms / 2 && !getenv("Y2_CONV_FORCE_STREAMK")) || a.units >= (1ll << 31) || a.M + 256 >= (1ll << 31)) return Y2_OK;
   // every CTA's range must be at least one tile long (a tile is then shared by at most two CTAs)
-  // CTA-pair kernel (cta_group::2) unless disabled: 74 pairs, every pair's range at least one tile long
-  const bool two_cta = !getenv("Y2_CONV_STREAMK_1CTA") && g_num_sms >= 2;
+  // 74 pairs, every pair's range at least one tile long
   const int npairs = a.tiles < g_num_sms / 2 ? a.tiles : g_num_sms / 2;
   const int grid = two_cta ? 2 * npairs : (a.tiles < g_num_sms ? a.tiles : g_num_sms);
   if (g_sk_ws_bytes < sk_workspace_bytes(g_num_sms)) return Y2_OK;
@@ -679,9 +712,15 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
     g_sk_flags_zeroed = true;
   }
   if (two_cta) {
-    const size_t smem = (size_t)SK2_STAGES * SK2_STAGE + 8 * SK_STG_WARP + 1024;
-    Y2_CUDA(cudaFuncSetAttribute(conv_streamk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_streamk2_kernel<<<grid, SK_THREADS, smem, st>>>(tmA, tmB, a);
+    const size_t smem = (size_t)Sk2Cfg<1>::STAGES * Sk2Cfg<1>::STAGE + 8 * SK_STG_WARP + 1024;     // same for both variants
+    static_assert(Sk2Cfg<1>::STAGES * Sk2Cfg<1>::STAGE == Sk2Cfg<2>::STAGES * Sk2Cfg<2>::STAGE, "operand smem");
+    if (halves == 2) {
+      Y2_CUDA(cudaFuncSetAttribute(conv_streamk2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv_streamk2_kernel<2><<<grid, SK_THREADS, smem, st>>>(tmA, tmB, a);
+    } else {
+      Y2_CUDA(cudaFuncSetAttribute(conv_streamk2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv_streamk2_kernel<1><<<grid, SK_THREADS, smem, st>>>(tmA, tmB, a);
+    }
   } else {
     const size_t smem = (size_t)SK_STAGES * SK_STAGE + 8 * SK_STG_WARP + 1024;
     Y2_CUDA(cudaFuncSetAttribute(conv_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -81,7 +81,9 @@ def test_conv_f32_vs_oracle(ops, N, H, W, Cin, Cout, k):
                                                     (6, 19, 1024, 256, 3, True), (8, 26, 256, 512, 3, False),
                                                     # more tiles than CTA pairs: tiles are split between neighbouring pairs
                                                     # and the partial accumulators travel through the workspace
-                                                    (64, 13, 512, 256, 3, False), (48, 13, 512, 512, 3, True)])
+                                                    (64, 13, 512, 256, 3, False), (48, 13, 512, 512, 3, True),
+                                                    # 512-row pair tiles (two accumulator halves per CTA), tiles split between pairs
+                                                    (64, 13, 256, 1024, 3, False), (60, 13, 256, 1024, 3, True)])
 def test_conv_streamk_vs_generic_and_oracle(ops, monkeypatch, N, S, Cin, Cout, k, out_f32):
     """Deep 3x3 layer on a small map: the 256x256 stream-K kernel (a tile's K range split between two CTAs, the partial
     travels through the workspace and the owner runs the fused epilogue) against the generic tcgen05 kernel and the
@@ -98,6 +100,8 @@ def test_conv_streamk_vs_generic_and_oracle(ops, monkeypatch, N, S, Cin, Cout, k
     ref = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw).float().cpu().numpy().reshape(-1, Cout)
     monkeypatch.delenv('Y2_CONV_NO_STREAMK')
     monkeypatch.setenv('Y2_CONV_FORCE_STREAMK', '1')           # small test shapes have fewer tiles than the auto rule wants
+    if S == 19:
+        monkeypatch.setenv('Y2_CONV_STREAMK_512', '1')         # ... and exercise the two-halves variant on a small shape too
     got1 = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw)
     got2 = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw)
     torch.cuda.synchronize()
