@@ -332,7 +332,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   single-buffered) that share its half of the filters: 48 KB per K step for twice the flops of 32 KB.  The HALVES = 1
 //   kernel runs at the L2 -> SM delivery limit (ncu: 1.64 GB in 143 us = 11.5 TB/s, tensor pipe 77 % busy, the issuer
 //   waiting on TMA), so fewer delivered bytes per flop is what is left; the price is an un-overlapped epilogue (~150 k clk
-//   of MMAs per drain at K = 9 x 1024, so a few per cent).
+//   of MMAs per drain at K = 9 x 1024, so a few per cent).  MEASURED: slower (see the launcher) -- kept as an opt-in.
 constexpr uint32_t SK2_A_BYTES = 128 * 128;
 template <int HALVES> struct Sk2Cfg {
   static constexpr uint32_t STAGE = (HALVES + 1) * SK2_A_BYTES;          // per CTA: HALVES x (128 px x 128 B) + 128 filters x 128 B
@@ -658,9 +658,10 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   // CTA-pair kernel (cta_group::2) unless disabled; 512-row pair tiles (two halves per CTA) unless disabled or too few tiles
   const bool two_cta = !getenv("Y2_CONV_STREAMK_1CTA") && g_num_sms >= 2;
   int halves = 1;
-  if (two_cta && !getenv("Y2_CONV_STREAMK_256") &&
-      (((a.M + 511) / 512) * a.n_tiles >= g_num_sms / 2 || getenv("Y2_CONV_STREAMK_512")))
-    halves = 2;
+  // 512-row pair tiles are opt-in (Y2_CONV_STREAMK_512=1): measured SLOWER on B200 (L19 149 vs 137 us, L6 116 vs 89 us) --
+  // the un-overlapped epilogue, the shallower 4-stage ring and the coarser tile quantisation cost more than the 1.33x
+  // fewer delivered bytes per flop bring
+  if (two_cta && getenv("Y2_CONV_STREAMK_512")) halves = 2;
   const long long m_tiles = (a.M + 256 * halves - 1) / (256 * halves);
   a.tiles = (int)(m_tiles * a.n_tiles);
   a.units = (long long)a.tiles * ksteps;
