@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/yolo2_b200.h"
 
@@ -42,5 +43,30 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 __device__ __forceinline__ float leaky(float v, float alpha) { return fmaxf(v, alpha * v); }
+
+// Programmatic dependent launch (PDL).  A persistent kernel calls pdl_launch_dependents() on entry -- the NEXT kernel of
+// the stream may then be scheduled onto SMs as this kernel's CTAs retire, instead of after the whole grid has drained plus
+// a launch latency -- and a kernel launched with the attribute calls pdl_wait() before its first access to global memory
+// (it returns once the preceding kernel has completed and its writes are visible).  Only the prologue (barrier init, TMEM
+// allocation, descriptor prefetch) runs ahead.  Both are no-ops when the launch carries no programmatic dependency.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// launch attribute list: cluster dimension (always) + programmatic stream serialization (unless Y2_NO_PDL is set)
+static inline int fill_launch_attrs(cudaLaunchAttribute* attr, unsigned cluster) {
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeClusterDimension;
+  attr[n].val.clusterDim.x = cluster;
+  attr[n].val.clusterDim.y = 1;
+  attr[n].val.clusterDim.z = 1;
+  ++n;
+  static const bool no_pdl = getenv("Y2_NO_PDL") != nullptr;
+  if (!no_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  return n;
+}
 
 }  // namespace y2

@@ -55,6 +55,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ __align__(8) uint64_t full_bar[SK_STAGES], empty_bar[SK_STAGES], tmem_full, tmem_empty;
   __shared__ uint32_t s_tmem_base;
   __shared__ uint8_t s_unit_tap[SK_MAX_UNITS], s_unit_cc[SK_MAX_UNITS];
+  pdl_launch_dependents();                                      // persistent grid: the next kernel may take SMs as my CTAs retire
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
@@ -85,6 +86,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();                                                   // everything above overlapped the previous kernel's tail
 
   if (warp == 8) {
     // =========================== TMA producer ===========================
@@ -350,6 +352,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __shared__ __align__(8) uint64_t full_bar[SK2_STAGES], empty_bar[SK2_STAGES], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t s_tmem_base;
   __shared__ uint8_t s_unit_tap[SK_MAX_UNITS], s_unit_cc[SK_MAX_UNITS];
+  pdl_launch_dependents();                                      // persistent grid: the next kernel may take SMs as my CTAs retire
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t rank = cluster_ctarank();                      // 0 = leader (issues the MMAs)
@@ -382,6 +385,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();                                           // the partner's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();                                                   // everything above overlapped the previous kernel's tail
 
   if (warp == 8) {
     // =========================== TMA producer (both CTAs) ===========================
@@ -715,17 +719,35 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   if (two_cta) {
     const size_t smem = (size_t)Sk2Cfg<1>::STAGES * Sk2Cfg<1>::STAGE + 8 * SK_STG_WARP + 1024;     // same for both variants
     static_assert(Sk2Cfg<1>::STAGES * Sk2Cfg<1>::STAGE == Sk2Cfg<2>::STAGES * Sk2Cfg<2>::STAGE, "operand smem");
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(SK_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = fill_launch_attrs(attr, 2u);                 // (matches the kernels' __cluster_dims__)
     if (halves == 2) {
       Y2_CUDA(cudaFuncSetAttribute(conv_streamk2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conv_streamk2_kernel<2><<<grid, SK_THREADS, smem, st>>>(tmA, tmB, a);
+      Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_streamk2_kernel<2>, tmA, tmB, a));
     } else {
       Y2_CUDA(cudaFuncSetAttribute(conv_streamk2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conv_streamk2_kernel<1><<<grid, SK_THREADS, smem, st>>>(tmA, tmB, a);
+      Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_streamk2_kernel<1>, tmA, tmB, a));
     }
   } else {
     const size_t smem = (size_t)SK_STAGES * SK_STAGE + 8 * SK_STG_WARP + 1024;
     Y2_CUDA(cudaFuncSetAttribute(conv_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_streamk_kernel<<<grid, SK_THREADS, smem, st>>>(tmA, tmB, a);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(SK_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = fill_launch_attrs(attr, 1u);
+    Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_streamk_kernel, tmA, tmB, a));
   }
   Y2_LAUNCHED();
   *handled = 1;

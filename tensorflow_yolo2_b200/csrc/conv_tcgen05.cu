@@ -308,6 +308,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(16) float s_shift[TP][BLOCK_N];
   __shared__ UnitDesc s_units[FIRST ? 1 : MAX_UNITS];
 
+  pdl_launch_dependents();                              // persistent grid: the next kernel may take SMs as my CTAs retire
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem, 1024-byte aligned (swizzle-128B atoms): [stationary B (optional)] [stage 0: A | B] [stage 1] ...
   const uint32_t smem_b_stat = (smem_u32(smem) + 1023u) & ~1023u;
@@ -378,6 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CS > 1) cluster_sync_all();                       // partner's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();                                           // everything above overlapped the previous kernel's tail
 
   if (warp == WARP_PRODUCER) {
     // =========================== TMA producer ===========================
@@ -812,13 +814,9 @@ static int launch_conv3(const CUtensorMap& tmA, const CUtensorMap& tmB, const Co
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = fill_launch_attrs(attr, (unsigned)CS);
   Y2_CUDA(cudaLaunchKernelEx(&cfg, (conv_tc_kernel<BLOCK_N, A_MODE, KIND, CTA2>), tmA, tmB, a));
   Y2_LAUNCHED();
   return Y2_OK;
