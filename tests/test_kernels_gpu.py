@@ -76,6 +76,39 @@ def test_conv_f32_vs_oracle(ops, N, H, W, Cin, Cout, k):
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())   # fp32 path: 1e-5
 
 
+# ---------------------------------------------------------------------------------- a1 halo-patch path, CTA pairs
+@pytest.mark.parametrize('N,H,W,Cin,Cout,pool', [(3, 72, 72, 32, 64, True),      # kw-merged stages, odd tile count (135)
+                                                 (2, 64, 80, 64, 128, False),    # one chunk, 128-wide, un-pooled
+                                                 (1, 104, 104, 128, 64, False),  # two chunks; 91 tiles: last pair half empty
+                                                 (2, 66, 70, 64, 128, True)])    # ragged borders inside the 8x16 tiles
+def test_conv_halo_pair_vs_single_cta_and_oracle(ops, monkeypatch, N, H, W, Cin, Cout, pool):
+    """3x3 layers on maps >= 64x64 run as CTA pairs on cta_group::2 MMAs (each CTA its own 8x16-pixel tile and half of the
+    resident filters): bit-identical to the single-CTA kernel (same products, same fp32 accumulation order per output) and
+    within bf16 tolerance of the oracle, with fused scale/shift (negative scales too), leaky and 2x2 pool."""
+    rs = np.random.RandomState(H + Cin)
+    x = rs.randn(N, H, W, Cin).astype(np.float32)
+    w = (rs.randn(3, 3, Cin, Cout) * 0.05).astype(np.float32)
+    b = rs.randn(Cout).astype(np.float32)
+    sc = (rs.uniform(0.5, 1.5, Cout) * np.where(rs.rand(Cout) < 0.3, -1, 1)).astype(np.float32)
+    xb = cu(x, torch.bfloat16)
+    wp = ops.pack_weights_bf16(cu(w))
+    kw = dict(scale=cu(sc), shift=cu(b), leaky=True, pool=pool)
+    got = ops.conv_fwd_bf16(xb, wp, 3, Cin, Cout, **kw)
+    monkeypatch.setenv('Y2_CONV_NO_CTA2', '1')
+    ref = ops.conv_fwd_bf16(xb, wp, 3, Cin, Cout, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+    want = O.conv2d_same(O.bf16_round(torch.tensor(x)).double(), O.bf16_round(torch.tensor(w)).double(), torch.float64)
+    want = want * torch.tensor(sc).double() + torch.tensor(b).double()
+    want = torch.maximum(O.ALPHA * want, want)
+    if pool:
+        want = want.reshape(N, H // 2, 2, W // 2, 2, Cout).amax(dim=(2, 4))
+    want = want.numpy()
+    g = got.float().cpu().numpy()
+    np.testing.assert_allclose(g, want, rtol=1e-2, atol=1e-2 * np.abs(want).max())
+    assert np.linalg.norm(g - want) / np.linalg.norm(want) < 4e-3
+
+
 # ---------------------------------------------------------------------------------- a1 stream-K 256x256 path
 @pytest.mark.parametrize('N,S,Cin,Cout,k,out_f32', [(16, 13, 512, 512, 3, True), (9, 13, 1024, 256, 3, False),
                                                     (6, 19, 1024, 256, 3, True), (8, 26, 256, 512, 3, False),
