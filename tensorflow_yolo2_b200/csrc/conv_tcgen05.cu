@@ -86,7 +86,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int unit, ui
   const uint32_t mt = mg * (uint32_t)a.cluster + crank;      // may be >= m_tiles for the last group: all rows masked
   if (a.a_mode == 0) {
     t.m0 = (long long)mt * TILE_M;                       // < 2^31 (checked on the host)
-    const uint32_t m = (uint32_t)t.m0;
+    const uint32_t m = t.m0 < a.M ? (uint32_t)t.m0 : 0u; // the empty half of a last pair loads valid pixels; its rows are masked
     const uint32_t row = fdiv(m, a.fd_w_mul, a.fd_w_shr);         // n*H + h
     t.w0 = (int)(m - row * (uint32_t)a.W);
     const uint32_t img = fdiv(row, a.fd_h_mul, a.fd_h_shr);
@@ -322,7 +322,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // CTA pair on one M = 256 MMA (see conv_streamk2_kernel for the why: the 64 B/clk smem operand path).  Each CTA keeps
   // its own 128-pixel tile and HALF of the resident filter bank; the leader (rank 0) issues, both run producer + epilogue.
   constexpr bool cta2 = CTA2;
-  static_assert(!CTA2 || (A_MODE == 2 && !FIRST), "the CTA-pair variant exists for the halo-patch mode only");
+  static_assert(!CTA2 || !FIRST, "no CTA-pair variant of the first-layer paths");
   const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
   const int sched_first = CS > 1 ? (int)(blockIdx.x / CS) : (int)blockIdx.x;
   const int sched_step = CS > 1 ? (int)(gridDim.x / CS) : (int)gridDim.x;
@@ -466,6 +466,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) {
             for (int j = 0; j < sps; ++j) {
               const UnitDesc d = s_units[st * sps + j];
+              if constexpr (cta2) {
+                // pair: my own pixels and my half of the filter rows, both counted on the leader's barrier
+                if constexpr (A_MODE == 0)
+                  tma_load_im2col_4d_2sm(sA + j * a.a_sub_bytes, &tmA, bar, d.a_c0, t.w0 - a.pad, t.h0 - a.pad, t.n0,
+                                         (uint16_t)d.kw, (uint16_t)d.kh);
+                else
+                  tma_load_4d_2sm(sA + j * a.a_sub_bytes, &tmA, bar, d.a_c0, t.w0 + d.kw - a.pad, t.h0 + d.kh - a.pad, t.n0);
+                if (!a.b_stationary) tma_load_2d_2sm(sB + j * a.b_sub_bytes, &tmB, bar, d.b_k, nrow0 + (int)crank * (BLOCK_N / 2));
+                continue;
+              }
               if constexpr (A_MODE == 0)
                 tma_load_im2col_4d(sA + j * a.a_sub_bytes, &tmA, bar, d.a_c0, t.w0 - a.pad, t.h0 - a.pad, t.n0,
                                    (uint16_t)d.kw, (uint16_t)d.kh);
@@ -628,7 +638,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < subs; ++j) {
 #pragma unroll
               for (int ks = 0; ks < KSTEPS; ++ks) {
-                umma_bf16(tmem_d, ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep, idesc, accum);
+                if constexpr (cta2) umma_bf16_2sm(tmem_d, ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep, idesc2, accum);
+                else umma_bf16(tmem_d, ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep, idesc, accum);
                 accum = 1;
               }
               ad += a_sub16;
@@ -824,6 +835,10 @@ static int launch_conv3(const CUtensorMap& tmA, const CUtensorMap& tmB, const Co
 
 template <int BLOCK_N, int KIND>
 static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, size_t smem, cudaStream_t st) {
+  if constexpr (KIND == 2 && BLOCK_N >= 128) {
+    if (a.cta2 && a.a_mode == 0) return launch_conv3<BLOCK_N, 0, KIND, true>(tmA, tmB, a, smem, st);
+    if (a.cta2 && a.a_mode == 1) return launch_conv3<BLOCK_N, 1, KIND, true>(tmA, tmB, a, smem, st);
+  }
   switch (a.a_mode) {
     case 0: return launch_conv3<BLOCK_N, 0, KIND>(tmA, tmB, a, smem, st);
     case 1: return launch_conv3<BLOCK_N, 1, KIND>(tmA, tmB, a, smem, st);
@@ -1003,6 +1018,14 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
       a.b_stage_bytes = 3 * half;
     }
   }
+  // ... and for the im2col / tiled-box modes with 128-byte rows and >= 128-wide tiles (pooled 52x52 / 26x26 layers, the
+  // 1x1 layers): the filter tile is streamed, each CTA fetching its half of the rows per stage
+  if (a.a_mode != 2 && !a.first_layer && a.row_bytes == 128 && block_n >= 128 && a.m_tiles >= 2 && !getenv("Y2_CONV_NO_CTA2") &&
+      !getenv("Y2_CONV_NO_CTA2_GENERIC") && !getenv("Y2_CONV_CLUSTER")) {
+    a.cta2 = 1;
+    a.b_sub_bytes = (uint32_t)(block_n / 2) * a.row_bytes;
+    a.b_stage_bytes = (uint32_t)a.sps * a.b_sub_bytes;
+  }
   // B-stationary: with a single N tile and a small filter bank, every tile of the CTA needs the same B
   a.b_total_bytes = a.first_layer ? a.b_sub_bytes : (uint32_t)a.kblocks * a.b_sub_bytes;
   a.b_stationary = (a.n_tiles == 1 && a.b_total_bytes + 4 * (size_t)a.a_stage_bytes <= SMEM_BUDGET &&
@@ -1021,8 +1044,8 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   // Measured on B200 it is ~15% SLOWER than independent CTAs: the kernel is bound by bytes delivered into
   // each SM (~49 B/clk/SM), which multicast does not reduce -- see DESIGN.md.
   a.cluster = a.cta2 ? 2 : 1;
-  if (a.cta2 && !a.b_stationary) {
-    set_error("y2_conv_fwd_bf16: internal: CTA-pair mode without a resident filter bank");
+  if (a.cta2 && a.a_mode == 2 && !a.b_stationary) {
+    set_error("y2_conv_fwd_bf16: internal: halo-patch CTA-pair mode without a resident filter bank");
     return Y2_ERR_UNSUPPORTED;
   }
   if (!a.first_layer && !a.b_stationary && a.m_tiles >= 2 && (a.b_sub_bytes / 2) % 1024 == 0 && block_n >= 64 &&
