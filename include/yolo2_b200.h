@@ -147,6 +147,9 @@ int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const flo
 /* a3: tf.nn.max_pool 2x2/2 (darknet.py:24-25) on bf16 [N,H,W,C] -> [N,H/2,W/2,C]; C % 8 == 0.  (The pool normally runs
  * in the conv epilogue; this kernel serves the layer whose un-pooled output is also the passthrough source.) */
 int y2_maxpool2x2_bf16(const void* x, void* y, int N, int H, int W, int C, y2_stream_t stream);
+/* tf.nn.avg_pool / tf.layers.average_pooling2d with ksize == stride, evenly divisible map (darknet.py:28-29,116: the
+ * 7x7 global pool of the darknet19 classifier).  x NHWC (x_dtype 0 = f32, 1 = bf16) -> y f32 [N,H/k,W/k,C]. */
+int y2_avgpool(const void* x, int x_dtype, float* y, int N, int H, int W, int C, int k, y2_stream_t stream);
 
 /* ---- a8: grid decode of show_yolo_detection (yolo2_nets/net_utils.py:393-407,418) -----------
  * net [N,S,S,C+5B] f32.  boxes [N,S,S,B,4] = ((x+j)/S, (y+i)/S, w^2, h^2); conf [N,S,S,B];

@@ -176,6 +176,24 @@ def darknet19_forward(x_nhwc, params_core, params_head, core_training=False, hea
     return x
 
 
+def avg_pool_kxk(x_nhwc, k):
+    """darknet.py:28-29 / :116: k x k, stride k average pool on an evenly divisible map."""
+    n, h, w, c = x_nhwc.shape
+    return x_nhwc.reshape(n, h // k, k, w // k, k, c).mean(dim=(2, 4))
+
+
+def darknet19_classifier_forward(x_nhwc, params_core, param_cls, training=False, dtype=None, bf16_operands=False):
+    """darknet.py:61-123: core layers + conv_bn_layer(1x1, 1024 -> 1000) + 7x7 average pool + reshape -> logits [N, 1000]."""
+    dtype = dtype or torch.float64
+    x = x_nhwc.to(dtype)
+    for (k, cin, cout, pool), p in zip(CORE_PLAN, params_core):
+        x, _, _ = conv_bn_layer(x, p, training, dtype, bf16_operands)
+        if pool:
+            x = max_pool_2x2(x)
+    x, _, _ = conv_bn_layer(x, param_cls, training, dtype, bf16_operands)
+    return avg_pool_kxk(x, 7).reshape(-1, x.shape[-1])
+
+
 # ----------------------------------------------------------------------------------------------
 # net_utils.py:222-260  get_iou      (numpy; dtype follows the inputs)
 # ----------------------------------------------------------------------------------------------

@@ -47,6 +47,7 @@ _SIGNATURES = {
     'y2_affine_leaky_pool': (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     'y2_affine_leaky_pool_ex': (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'y2_maxpool2x2_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'y2_avgpool': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     'y2_decode_ref_v1': (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     'y2_decode_region': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     'y2_nms_workspace_bytes': (_sz, [_i, _i, _i]),

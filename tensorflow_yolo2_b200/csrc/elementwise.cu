@@ -401,6 +401,28 @@ __global__ void maxpool2x2_bf16_kernel(const uint4* __restrict__ x, uint4* __res
 }
 
 // a11  tf.train.AdamOptimizer (pascal_train_darknet.py:51): TF1 update form, lr_t from the host.
+// tf.nn.avg_pool / tf.layers.average_pooling2d with ksize == stride on an evenly divisible map (darknet.py:28-29,116: the
+// 7x7 global pool of the darknet19 classifier): NHWC bf16 or f32 in, f32 out; one thread per output element, window summed
+// row-major in float32.
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int k) {
+  const int Ho = H / k, Wo = W / k;
+  const size_t total = (size_t)N * Ho * Wo * C;
+  const float inv = 1.0f / (float)(k * k);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t pix = i / C;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho), n = (int)(pix / Ho);
+    float acc = 0.0f;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx)
+        acc += (float)x[((size_t)(n * H + ho * k + dy) * W + wo * k + dx) * C + c];
+    y[i] = acc * inv;
+  }
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr_t, float b1, float b2, float eps) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -615,6 +637,15 @@ int y2_maxpool2x2_bf16(const void* x, void* y, int N, int H, int W, int C, y2_st
   Y2_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
   size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
   maxpool2x2_bf16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, N, H, W, C / 8);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_avgpool(const void* x, int x_dtype, float* y, int N, int H, int W, int C, int k, y2_stream_t stream) {
+  Y2_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && k > 0 && H % k == 0 && W % k == 0 && (x_dtype == 0 || x_dtype == 1));
+  const size_t total = (size_t)N * (H / k) * (W / k) * C;
+  if (x_dtype == 1) avgpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, N, H, W, C, k);
+  else avgpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, y, N, H, W, C, k);
   Y2_LAUNCHED();
   return Y2_OK;
 }

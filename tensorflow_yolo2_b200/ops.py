@@ -270,6 +270,18 @@ def maxpool2x2_bf16(x, out=None):
     return out
 
 
+def avg_pool(x, k):
+    """[N,H,W,C] bf16 or f32 -> f32 [N,H/k,W/k,C]: k x k / stride k average pool (darknet.py:28-29,116)."""
+    N, H, W, C_ = x.shape
+    assert H % k == 0 and W % k == 0
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    out = torch.empty((N, H // k, W // k, C_), dtype=torch.float32, device=x.device)
+    check(_lib.load().y2_avgpool(_p(x), 1 if x.dtype == torch.bfloat16 else 0, _p(out), N, H, W, C_, k, _stream()), 'y2_avgpool')
+    return out
+
+
 # ---- a8 / a' -------------------------------------------------------------------------------
 def decode_ref_v1(net, S, B, C_, thresh=0.5):
     N = net.shape[0]

@@ -113,6 +113,25 @@ def max_pool(x, pool_size, stride):
     return ops.affine_leaky_pool(xf.contiguous(), N, H, W, C, leaky=False, pool=True, out_bf16=out_bf16)
 
 
+def avg_pool(x, pool_size, stride):
+    """darknet.py:28-29: tf.nn.avg_pool(SAME) -- with pool_size == stride on an evenly divisible map, as every use in the
+    reference (the 7x7 global pool, darknet.py:116), SAME and VALID coincide.  Returns float32."""
+    assert pool_size == stride and x.shape[1] % stride == 0 and x.shape[2] % stride == 0
+    return ops.avg_pool(x, pool_size)
+
+
+def fc_layer(x, input_dim, output_dim, flat=False, linear=False):
+    """darknet.py:49-57: x @ W + b (exact fp32 kernel: a 1x1 convolution over a 1x1 map), leaky(0.1) unless linear."""
+    W_fc = weight_variable([input_dim, output_dim])
+    b_fc = bias_variable([output_dim])
+    if flat:
+        x = x.reshape(-1, input_dim)
+    n = x.shape[0]
+    h = ops.conv_fwd_f32(x.float().contiguous().view(n, 1, 1, input_dim), W_fc.view(1, 1, input_dim, output_dim), b_fc)
+    h = h.view(n, output_dim)
+    return h if linear else torch.maximum(alpha * h, h)
+
+
 def conv_layer(x, filter_size, input_chl, output_chl, stride):
     """darknet.py:32-36: conv + bias (fp32)."""
     assert stride == 1
@@ -235,6 +254,21 @@ def darknet19_core(inputs, num_classes=None, is_training=True, global_pool=True,
             else:
                 net = conv_bn_layer(net, k, cin, cout, 1, is_training, _pool=pool)
     return (net, pt) if return_passthrough else net
+
+
+def darknet19(inputs, num_classes=None, is_training=True, global_pool=True, output_stride=None, reuse=None,
+              scope='darknet19'):
+    """darknet.py:61-123, the ImageNet classifier: the 18 core layers, a 19th conv_bn_layer (1x1, 1024 -> 1000) in the SAME
+    variable scope (so its variables continue the core's numbering: Variable_36/37, batch_normalization_18), the 7x7 average
+    pool (darknet.py:116) and the reshape to [N, 1000].  224x224 input only, like the reference (7x7 final map)."""
+    net = inputs
+    with _variable_scope(scope, reuse=reuse):
+        for (k, cin, cout, pool) in CORE_PLAN:
+            net = conv_bn_layer(net, k, cin, cout, 1, is_training, _pool=pool)
+        net = conv_bn_layer(net, 1, 1024, 1000, 1, is_training)
+        assert net.shape[1] == 7 and net.shape[2] == 7, 'darknet19 classifier expects a 224x224 input (darknet.py:116)'
+        logits = avg_pool(net, 7, 7).reshape(-1, 1000)
+    return logits
 
 
 def darknet19_detection(net, output_filter, is_training=True, scope='darknet19_detection', reuse=None,

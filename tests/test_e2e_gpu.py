@@ -89,6 +89,46 @@ def test_builders_bf16_vs_oracle(fresh, tame):
     assert e_out < 5e-2
 
 
+# ---- darknet19 ImageNet classifier (darknet.py:61-123): core + 1x1 -> 1000 + 7x7 average pool -----------------------
+@pytest.mark.parametrize('mode,training', [('fp32', False), ('bf16', False), ('bf16', True)])
+def test_darknet19_classifier_vs_oracle(fresh, mode, training):
+    """SURVEY 8(f) rank 4 (parity unpinned: the reference ships no fixture for it; oracle = the restatement).  The 19th
+    layer's variables continue the core's numbering inside the one 'darknet19' scope, like the reference's graph."""
+    from tensorflow_yolo2_b200 import variables
+    from tensorflow_yolo2_b200.yolo2_nets.darknet import darknet19
+    fresh.COMPUTE = mode
+    st, layers = make_store(125, tame=True)
+    core_p, _ = oracle_params(st, layers)
+    rs = np.random.RandomState(11)
+    cls = dict(W=torch.tensor((rs.randn(1, 1, 1024, 1000) * np.sqrt(2.0 / 1024)).astype(np.float32)),
+               b=torch.tensor((rs.randn(1000) * 0.1).astype(np.float32)),
+               gamma=torch.tensor(rs.uniform(0.5, 1.5, 1000).astype(np.float32)), beta=torch.tensor((rs.randn(1000) * 0.2).astype(np.float32)),
+               mm=torch.tensor((rs.randn(1000) * 0.2).astype(np.float32)), mv=torch.tensor(rs.uniform(0.5, 2.0, 1000).astype(np.float32)))
+    # a fresh store holding the core variables; the 19th layer's are created by the builder, then overwritten
+    variables.reset_default_store(seed=0)
+    store = variables.default_store()
+    x = rs.uniform(-1, 1, (2, 224, 224, 3)).astype(np.float32)
+    darknet19(torch.tensor(x).cuda(), is_training=training)                 # creates darknet19/Variable .. Variable_37
+    names = store.names()
+    assert 'darknet19/Variable_36' in names and 'darknet19/Variable_37' in names
+    assert 'darknet19/batch_normalization_18/gamma' in names
+    for L in [l for l in layers if not l['head']]:
+        for k in [L['W'], L['b']] + list(L['bn'].values()):
+            store[k] = st[k]
+    store['darknet19/Variable_36'], store['darknet19/Variable_37'] = cls['W'].numpy(), cls['b'].numpy()
+    bn = 'darknet19/batch_normalization_18/'
+    store[bn + 'gamma'], store[bn + 'beta'] = cls['gamma'].numpy(), cls['beta'].numpy()
+    store[bn + 'moving_mean'], store[bn + 'moving_variance'] = cls['mm'].numpy(), cls['mv'].numpy()
+    logits = darknet19(torch.tensor(x).cuda(), is_training=training, reuse=True)
+    assert logits.shape == (2, 1000) and logits.dtype == torch.float32
+    want = O.darknet19_classifier_forward(torch.tensor(x), core_p, cls, training=training, dtype=torch.float64,
+                                          bf16_operands=(mode == 'bf16')).numpy()
+    e = rel_l2(logits.cpu().numpy(), want)
+    print('darknet19 classifier %s training=%s: rel_l2=%.3g' % (mode, training, e))
+    assert e < (1e-5 if mode == 'fp32' else 2e-2)
+    fresh.COMPUTE = 'bf16'
+
+
 # ---- engine == builders, decode + NMS on top ----------------------------------------------------
 def test_engine_matches_builders_and_oracle_detections(fresh):
     from tensorflow_yolo2_b200.engine import Yolo2Engine

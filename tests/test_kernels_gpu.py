@@ -109,6 +109,29 @@ def test_conv_halo_pair_vs_single_cta_and_oracle(ops, monkeypatch, N, H, W, Cin,
     assert np.linalg.norm(g - want) / np.linalg.norm(want) < 4e-3
 
 
+@pytest.mark.parametrize('N,S,Cin,Cout,k,pool,out_f32', [(5, 26, 256, 512, 3, True, False),     # tiled boxes + fused pool, 256-wide, streamed B
+                                                         (7, 13, 1024, 512, 1, False, False),   # 1x1, 10 tiles of 128 rows -> 5 pairs, 2 N tiles
+                                                         (3, 13, 512, 256, 1, False, False),    # 1x1 with a resident half bank, 4 tiles
+                                                         (3, 13, 1024, 125, 1, False, True)])   # detection layer: 125 -> 128 columns, float32 rows
+def test_conv_generic_pair_vs_single_cta(ops, monkeypatch, N, S, Cin, Cout, k, pool, out_f32):
+    """im2col / tiled-box layers as CTA pairs == the single-CTA kernel, bit for bit (odd tile counts, ragged last tile)."""
+    rs = np.random.RandomState(S + Cout + k)
+    xb = cu(rs.randn(N, S, S, Cin).astype(np.float32), torch.bfloat16)
+    wp = ops.pack_weights_bf16(cu((rs.randn(k, k, Cin, Cout) * 0.05).astype(np.float32)))
+    sc = cu((rs.uniform(0.5, 1.5, Cout) * np.where(rs.rand(Cout) < 0.3, -1, 1)).astype(np.float32))
+    ld = (Cout + 31) // 32 * 32
+    kw = dict(scale=None if out_f32 else sc, shift=cu(rs.randn(Cout).astype(np.float32)), leaky=not out_f32, pool=pool,
+              out_f32=out_f32, ldy=ld if out_f32 else None)
+    monkeypatch.setenv('Y2_CONV_NO_STREAMK', '1')
+    got = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw)
+    monkeypatch.setenv('Y2_CONV_NO_CTA2', '1')
+    ref = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw)
+    torch.cuda.synchronize()
+    g, r = got.reshape(-1, got.shape[-1])[:, :Cout], ref.reshape(-1, ref.shape[-1])[:, :Cout]
+    assert torch.equal(g, r)
+    assert float(g.float().abs().sum()) > 0
+
+
 # ---------------------------------------------------------------------------------- a1 stream-K 256x256 path
 @pytest.mark.parametrize('N,S,Cin,Cout,k,out_f32', [(16, 13, 512, 512, 3, True), (9, 13, 1024, 256, 3, False),
                                                     (6, 19, 1024, 256, 3, True), (8, 26, 256, 512, 3, False),

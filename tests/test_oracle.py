@@ -186,3 +186,12 @@ def test_space_to_depth_matches_definition():
                     for dj in range(2):
                         for c in range(3):
                             assert y[n, i, j, (di * 2 + dj) * 3 + c] == x[n, 2 * i + di, 2 * j + dj, c]
+
+
+def test_avg_pool_and_classifier_shapes():
+    """darknet.py:28-29,116: k x k / stride k average pool; classifier forward returns [N, 1000] logits."""
+    x = torch.arange(2 * 4 * 4 * 3, dtype=torch.float64).reshape(2, 4, 4, 3)
+    y = O.avg_pool_kxk(x, 2)
+    assert y.shape == (2, 2, 2, 3)
+    np.testing.assert_allclose(y[0, 0, 0].numpy(), x[0, :2, :2].reshape(4, 3).mean(0).numpy())
+    np.testing.assert_allclose(O.avg_pool_kxk(x, 4)[1, 0, 0].numpy(), x[1].reshape(16, 3).mean(0).numpy())
