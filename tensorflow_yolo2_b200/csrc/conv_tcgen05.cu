@@ -56,6 +56,8 @@ struct ConvArgs {
   int b_stationary;       // whole B operand resident in smem for the CTA's lifetime (n_tiles == 1, small B)
   uint32_t b_total_bytes;
   int sps;                // (tap, channel-chunk) sub-blocks per pipeline stage
+  int tma_store;          // mode 2, un-pooled bf16 output: rows leave through swizzled smem and TMA box stores
+  uint32_t stg_offset;    // byte offset of the store staging area (4 groups x 2 x 8 KB) from the aligned smem base
   int cta2;               // mode 2, stationary B: CTA pair, tcgen05 cta_group::2 MMAs (M = 256, each CTA holds half of the filters)
   int kw_merge;           // mode 2: the three horizontally shifted patches share one stage (stationary B, one chunk)
   int stages_per_tile;    // kblocks / sps
@@ -285,9 +287,12 @@ __device__ __forceinline__ void epilogue_chunk_pooled_bf16(const ConvArgs& a, co
 // KIND: 0 = first layer (Cin 3 -> 8, un-swizzled 16-byte rows), 1 = 64-byte rows (Cin 32), 2 = 128-byte rows
 // CTA2: CTA-pair variant (tcgen05 cta_group::2).  A template parameter, not a run-time flag: a kernel that merely CONTAINS
 // cta_group::2 instructions can only be launched with an even cluster size (launch error "cluster misconfiguration").
-template <int BLOCK_N, int A_MODE, int KIND, bool CTA2 = false>
+// TMAST: TMA-store epilogue (un-pooled bf16 rows through swizzled smem) -- a separate instantiation, so that its registers do
+// not weigh on the other epilogues (as a run-time branch it pushed them from 24 to 100 bytes of spills under the 96-register cap).
+template <int BLOCK_N, int A_MODE, int KIND, bool CTA2 = false, bool TMAST = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmY, const ConvArgs a) {
   constexpr bool FIRST = KIND == 0;
   constexpr uint32_t ROW_BYTES = KIND == 0 ? 16u : (KIND == 1 ? 64u : 128u);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -684,6 +689,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool r_even = ((r_tw | r_th) & 1) == 0;
     const int Ho = pool ? a.H >> 1 : a.H, Wo = pool ? a.W >> 1 : a.W;
     int staged_ntile = -1;
+    // TMA-store epilogue (mode 2, un-pooled bf16): the group's 128 rows x 32 channels of a chunk are staged in 64B-swizzled
+    // smem and leave as ONE box store.  The direct path issues four 16-byte stores per lane, each touching 32 different
+    // lines: ncu (layer 3 vs the pooled layer 5, identical MMA work) showed the LSU/MIO pipe congested by them -- LDS of
+    // scale/shift stalling (short scoreboard), the MMA warp's own LDS delayed, tensor pipe 48 % vs 71 %.
+    constexpr bool tma_store = TMAST;
+    static_assert(!TMAST || (A_MODE == 2 && !FIRST), "TMA-store epilogue: halo-patch mode only");
+    const uint32_t stg_group = smem_b_stat + a.stg_offset + (uint32_t)gi * 16384u;
+    uint32_t nstore = 0;
     for (int it = tp;; it += TP) {
       const int tile = sched_first + it * sched_step;
       if (tile >= total_tiles) break;
@@ -737,13 +750,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         const int c0 = nbase + cc;
-        if (A_MODE != 0 && pool && !out_f32 && c0 + 32 <= a.Cout && (a.ldy & 7) == 0) {
+        if constexpr (tma_store) {
+          const uint32_t stg = stg_group + (nstore & 1u) * 8192u;
+          if (r == 0) bulk_wait_group_read<1>();              // the store that last used this buffer has read it
+          asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
+          // row r = h * 8 + w of the box, 64 B per row; 16-byte unit j (8 channels) at j ^ ((r >> 1) & 3)  (SWIZZLE_64B);
+          // one unit at a time: affine + leaky + pack + store, so that only the 32 accumulators stay live
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = 8 * j + 4 * h;
+              const float4 sc = *reinterpret_cast<const float4*>(&my_scale[cc + i]);
+              const float4 sh = *reinterpret_cast<const float4*>(&my_shift[cc + i]);
+              float f0 = fmaf(__uint_as_float(v[i + 0]), sc.x, sh.x), f1 = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
+              float f2 = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z), f3 = fmaf(__uint_as_float(v[i + 3]), sc.w, sh.w);
+              if (leaky_on) {
+                f0 = fmaxf(f0, a.alpha * f0); f1 = fmaxf(f1, a.alpha * f1);
+                f2 = fmaxf(f2, a.alpha * f2); f3 = fmaxf(f3, a.alpha * f3);
+              }
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(f0, f1), h1 = __floats2bfloat162_rn(f2, f3);
+              pk[2 * h] = *reinterpret_cast<const uint32_t*>(&h0);
+              pk[2 * h + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4)),
+                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
+          if (r == 0) {
+            tma_store_4d(&tmY, stg, c0, t.w0, t.h0, t.n0);     // rows / pixels outside the tensor are clipped by the TMA unit
+            bulk_commit_group();
+          }
+          ++nstore;
+        } else if (A_MODE != 0 && pool && !out_f32 && c0 + 32 <= a.Cout && (a.ldy & 7) == 0) {
           epilogue_chunk_pooled_bf16(a, v, my_scale, my_shift, cc, c0, valid_px, orow, leaky_on, lane);
         } else if (c0 < a.ldy) {
           epilogue_chunk<32>(a, v, my_scale, my_shift, cc, c0, valid, orow, pool, leaky_on, out_f32);
         }
         __syncwarp();                               // reconverge before the next .sync.aligned TMEM load
       }
+    }
+    if constexpr (tma_store) {
+      if (r == 0) bulk_wait_group_read<0>();             // smem must outlive the last box stores' reads
     }
   }
 
@@ -810,9 +861,9 @@ static void choose_box(int N, int H, int W, bool pool, int* tw, int* th, int* nb
   *tw = btw; *th = bth; *nb = bnb;
 }
 
-template <int BLOCK_N, int A_MODE, int KIND, bool CTA2 = false>
-static int launch_conv3(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, size_t smem, cudaStream_t st) {
-  Y2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, A_MODE, KIND, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int BLOCK_N, int A_MODE, int KIND, bool CTA2 = false, bool TMAST = false>
+static int launch_conv3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const ConvArgs& a, size_t smem, cudaStream_t st) {
+  Y2_CUDA(cudaFuncSetAttribute((conv_tc_kernel<BLOCK_N, A_MODE, KIND, CTA2, TMAST>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
   const int CS = a.cluster;
   long long units = (long long)((a.m_tiles + CS - 1) / CS) * a.n_tiles;
@@ -828,42 +879,45 @@ static int launch_conv3(const CUtensorMap& tmA, const CUtensorMap& tmB, const Co
   cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
   cfg.numAttrs = fill_launch_attrs(attr, (unsigned)CS);
-  Y2_CUDA(cudaLaunchKernelEx(&cfg, (conv_tc_kernel<BLOCK_N, A_MODE, KIND, CTA2>), tmA, tmB, a));
+  Y2_CUDA(cudaLaunchKernelEx(&cfg, (conv_tc_kernel<BLOCK_N, A_MODE, KIND, CTA2, TMAST>), tmA, tmB, tmY, a));
   Y2_LAUNCHED();
   return Y2_OK;
 }
 
 template <int BLOCK_N, int KIND>
-static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, size_t smem, cudaStream_t st) {
+static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const ConvArgs& a, size_t smem, cudaStream_t st) {
   if constexpr (KIND == 2 && BLOCK_N >= 128) {
-    if (a.cta2 && a.a_mode == 0) return launch_conv3<BLOCK_N, 0, KIND, true>(tmA, tmB, a, smem, st);
-    if (a.cta2 && a.a_mode == 1) return launch_conv3<BLOCK_N, 1, KIND, true>(tmA, tmB, a, smem, st);
+    if (a.cta2 && a.a_mode == 0) return launch_conv3<BLOCK_N, 0, KIND, true>(tmA, tmB, tmY, a, smem, st);
+    if (a.cta2 && a.a_mode == 1) return launch_conv3<BLOCK_N, 1, KIND, true>(tmA, tmB, tmY, a, smem, st);
   }
   switch (a.a_mode) {
-    case 0: return launch_conv3<BLOCK_N, 0, KIND>(tmA, tmB, a, smem, st);
-    case 1: return launch_conv3<BLOCK_N, 1, KIND>(tmA, tmB, a, smem, st);
+    case 0: return launch_conv3<BLOCK_N, 0, KIND>(tmA, tmB, tmY, a, smem, st);
+    case 1: return launch_conv3<BLOCK_N, 1, KIND>(tmA, tmB, tmY, a, smem, st);
     default:
       if constexpr (KIND != 0 && BLOCK_N <= 128) {
-        if (a.cta2) return launch_conv3<BLOCK_N, 2, KIND, true>(tmA, tmB, a, smem, st);
+        if constexpr (KIND == 2 && BLOCK_N == 128) {
+          if (a.cta2 && a.tma_store) return launch_conv3<BLOCK_N, 2, KIND, true, true>(tmA, tmB, tmY, a, smem, st);
+        }
+        if (a.cta2) return launch_conv3<BLOCK_N, 2, KIND, true>(tmA, tmB, tmY, a, smem, st);
       }
-      return launch_conv3<BLOCK_N, 2, KIND>(tmA, tmB, a, smem, st);
+      return launch_conv3<BLOCK_N, 2, KIND>(tmA, tmB, tmY, a, smem, st);
   }
 }
 
-static int launch_conv(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, size_t smem,
-                       cudaStream_t st) {
-  if (a.first_layer) return launch_conv2<32, 0>(tmA, tmB, a, smem, st);
+static int launch_conv(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const ConvArgs& a,
+                       size_t smem, cudaStream_t st) {
+  if (a.first_layer) return launch_conv2<32, 0>(tmA, tmB, tmY, a, smem, st);
   if (a.row_bytes == 64) {
     switch (block_n) {
-      case 64: return launch_conv2<64, 1>(tmA, tmB, a, smem, st);
-      case 128: return launch_conv2<128, 1>(tmA, tmB, a, smem, st);
-      default: return launch_conv2<256, 1>(tmA, tmB, a, smem, st);
+      case 64: return launch_conv2<64, 1>(tmA, tmB, tmY, a, smem, st);
+      case 128: return launch_conv2<128, 1>(tmA, tmB, tmY, a, smem, st);
+      default: return launch_conv2<256, 1>(tmA, tmB, tmY, a, smem, st);
     }
   }
   switch (block_n) {
-    case 64: return launch_conv2<64, 2>(tmA, tmB, a, smem, st);
-    case 128: return launch_conv2<128, 2>(tmA, tmB, a, smem, st);
-    default: return launch_conv2<256, 2>(tmA, tmB, a, smem, st);
+    case 64: return launch_conv2<64, 2>(tmA, tmB, tmY, a, smem, st);
+    case 128: return launch_conv2<128, 2>(tmA, tmB, tmY, a, smem, st);
+    default: return launch_conv2<256, 2>(tmA, tmB, tmY, a, smem, st);
   }
 }
 
@@ -1055,14 +1109,26 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   uint32_t stage_bytes = a.a_stage_bytes + (a.b_stationary ? 0u : a.b_stage_bytes);
   Y2_ARG(a.first_layer || (a.a_stage_bytes % 1024 == 0 && a.b_stage_bytes % 1024 == 0));
   const size_t b_region = a.b_stationary ? (((size_t)a.b_total_bytes + 1023) & ~(size_t)1023) : 0;
-  int stages = (int)((SMEM_BUDGET - b_region) / stage_bytes);
+  // TMA-store epilogue for the un-pooled 128-channel bf16 output of the halo-patch pair kernel (layer 3): 4 groups x 2 x 8 KB
+  // of staging.  (Measured: layer 3 119 -> 100 us; the 64-channel layer 4 got slower -- two chunks per tile do not amortise
+  // the per-chunk group barriers and the ring loses four stages -- so it keeps the direct stores.)
+  const size_t STG_BYTES = 4 * 2 * 8192;
+  a.tma_store = 0;
+  if (a.a_mode == 2 && !a.first_layer && !pool && !out_f32 && p->Cout % 32 == 0 && a.ldy % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(p->y) & 15) == 0 && EPI_GROUPS == 4 && block_n == 128 && a.row_bytes == 128 && a.cta2 &&
+      b_region + 3 * (size_t)stage_bytes + STG_BYTES <= SMEM_BUDGET && !getenv("Y2_CONV_NO_TMA_STORE") &&
+      getenv("Y2_CONV_TMA_STORE"))    // TODO(default on once the templated variant has passed on the GPU)
+    a.tma_store = 1;
+  const size_t stg_bytes = a.tma_store ? STG_BYTES : 0;
+  int stages = (int)((SMEM_BUDGET - b_region - stg_bytes) / stage_bytes);
   if (stages > 12) stages = 12;
   if (stages < 2) {
     set_error("y2_conv_fwd_bf16: tile configuration needs %u B per stage; fewer than 2 stages fit", stage_bytes);
     return Y2_ERR_UNSUPPORTED;
   }
   a.stages = stages;
-  size_t smem = b_region + (size_t)stages * stage_bytes + 1024;
+  a.stg_offset = (uint32_t)(b_region + (size_t)stages * stage_bytes);
+  size_t smem = b_region + (size_t)stages * stage_bytes + stg_bytes + 1024;
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB;
@@ -1140,7 +1206,23 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
       return Y2_ERR_DRIVER;
     }
   }
+  CUtensorMap tmY;
+  memset(&tmY, 0, sizeof(tmY));
+  if (a.tma_store) {
+    // output [N, H, W, Cout] with row stride ldy: boxes of 32 channels x the 8 x 16 pixel tile, 64-byte swizzled rows
+    cuuint64_t dims[4] = {(cuuint64_t)p->Cout, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t strides[3] = {(cuuint64_t)a.ldy * 2, (cuuint64_t)p->W * a.ldy * 2, (cuuint64_t)p->H * p->W * a.ldy * 2};
+    cuuint32_t box[4] = {32, 8, 16, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encodeTiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p->y, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("y2_conv_fwd_bf16: tensor map Y encode failed (CUresult %d)", (int)r);
+      return Y2_ERR_DRIVER;
+    }
+  }
   (void)out_f32;
   cudaStream_t st = (cudaStream_t)stream;
-  return launch_conv(block_n, tmA, tmB, a, smem, st);
+  return launch_conv(block_n, tmA, tmB, tmY, a, smem, st);
 }
