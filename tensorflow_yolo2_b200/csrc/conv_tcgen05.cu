@@ -1110,14 +1110,13 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   Y2_ARG(a.first_layer || (a.a_stage_bytes % 1024 == 0 && a.b_stage_bytes % 1024 == 0));
   const size_t b_region = a.b_stationary ? (((size_t)a.b_total_bytes + 1023) & ~(size_t)1023) : 0;
   // TMA-store epilogue for the un-pooled 128-channel bf16 output of the halo-patch pair kernel (layer 3): 4 groups x 2 x 8 KB
-  // of staging.  (Measured: layer 3 119 -> 100 us; the 64-channel layer 4 got slower -- two chunks per tile do not amortise
+  // of staging.  (Measured: layer 3 108 -> 93 us; the 64-channel layer 4 got slower -- two chunks per tile do not amortise
   // the per-chunk group barriers and the ring loses four stages -- so it keeps the direct stores.)
   const size_t STG_BYTES = 4 * 2 * 8192;
   a.tma_store = 0;
   if (a.a_mode == 2 && !a.first_layer && !pool && !out_f32 && p->Cout % 32 == 0 && a.ldy % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(p->y) & 15) == 0 && EPI_GROUPS == 4 && block_n == 128 && a.row_bytes == 128 && a.cta2 &&
-      b_region + 3 * (size_t)stage_bytes + STG_BYTES <= SMEM_BUDGET && !getenv("Y2_CONV_NO_TMA_STORE") &&
-      getenv("Y2_CONV_TMA_STORE"))    // TODO(default on once the templated variant has passed on the GPU)
+      b_region + 3 * (size_t)stage_bytes + STG_BYTES <= SMEM_BUDGET && !getenv("Y2_CONV_NO_TMA_STORE"))
     a.tma_store = 1;
   const size_t stg_bytes = a.tma_store ? STG_BYTES : 0;
   int stages = (int)((SMEM_BUDGET - b_region - stg_bytes) / stage_bytes);
