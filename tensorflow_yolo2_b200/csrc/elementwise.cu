@@ -346,6 +346,57 @@ __global__ void __launch_bounds__(256) affine_leaky_rows_bf16_kernel(const float
   }
 }
 
+// ... and with the 2x2 max-pool (training forward of the pooled layers: conv -> batch-stat BN -> leaky -> pool): a thread owns
+// 8 channels and walks POOLED pixels; eight 16-byte loads in flight per pooled pixel, 32-bit index arithmetic.
+__global__ void __launch_bounds__(256) affine_leaky_pool_rows_bf16_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ sub,
+                                                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                          float alpha, int leaky_on, __nv_bfloat16* __restrict__ out,
+                                                                          int ldo, int H, int W, unsigned units, int C8) {
+  const int cx = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cx >= C8) return;
+  const int c0 = cx * 8;
+  float sb[8], sc[8], sh[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    sb[v] = sub ? sub[c0 + v] : 0.0f;
+    sc[v] = scale ? scale[c0 + v] : 1.0f;
+    sh[v] = shift ? shift[c0 + v] : 0.0f;
+  }
+  const unsigned Wo = (unsigned)W >> 1, Ho = (unsigned)H >> 1;
+  const unsigned ustep = gridDim.x * blockDim.y;
+  for (unsigned u = blockIdx.x * blockDim.y + threadIdx.y; u < units; u += ustep) {
+    const unsigned wo = u % Wo, t = u / Wo, ho = t % Ho, n = t / Ho;
+    const size_t base = ((size_t)n * H + 2 * ho) * (size_t)W + 2 * wo;
+    const size_t rows[4] = {base, base + 1, base + W, base + W + 1};
+    float4 a[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4* px = reinterpret_cast<const float4*>(x + rows[k] * ldx + c0);
+      a[k] = __ldcs(px);
+      b[k] = __ldcs(px + 1);
+    }
+    float r[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) r[v] = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float tt[8] = {a[k].x, a[k].y, a[k].z, a[k].w, b[k].x, b[k].y, b[k].z, b[k].w};
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        float y = (tt[v] - sb[v]) * sc[v] + sh[v];               // same expression as the generic kernel
+        if (leaky_on) y = leaky(y, alpha);
+        r[v] = fmaxf(r[v], y);
+      }
+    }
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(r[0], r[1]), h1 = __floats2bfloat162_rn(r[2], r[3]);
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(r[4], r[5]), h3 = __floats2bfloat162_rn(r[6], r[7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+    pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(out + (size_t)u * ldo + c0) = pk;
+  }
+}
+
 // Same idea for the float32 output of the detection layer (C = 125, rows padded to 128 in, dense out): one thread per
 // channel holds its constants and walks rows; loads and stores are coalesced along the channels.  (The generic kernel
 // took 15 us for 5.6 MB.)
@@ -593,6 +644,21 @@ int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const flo
     if (gx < 1) gx = 1;
     affine_leaky_rows_bf16_kernel<<<dim3(gx, (C8 + bx - 1) / bx), dim3(bx, by), 0, st>>>(
         x, ldx, sub, scale, shift, alpha, leaky_on, reinterpret_cast<__nv_bfloat16*>(out), ldo, M, C8);
+    Y2_LAUNCHED();
+    return Y2_OK;
+  }
+  if (pool && !space_to_depth && out_dtype == 1 && C % 8 == 0 && ldx % 4 == 0 && ldo % 8 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0 &&
+      (long long)N * H * W < (1ll << 31) && !getenv("Y2_AFFINE_GENERIC")) {
+    const unsigned units = (unsigned)((long long)N * Ho * Wo);
+    const int C8 = C / 8;
+    const int bx = C8 >= 32 ? 32 : (C8 >= 16 ? 16 : (C8 >= 8 ? 8 : 4));
+    const int by = 256 / bx;
+    long long gx = (long long)g_sms_elementwise() * 16 / ((C8 + bx - 1) / bx);
+    const long long need = ((long long)units + by - 1) / by;
+    if (gx > need) gx = need;
+    if (gx < 1) gx = 1;
+    affine_leaky_pool_rows_bf16_kernel<<<dim3((unsigned)gx, (unsigned)((C8 + bx - 1) / bx)), dim3(bx, by), 0, st>>>(
+        x, ldx, sub, scale, shift, alpha, leaky_on, reinterpret_cast<__nv_bfloat16*>(out), ldo, H, W, units, C8);
     Y2_LAUNCHED();
     return Y2_OK;
   }

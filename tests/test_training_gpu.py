@@ -272,3 +272,35 @@ def test_ddp_two_gpus_matches_mean_of_shard_gradients():
                        capture_output=True, text=True, timeout=600, cwd=root)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and 'OK' in r.stdout
+
+
+@pytest.mark.parametrize('pool,dy_bf16,C,ld', [(True, True, 64, 64), (False, False, 128, 128), (True, False, 32, 64), (False, True, 96, 128)])
+def test_bn_bwd_apply_rows_equals_generic(ops, monkeypatch, pool, dy_bf16, C, ld):
+    """The row-walking bn_bwd apply kernel == the generic one, bit for bit (incl. zero padding columns), and so is the
+    pooled row-walking forward affine."""
+    import torch
+    rs = np.random.RandomState(C + ld)
+    N, H, W = 2, 12, 10
+    M = N * H * W
+    cu = lambda a, dt=None: torch.tensor(a).cuda() if dt is None else torch.tensor(a).cuda().to(dt)
+    h = cu((rs.randn(M, ld) * 2).astype(np.float32))
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    dy = cu(rs.randn(N, Ho, Wo, C).astype(np.float32), torch.bfloat16 if dy_bf16 else None)
+    mean, var = ops.bn_stats(h, C, ld=ld)
+    gamma, beta = cu(rs.uniform(0.5, 1.5, C).astype(np.float32)), cu(rs.randn(C).astype(np.float32))
+    outs = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv('Y2_BN_BWD_GENERIC', '1')
+            monkeypatch.setenv('Y2_AFFINE_GENERIC', '1')
+        dg, db, dh = ops.bn_leaky_pool_bwd(h, dy, mean, var, gamma, beta, N, H, W, C, ldh=ld, leaky=True, pool=pool, ld_dh=ld)
+        fwd = None
+        if C % 8 == 0:
+            fwd = ops.affine_leaky_pool(h, N, H, W, C, ldx=ld, sub=mean, scale=gamma, shift=beta, leaky=True, pool=pool, out_bf16=True)
+        outs.append((dg.clone(), db.clone(), dh.clone(), fwd))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2].float() + 0.0, outs[1][2].float() + 0.0)          # (+0.0: -0 == 0 in the padding columns)
+    assert float(outs[0][2].float().abs().sum()) > 0
+    if outs[0][3] is not None:
+        assert torch.equal(outs[0][3], outs[1][3])
