@@ -15,9 +15,15 @@ value      device-timed throughput with the batch already resident in HBM (CUDA 
 e2e        same metric through Yolo2Engine.submit(): pinned host uint8 batch -> H2D -> step -> D2H of
            the detections, every copy inside the timed region (the H2D of batch i+1 runs on a copy
            stream and overlaps the kernels of batch i, as a serving loop would).
-roofline   tensor-core bound: algorithmic conv FLOPs of one step / summed conv-kernel time per step,
-           measured live with CUDA events around each conv launch, vs MEASURED_PEAKS.json.
+roofline   tensor-core bound: algorithmic conv FLOPs of one step / conv time per step vs MEASURED_PEAKS.json.
+           Conv time = min(sum of CUDA events around each of the 22 conv launches in an eager replay, the whole
+           device-timed graph step): eager launches leave idle gaps that the events count, and the convs cannot take
+           longer than the step that contains them (roofline.conv_ms_source names the bound used).  roofline.traffic =
+           DRAM bytes of those launches from the committed ncu launch list (profiles/*_traffic.json).
 cpu_baseline  the oracle (CPU restatement of the reference, PyTorch-CPU fp32) on a bounded sample.
+
+    --image-size 608 --batch 32    BASELINE.json configs[3] (19x19 grid) instead of the headline 416 / 64
+    --no-graph                     eager launches (for ncu launch lists);  --no-cpu-baseline skips the CPU leg
 """
 import argparse
 import json
