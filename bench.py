@@ -71,8 +71,8 @@ def make_config(world, extra=None):
 
 def load_traffic():
     """DRAM bytes (read + write) of the 22 conv launches of one step, from the committed ncu launch list of this same
-    command (profiles/r1e_traffic.json; ncu numbers are never taken live inside a timed run)."""
-    p = os.path.join(ROOT, 'profiles', 'r1e_traffic.json')
+    command (profiles/r1f_traffic.json; ncu numbers are never taken live inside a timed run)."""
+    p = os.path.join(ROOT, 'profiles', 'r1f_traffic.json')
     try:
         return float(json.load(open(p))['conv_dram_bytes_per_step'])
     except Exception:  # noqa: BLE001
@@ -302,7 +302,7 @@ def run_ours(args):
     achieved = N * flops_img / (conv_total_ms * 1e-3) / 1e12
     roofline = dict(bound='tensor', achieved=achieved, peak=peaks['sustained'], unit='TFLOP/s',
                     frac=achieved / peaks['sustained'], traffic=load_traffic() if IMAGE_SIZE == 416 and N == 64 else None,
-                    algorithmic_bytes=N * (35.0e6 if IMAGE_SIZE == 416 else 35.0e6 * IMAGE_SIZE * IMAGE_SIZE / (416.0 * 416.0)), traffic_source='profiles/r1e_traffic.json (ncu launch list of this command)', peak_source=peaks['which'] + ' sustained bf16',
+                    algorithmic_bytes=N * (35.0e6 if IMAGE_SIZE == 416 else 35.0e6 * IMAGE_SIZE * IMAGE_SIZE / (416.0 * 416.0)), traffic_source='profiles/r1f_traffic.json (ncu launch list of this command)', peak_source=peaks['which'] + ' sustained bf16',
                     kernel='conv_tc_kernel x21 + conv1_u8_pool_kernel (22 conv launches/step)', conv_ms_per_step=conv_total_ms, conv_ms_source=conv_ms_source,
                     per_layer_tflops=[round(N * f / (ms * 1e-3) / 1e12, 1) for f, ms in zip(per_layer, conv_ms)])
 
