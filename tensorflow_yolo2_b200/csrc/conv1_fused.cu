@@ -106,6 +106,7 @@ __device__ __forceinline__ C1Tile c1_tile(const Conv1Args& a, int tile) {
 
 __global__ void __launch_bounds__(C1_THREADS, 1)
 conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args a) {
+  pdl_launch_dependents();   // persistent grid: layer 2 (launched with programmatic serialization) may take SMs as my CTAs retire
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t raw_full[C1_RAW_STAGES], raw_empty[C1_RAW_STAGES];
   __shared__ __align__(8) uint64_t a_full[C1_A_STAGES], a_empty[C1_A_STAGES];
