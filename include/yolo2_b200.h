@@ -72,6 +72,17 @@ int y2_conv_fwd_f32(const float* x, const float* w_hwio, const float* bias, floa
 #define Y2_CONV_LEAKY 1
 #define Y2_CONV_POOL2 2
 #define Y2_CONV_OUT_F32 4
+/* "bf16x3" precision mode (the 1e-3 detections bar of the spec; a single bf16 rounding per operand is ~1e-2 after 22
+ * layers).  Every value v travels as TWO bf16 numbers hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits together) and a
+ * product a*w is evaluated as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo -- three tcgen05.mma per K step into the same fp32
+ * accumulator (the dropped a_lo*w_lo term is 2^-18 relative).
+ *   IN_SPLIT   x is bf16 [N,H,W,2*Cin] = [hi(Cin) | lo(Cin)] per pixel and w_packed comes from
+ *              y2_pack_weights_bf16_split (K per tap = 3*Cin: [w_hi | w_hi | w_lo], meeting x's [hi | lo | hi]).
+ *              Cin must be a multiple of 32.
+ *   OUT_SPLIT  the bf16 output row holds hi at columns [0, Cout) and lo at [lo_off, lo_off + Cout); ldy >= lo_off + Cout
+ *              (lo_off = 0 means Cout: a dense [N,Ho,Wo,2*Cout] tensor).  Ignored with OUT_F32. */
+#define Y2_CONV_IN_SPLIT 8
+#define Y2_CONV_OUT_SPLIT 16
 typedef struct y2_conv_params {
   const void* x;
   const void* w_packed;
@@ -82,11 +93,14 @@ typedef struct y2_conv_params {
   int flags;
   float alpha;
   int ldy;      /* output row stride in elements; 0 -> Cout */
-  int reserved; /* must be 0 */
+  int lo_off;   /* OUT_SPLIT: column of the lo half (0 -> Cout); must be 0 otherwise */
 } y2_conv_params;
 int y2_conv_cin_padded(int Cin);
 size_t y2_conv_packed_weight_elems(int ksize, int Cin, int Cout);
 int y2_pack_weights_bf16(const float* w_hwio, void* w_packed, int ksize, int Cin, int Cout, y2_stream_t stream);
+/* IN_SPLIT operand: [Cout_p][k*k][3*Cin] bf16 = per tap [w_hi | w_hi | w_lo]; y2_conv_packed_weight_split_elems elements. */
+size_t y2_conv_packed_weight_split_elems(int ksize, int Cin, int Cout);
+int y2_pack_weights_bf16_split(const float* w_hwio, void* w_packed, int ksize, int Cin, int Cout, y2_stream_t stream);
 int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream);
 
 /* Scratch for the stream-K variant of y2_conv_fwd_bf16 (256x256 tiles whose K range is split between two CTAs: the
@@ -107,6 +121,13 @@ size_t y2_conv1_u8_packed_weight_elems(void);
 int y2_pack_weights_conv1_u8(const float* w_hwio, const float* scale, void* w_packed, y2_stream_t stream);
 int y2_conv1_u8_pool_fwd(const uint8_t* img, const void* w_packed, const float* shift, void* y, int N, int H, int W,
                          float alpha, y2_stream_t stream);
+/* bf16x3 variant of the same layer: the raw bytes enter the MMA as exact bf16 integers plus a "ones" channel (1 inside
+ * the image, 0 in the SAME-padding halo); x = v*2/255 - 1 is folded into the weights, which are a hi + lo bf16 pair
+ * (2 * y2_conv1_u8_packed_weight_elems() elements from y2_pack_weights_conv1_u8_split).  y bf16 [N,H/2,W/2,64] =
+ * [hi(32) | lo(32)] per pixel (the Y2_CONV_IN_SPLIT input layout of the next layer). */
+int y2_pack_weights_conv1_u8_split(const float* w_hwio, const float* scale, void* w_packed, y2_stream_t stream);
+int y2_conv1_u8_pool_fwd_split(const uint8_t* img, const void* w_packed, const float* shift, void* y, int N, int H, int W,
+                               float alpha, y2_stream_t stream);
 
 /* ---- a2: batch normalisation pieces (darknet.py:42-44, tf.layers.batch_normalization) -------
  * y2_bn_stats: per-channel mean and BIASED variance over the M rows of x [M, ld] (float32),
@@ -140,10 +161,12 @@ int y2_affine_leaky_pool(const float* x, int ldx, const float* sub, const float*
 /* Same, with an output row stride `ldo` (elements; the result may be a channel slice of a wider, concatenated tensor)
  * and, with space_to_depth != 0, the passthrough / reorg layer (absent from the reference) folded
  * into the store address: tf.space_to_depth(block_size=2) semantics, pixel (h, w) -> row (h/2, w/2), channels
- * [((h%2)*2 + (w%2))*C, +C).  `out` then points at the first channel of the slice inside [N, H/2, W/2, ldo]. */
+ * [((h%2)*2 + (w%2))*C, +C).  `out` then points at the first channel of the slice inside [N, H/2, W/2, ldo].
+ * out_dtype 2 = bf16 "hi | lo" pair (the bf16x3 precision mode, see Y2_CONV_IN_SPLIT): hi = bf16(v) at column c and
+ * lo = bf16(v - hi) at column lo_off + c of the same row (lo_off 0 -> C, or ldo/2 with space_to_depth); ldo 0 -> 2*C. */
 int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const float* scale, const float* shift, float alpha,
-                            int leaky, int pool, void* out, int out_dtype, int ldo, int space_to_depth, int N, int H, int W,
-                            int C, y2_stream_t stream);
+                            int leaky, int pool, void* out, int out_dtype, int ldo, int space_to_depth, int lo_off, int N,
+                            int H, int W, int C, y2_stream_t stream);
 /* a3: tf.nn.max_pool 2x2/2 (darknet.py:24-25) on bf16 [N,H,W,C] -> [N,H/2,W/2,C]; C % 8 == 0.  (The pool normally runs
  * in the conv epilogue; this kernel serves the layer whose un-pooled output is also the passthrough source.) */
 int y2_maxpool2x2_bf16(const void* x, void* y, int N, int H, int W, int C, y2_stream_t stream);

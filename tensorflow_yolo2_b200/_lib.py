@@ -8,14 +8,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('Y2_LIB_PATH') or os.path.join(_HERE, 'lib', 'libyolo2_b200.so')   # override: A/B experiments
 
-Y2_CONV_LEAKY, Y2_CONV_POOL2, Y2_CONV_OUT_F32 = 1, 2, 4
+Y2_CONV_LEAKY, Y2_CONV_POOL2, Y2_CONV_OUT_F32, Y2_CONV_IN_SPLIT, Y2_CONV_OUT_SPLIT = 1, 2, 4, 8, 16
 
 
 class ConvParams(C.Structure):
     _fields_ = [('x', C.c_void_p), ('w_packed', C.c_void_p), ('scale', C.c_void_p), ('shift', C.c_void_p),
                 ('y', C.c_void_p), ('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int),
                 ('Cout', C.c_int), ('ksize', C.c_int), ('flags', C.c_int), ('alpha', C.c_float),
-                ('ldy', C.c_int), ('reserved', C.c_int)]
+                ('ldy', C.c_int), ('lo_off', C.c_int)]
 
 
 class Y2Error(RuntimeError):
@@ -33,19 +33,23 @@ _SIGNATURES = {
     'y2_conv_cin_padded': (_i, [_i]),
     'y2_conv_packed_weight_elems': (_sz, [_i, _i, _i]),
     'y2_pack_weights_bf16': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'y2_conv_packed_weight_split_elems': (_sz, [_i, _i, _i]),
+    'y2_pack_weights_bf16_split': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'y2_conv_fwd_bf16': (_i, [C.POINTER(ConvParams), _vp]),
     'y2_conv_workspace_bytes': (_sz, []),
     'y2_conv_set_workspace': (_i, [_vp, _sz]),
     'y2_conv1_u8_packed_weight_elems': (_sz, []),
     'y2_pack_weights_conv1_u8': (_i, [_vp, _vp, _vp, _vp]),
     'y2_conv1_u8_pool_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    'y2_pack_weights_conv1_u8_split': (_i, [_vp, _vp, _vp, _vp]),
+    'y2_conv1_u8_pool_fwd_split': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     'y2_bn_stats_workspace_bytes': (_sz, [_i, _i]),
     'y2_bn_stats': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'y2_bn_stats_fold': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
     'y2_bn_fold': (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),
     'y2_bn_update_moving': (_i, [_vp, _vp, _vp, _vp, _f, _i, _vp]),
     'y2_affine_leaky_pool': (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
-    'y2_affine_leaky_pool_ex': (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'y2_affine_leaky_pool_ex': (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'y2_maxpool2x2_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'y2_avgpool': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     'y2_decode_ref_v1': (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),

@@ -65,6 +65,12 @@ static_assert(C1_A_STAGES % C1_MMA_WARPS == 0 && C1_RAW_STAGES % C1_CVT_WARPS ==
               "stage -> warp ownership must be static");
 constexpr int C1_TASKS = C1_PROWS * (C1_PCOLS / 2);     // 16-byte (two-pixel) units per patch
 constexpr size_t C1_SMEM = 1024 + C1_B_BYTES + C1_A_STAGES * C1_A_STAGE + C1_RAW_STAGES * C1_RAW_STAGE;
+// bf16x3 variant (SPLIT): the patch holds the raw bytes as EXACT bf16 integers (v0, v1, v2) plus a "ones" channel that is
+// 1 inside the image and 0 in the SAME-padding halo; the preprocessing x = v*2/255 - 1 is folded into the weights
+// (w*2/255 on the colour channels, -sum_c w on the ones channel), which are kept as a hi + lo bf16 pair.  So A is exact,
+// B carries 16 mantissa bits, and a tile costs 8 MMAs (4 footprint rows x {hi, lo}) into the same accumulator.  The output
+// row is [hi(32) | lo(32)] (Y2_CONV_OUT_SPLIT layout).
+constexpr size_t C1_SMEM_SPLIT = C1_SMEM + C1_B_BYTES;
 
 struct Conv1Args {
   const uint4* w_packed;
@@ -82,6 +88,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr)
                : "memory");
+}
+
+// two bytes -> two bf16 holding the byte values exactly, packed (first byte in the low half)
+__device__ __forceinline__ uint32_t c1_cvt2_int(uint32_t b0, uint32_t b1) {
+  __nv_bfloat162 h = __floats2bfloat162_rn((float)b0, (float)b1);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // two bytes -> two bf16 of (v/255)*2-1, packed (first byte in the low half)
@@ -104,8 +116,10 @@ __device__ __forceinline__ C1Tile c1_tile(const Conv1Args& a, int tile) {
   return t;
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(C1_THREADS, 1)
 conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args a) {
+  constexpr int B_BYTES = SPLIT ? 2 * C1_B_BYTES : C1_B_BYTES;
   pdl_launch_dependents();   // persistent grid: layer 2 (launched with programmatic serialization) may take SMs as my CTAs retire
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t raw_full[C1_RAW_STAGES], raw_empty[C1_RAW_STAGES];
@@ -117,13 +131,13 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sm0 = (smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t sB = sm0;
-  const uint32_t sA = sB + C1_B_BYTES;
+  const uint32_t sA = sB + B_BYTES;
   const uint32_t sRaw = sA + C1_A_STAGES * C1_A_STAGE;
   uint8_t* const gen0 = smem + (sm0 - smem_u32(smem));              // generic pointer to the aligned base
 
   // ---- one-time setup ----
   if (threadIdx.x < C1_COUT) s_shift[threadIdx.x] = a.shift ? __ldg(a.shift + threadIdx.x) : 0.0f;
-  for (int i = threadIdx.x; i < C1_B_BYTES / 16; i += C1_THREADS)
+  for (int i = threadIdx.x; i < B_BYTES / 16; i += C1_THREADS)
     reinterpret_cast<uint4*>(gen0)[i] = __ldg(a.w_packed + i);
   fence_proxy_async_smem();                                         // B is read by the tensor core (async proxy)
   if (warp == C1_WARP_PRODUCER && lane == 0) {
@@ -182,13 +196,24 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args 
         // bf16_rn(fma(v, 2/255, -1)) == bf16_rn((v/255)*2 - 1) for all 256 byte values (tests/test_abi_cpu.py checks
         // the identity), so no LUT: the smem crossbar is the contended resource of this kernel
         uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-        if (va) {
-          w0 = c1_cvt2(p[0], p[1]);
-          w1 = c1_cvt2(p[2], 0) & 0xffffu;         // channel 3 is zero padding
-        }
-        if (vb) {
-          w2 = c1_cvt2(p[3], p[4]);
-          w3 = c1_cvt2(p[5], 0) & 0xffffu;
+        if constexpr (SPLIT) {
+          if (va) {
+            w0 = c1_cvt2_int(p[0], p[1]);
+            w1 = (c1_cvt2_int(p[2], 0) & 0xffffu) | 0x3f800000u;   // channel 3 = 1.0 inside the image
+          }
+          if (vb) {
+            w2 = c1_cvt2_int(p[3], p[4]);
+            w3 = (c1_cvt2_int(p[5], 0) & 0xffffu) | 0x3f800000u;
+          }
+        } else {
+          if (va) {
+            w0 = c1_cvt2(p[0], p[1]);
+            w1 = c1_cvt2(p[2], 0) & 0xffffu;         // channel 3 is zero padding
+          }
+          if (vb) {
+            w2 = c1_cvt2(p[3], p[4]);
+            w3 = c1_cvt2(p[5], 0) & 0xffffu;
+          }
         }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dstA + pr * C1_PITCH + j * 16), "r"(w0), "r"(w1),
                      "r"(w2), "r"(w3)
@@ -225,6 +250,11 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args 
 #pragma unroll
         for (int ty = 0; ty < 4; ++ty)
           if (!(a.debug & 8)) umma_bf16(tmem_d, ad + (uint32_t)((ty * C1_PITCH) >> 4), bdesc0 + (uint32_t)((ty * 4096) >> 4), idesc, ty > 0);
+        if constexpr (SPLIT) {
+#pragma unroll
+          for (int ty = 0; ty < 4; ++ty)          // the lo halves of the weights, same patch rows
+            umma_bf16(tmem_d, ad + (uint32_t)((ty * C1_PITCH) >> 4), bdesc0 + (uint32_t)((C1_B_BYTES + ty * 4096) >> 4), idesc, 1u);
+        }
         umma_commit(&a_empty[as]);
         umma_commit(&tmem_full[mw]);
       }
@@ -241,7 +271,7 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args 
       if (tile >= a.total_tiles) break;
       const int buf = it % C1_NBUF;
       const C1Tile t = c1_tile(a, tile);
-      uint4* dst = reinterpret_cast<uint4*>(a.y + ((size_t)((size_t)t.n * Ho + t.ph0 + g) * Wo + t.pw0 + i) * C1_COUT);
+      uint4* dst = reinterpret_cast<uint4*>(a.y + ((size_t)((size_t)t.n * Ho + t.ph0 + g) * Wo + t.pw0 + i) * (SPLIT ? 2 * C1_COUT : C1_COUT));
       mbar_wait(&tmem_full[buf], (uint32_t)(it / C1_NBUF) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
@@ -282,6 +312,16 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args 
           o[e] = *reinterpret_cast<uint32_t*>(&h);
         }
         dst[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+        if constexpr (SPLIT) {
+          uint32_t l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o[e]));
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+            l[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          dst[4 + ch] = make_uint4(l[0], l[1], l[2], l[3]);     // lo half: channels 32..63 of the row
+        }
       }
       __syncwarp();
     }
@@ -314,11 +354,41 @@ __global__ void pack_conv1_u8_kernel(const float* __restrict__ w, const float* _
   out[idx] = __float2bfloat16_rn(v);
 }
 
+// bf16x3 variant: same index space twice (hi at [0, 8192), lo at [8192, 16384)); value = scale[ch] * 2/255 * w on the three
+// colour channels and -scale[ch] * sum_c w on the "ones" channel (the -1 of x = v*2/255 - 1, absent in the zero-padded halo)
+__global__ void pack_conv1_u8_split_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                           __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 4 * 2 * 128 * 8) return;
+  const int e = idx & 7, n = (idx >> 3) & 127, kg = (idx >> 10) & 1, ty = idx >> 11;
+  const int c = e & 3, tx = kg * 2 + (e >> 2);
+  const int win = n >> 5, ch = n & 31, dy = win >> 1, dx = win & 1;
+  const int kh = ty - dy, kw = tx - dx;
+  double v = 0.0;
+  if (kh >= 0 && kh < 3 && kw >= 0 && kw < 3) {
+    const float* wt = w + ((kh * 3 + kw) * 3) * C1_COUT + ch;
+    const double sc = scale ? (double)scale[ch] : 1.0;
+    if (c < 3) v = sc * (double)wt[c * C1_COUT] * (2.0 / 255.0);
+    else v = -sc * ((double)wt[0] + (double)wt[C1_COUT] + (double)wt[2 * C1_COUT]);
+  }
+  const __nv_bfloat16 hi = __float2bfloat16_rn((float)v);
+  out[idx] = hi;
+  out[4 * 2 * 128 * 8 + idx] = __float2bfloat16_rn((float)(v - (double)__bfloat162float(hi)));
+}
+
 }  // namespace y2
 
 using namespace y2;
 
 extern "C" size_t y2_conv1_u8_packed_weight_elems(void) { return 4 * 2 * 128 * 8; }
+
+extern "C" int y2_pack_weights_conv1_u8_split(const float* w_hwio, const float* scale, void* w_packed, y2_stream_t stream) {
+  Y2_ARG(w_hwio && w_packed);
+  pack_conv1_u8_split_kernel<<<(4 * 2 * 128 * 8 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_hwio, scale,
+                                                                                               (__nv_bfloat16*)w_packed);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
 
 extern "C" int y2_pack_weights_conv1_u8(const float* w_hwio, const float* scale, void* w_packed, y2_stream_t stream) {
   Y2_ARG(w_hwio && w_packed);
@@ -328,8 +398,8 @@ extern "C" int y2_pack_weights_conv1_u8(const float* w_hwio, const float* scale,
   return Y2_OK;
 }
 
-extern "C" int y2_conv1_u8_pool_fwd(const uint8_t* img, const void* w_packed, const float* shift, void* y, int N, int H,
-                                    int W, float alpha, y2_stream_t stream) {
+static int conv1_u8_pool_launch(const uint8_t* img, const void* w_packed, const float* shift, void* y, int N, int H,
+                                int W, float alpha, bool split, y2_stream_t stream) {
   Y2_ARG(img && w_packed && y && N > 0 && H > 0 && W > 0);
   if (H % (2 * C1_TH) != 0 || W % (2 * C1_TW) != 0) {
     set_error("y2_conv1_u8_pool_fwd: H must be a multiple of %d and W of %d (got %dx%d)", 2 * C1_TH, 2 * C1_TW, H, W);
@@ -367,9 +437,24 @@ extern "C" int y2_conv1_u8_pool_fwd(const uint8_t* img, const void* w_packed, co
       return Y2_ERR_DRIVER;
     }
   }
-  Y2_CUDA(cudaFuncSetAttribute(conv1_u8_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1_SMEM));
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  conv1_u8_pool_kernel<<<grid, C1_THREADS, C1_SMEM, (cudaStream_t)stream>>>(tmImg, a);
+  if (split) {
+    Y2_CUDA(cudaFuncSetAttribute(conv1_u8_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1_SMEM_SPLIT));
+    conv1_u8_pool_kernel<true><<<grid, C1_THREADS, C1_SMEM_SPLIT, (cudaStream_t)stream>>>(tmImg, a);
+  } else {
+    Y2_CUDA(cudaFuncSetAttribute(conv1_u8_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1_SMEM));
+    conv1_u8_pool_kernel<false><<<grid, C1_THREADS, C1_SMEM, (cudaStream_t)stream>>>(tmImg, a);
+  }
   Y2_LAUNCHED();
   return Y2_OK;
+}
+
+extern "C" int y2_conv1_u8_pool_fwd(const uint8_t* img, const void* w_packed, const float* shift, void* y, int N, int H,
+                                    int W, float alpha, y2_stream_t stream) {
+  return conv1_u8_pool_launch(img, w_packed, shift, y, N, H, W, alpha, false, stream);
+}
+
+extern "C" int y2_conv1_u8_pool_fwd_split(const uint8_t* img, const void* w_packed, const float* shift, void* y, int N, int H,
+                                          int W, float alpha, y2_stream_t stream) {
+  return conv1_u8_pool_launch(img, w_packed, shift, y, N, H, W, alpha, true, stream);
 }

@@ -29,7 +29,7 @@ namespace y2 {
 constexpr int SK_THREADS = 64 + 8 * 32;        // warps 0-7 epilogue (2 per TMEM lane quarter), 8 TMA, 9 MMA
 constexpr int SK_STAGES = 3;                   // 64 KB each: A 2 x (128 px x 128 B), B 256 x 128 B
 constexpr uint32_t SK_A_HALF = 128 * 128, SK_B_BYTES = 256 * 128, SK_STAGE = 2 * SK_A_HALF + SK_B_BYTES;
-constexpr int SK_MAX_UNITS = 192;
+constexpr int SK_MAX_UNITS = 1024;             // K steps per tile (bf16x3, 3x3, 1280 channels: 9 * 60 = 540)
 
 struct SkArgs {
   const float* scale;
@@ -41,7 +41,10 @@ struct SkArgs {
   int leaky, out_f32;
   long long M;
   int H, W, ldy, pad;
-  int cin_p, cchunks, ksteps;       // K steps per tile = taps * cchunks
+  int cin_p, cchunks, ksteps;       // K steps per tile = taps * cchunks   (cin_p: K extent per tap of the B operand)
+  int a_wrap;                       // channel chunks of the A tensor (bf16x3: 2/3 of cchunks -- the K loop walks [hi | lo | hi])
+  int split_out, lo_off;            // bf16x3 output: hi at column c, lo at column lo_off + c
+  uint32_t fd_cc_mul, fd_cc_shr;    // division by cchunks
   int n_tiles, tiles;
   long long units;                  // tiles * ksteps
   uint32_t fd_nt_mul, fd_nt_shr, fd_w_mul, fd_w_shr, fd_h_mul, fd_h_shr, fd_ks_mul, fd_ks_shr;
@@ -49,12 +52,62 @@ struct SkArgs {
 
 constexpr uint32_t SK_STG_WARP = 32 * 128;     // per-warp store staging: 32 rows x 32 floats (or bf16), 128B-swizzled
 
+// K step -> (filter tap, A channel coordinate, B K coordinate).  bf16x3: the third block of a tap re-reads the hi channels.
+__device__ __forceinline__ void sk_unit(const SkArgs& a, int k, int& tap, int& a_c0, int& b_k) {
+  tap = (int)fdiv((uint32_t)k, a.fd_cc_mul, a.fd_cc_shr);
+  const int j = k - tap * a.cchunks;
+  a_c0 = (j < a.a_wrap ? j : j - a.a_wrap) * 64;
+  b_k = tap * a.cin_p + j * 64;
+}
+
+// 32 rows x 32 bf16 columns of one warp (lane = row, pk = its 16 packed pairs) -> global rows, through the warp's swizzled
+// staging tile so that one store instruction covers whole 64-byte row segments
+__device__ __forceinline__ void sk_store_rows_bf16(uint32_t stg, int lane, const uint32_t* pk, __nv_bfloat16* dst, long long grow0,
+                                                   long long M, int ldy) {
+  // 64-byte rows, 4 units, unit j of row r at (j ^ ((r >> 1) & 3))
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
+                 "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                 : "memory");
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int r = t * 8 + (lane >> 2), j = lane & 3;
+    uint4 o;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                 : "r"(stg + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)));
+    if (grow0 + r < M) *reinterpret_cast<uint4*>(dst + (size_t)(grow0 + r) * ldy + j * 8) = o;
+  }
+  __syncwarp();
+}
+
+// affine + leaky done: convert (and, bf16x3, split into hi / lo) and store one 32 x 32 chunk
+__device__ __forceinline__ void sk_store_chunk_bf16(const SkArgs& a, uint32_t stg, int lane, const float* f, int col, long long grow0) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + col;
+  sk_store_rows_bf16(stg, lane, pk, dst, grow0, a.M, a.ldy);
+  if (a.split_out) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[i]));
+      const __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+      pk[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    sk_store_rows_bf16(stg, lane, pk, dst + a.lo_off, grow0, a.M, a.ldy);
+  }
+}
+
 __global__ void __launch_bounds__(SK_THREADS, 1)
 conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SkArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[SK_STAGES], empty_bar[SK_STAGES], tmem_full, tmem_empty;
   __shared__ uint32_t s_tmem_base;
-  __shared__ uint8_t s_unit_tap[SK_MAX_UNITS], s_unit_cc[SK_MAX_UNITS];
   pdl_launch_dependents();                                      // persistent grid: the next kernel may take SMs as my CTAs retire
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
@@ -70,11 +123,6 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tmem_full, 1);
       mbar_init(&tmem_empty, 8);
       fence_barrier_init();
-    }
-    for (int u = lane; u < a.ksteps; u += 32) {
-      const int tap = u / a.cchunks;
-      s_unit_tap[u] = (uint8_t)tap;
-      s_unit_cc[u] = (uint8_t)(u - tap * a.cchunks);
     }
   }
   if (warp == 9) {
@@ -114,13 +162,14 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int k = k0; k < k1; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_expect_tx(&full_bar[stage], SK_STAGE);
-          const int tap = s_unit_tap[k], a_c0 = s_unit_cc[k] * 64;
+          int tap, a_c0, b_k;
+          sk_unit(a, k, tap, a_c0, b_k);
           const int kh = a.pad ? (tap * 11) >> 5 : 0, kw = tap - kh * 3;       // tap / 3 for tap < 9 (1x1: tap == 0)
           const uint32_t sA = smem_base + stage * SK_STAGE;
           const uint32_t bar = smem_u32(&full_bar[stage]);
           tma_load_im2col_4d(sA, &tmA, bar, a_c0, w0[0] - a.pad, h0[0] - a.pad, n0[0], (uint16_t)kw, (uint16_t)kh);
           tma_load_im2col_4d(sA + SK_A_HALF, &tmA, bar, a_c0, w0[1] - a.pad, h0[1] - a.pad, n0[1], (uint16_t)kw, (uint16_t)kh);
-          tma_load_2d(sA + 2 * SK_A_HALF, &tmB, bar, tap * a.cin_p + a_c0, nrow0);
+          tma_load_2d(sA + 2 * SK_A_HALF, &tmB, bar, b_k, nrow0);
           if (++stage == SK_STAGES) { stage = 0; phase ^= 1u; }
         }
         u += k1 - k0;
@@ -268,26 +317,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (grow0 + r < a.M) *reinterpret_cast<float4*>(dst + (size_t)(grow0 + r) * a.ldy + j * 4) = o;
           }
         } else {
-          // bf16: 64-byte rows, 4 units, unit j of row r at (j ^ ((r >> 1) & 3))
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
-                         : "memory");
-          }
-          __syncwarp();
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + col0 + c;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int r = t * 8 + (lane >> 2), j = lane & 3;
-            uint4 o;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
-                         : "r"(stg + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)));
-            if (grow0 + r < a.M) *reinterpret_cast<uint4*>(dst + (size_t)(grow0 + r) * a.ldy + j * 8) = o;
-          }
+          sk_store_chunk_bf16(a, stg, lane, f, col0 + c, grow0);
         }
         __syncwarp();                                           // staging tile free for the next chunk
       }
@@ -351,7 +381,6 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[SK2_STAGES], empty_bar[SK2_STAGES], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ uint8_t s_unit_tap[SK_MAX_UNITS], s_unit_cc[SK_MAX_UNITS];
   pdl_launch_dependents();                                      // persistent grid: the next kernel may take SMs as my CTAs retire
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
@@ -368,11 +397,6 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int s = 0; s < SK2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 16); }   // 8 warps x 2 CTAs
       fence_barrier_init();
-    }
-    for (int u = lane; u < a.ksteps; u += 32) {
-      const int tap = u / a.cchunks;
-      s_unit_tap[u] = (uint8_t)tap;
-      s_unit_cc[u] = (uint8_t)(u - tap * a.cchunks);
     }
   }
   if (warp == 9) {
@@ -413,7 +437,8 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int k = k0; k < k1; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);             // my own copy: the leader's commit arrives on both
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * SK2_STAGE);
-          const int tap = s_unit_tap[k], a_c0 = s_unit_cc[k] * 64;
+          int tap, a_c0, b_k;
+          sk_unit(a, k, tap, a_c0, b_k);
           const int kh = a.pad ? (tap * 11) >> 5 : 0, kw = tap - kh * 3;       // tap / 3 for tap < 9 (1x1: tap == 0)
           const uint32_t sA = smem_base + stage * SK2_STAGE;
           const uint32_t bar = smem_u32(&full_bar[stage]) & PEER_BIT_MASK;      // the leader's barrier
@@ -421,7 +446,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int h = 0; h < HALVES; ++h)
             tma_load_im2col_4d_2sm(sA + (uint32_t)h * SK2_A_BYTES, &tmA, bar, a_c0, w0[h] - a.pad, h0[h] - a.pad, n0[h], (uint16_t)kw,
                                    (uint16_t)kh);
-          tma_load_2d_2sm(sA + HALVES * SK2_A_BYTES, &tmB, bar, tap * a.cin_p + a_c0, nrow0);
+          tma_load_2d_2sm(sA + HALVES * SK2_A_BYTES, &tmB, bar, b_k, nrow0);
           if (++stage == SK2_STAGES) { stage = 0; phase ^= 1u; }
         }
         u += k1 - k0;
@@ -576,26 +601,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (grow0 + r < a.M) *reinterpret_cast<float4*>(dst + (size_t)(grow0 + r) * a.ldy + j * 4) = o;
           }
         } else {
-          // bf16: 64-byte rows, 4 units, unit j of row r at (j ^ ((r >> 1) & 3))
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
-                         : "memory");
-          }
-          __syncwarp();
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + col0 + c;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int r = t * 8 + (lane >> 2), j = lane & 3;
-            uint4 o;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
-                         : "r"(stg + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)));
-            if (grow0 + r < a.M) *reinterpret_cast<uint4*>(dst + (size_t)(grow0 + r) * a.ldy + j * 8) = o;
-          }
+          sk_store_chunk_bf16(a, stg, lane, f, col0 + c, grow0);
         }
         __syncwarp();                                           // staging tile free for the next chunk
       }
@@ -637,11 +643,16 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   if (!(p->ksize == 1 || p->ksize == 3) || p->Cin % 64 != 0 || p->Cout % 256 != 0) return Y2_OK;
   if (p->H >= 64 && p->W >= 64) return Y2_OK;                   // large maps: the halo-patch mode of conv_tc_kernel wins
   const bool out_f32 = (p->flags & Y2_CONV_OUT_F32) != 0;
-  const int ldy = p->ldy > 0 ? p->ldy : p->Cout;
+  const int ldy = p->ldy > 0 ? p->ldy : (((p->flags & Y2_CONV_OUT_SPLIT) != 0 && !out_f32) ? 2 * p->Cout : p->Cout);
   if (ldy % (out_f32 ? 4 : 8) != 0 || (reinterpret_cast<uintptr_t>(p->y) & 15) != 0) return Y2_OK;
   if ((p->shift && (reinterpret_cast<uintptr_t>(p->shift) & 15) != 0) || (p->scale && (reinterpret_cast<uintptr_t>(p->scale) & 15) != 0))
     return Y2_OK;
-  const int taps = p->ksize * p->ksize, cchunks = p->Cin / 64, ksteps = taps * cchunks;
+  const bool split_in = (p->flags & Y2_CONV_IN_SPLIT) != 0;
+  const bool split_out = (p->flags & Y2_CONV_OUT_SPLIT) != 0 && !out_f32;
+  const int a_cin = split_in ? 2 * p->Cin : p->Cin, b_cin = split_in ? 3 * p->Cin : p->Cin;
+  const int taps = p->ksize * p->ksize, cchunks = b_cin / 64, ksteps = taps * cchunks;
+  const int lo_off = split_out ? (p->lo_off > 0 ? p->lo_off : p->Cout) : 0;
+  if (split_out && ((lo_off & 7) != 0 || ldy < lo_off + p->Cout)) return Y2_OK;
   int min_ksteps = 18;                                          // short K: the epilogue starts to show
   if (const char* e = getenv("Y2_CONV_STREAMK_MIN_KSTEPS")) min_ksteps = atoi(e);
   if (ksteps < min_ksteps || ksteps > SK_MAX_UNITS) return Y2_OK;
@@ -657,7 +668,11 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   a.out_f32 = out_f32;
   a.M = (long long)p->N * p->H * p->W;
   a.H = p->H; a.W = p->W; a.ldy = ldy; a.pad = p->ksize / 2;
-  a.cin_p = p->Cin; a.cchunks = cchunks; a.ksteps = ksteps;
+  a.cin_p = b_cin; a.cchunks = cchunks; a.ksteps = ksteps;
+  a.a_wrap = a_cin / 64;
+  a.split_out = split_out ? 1 : 0;
+  a.lo_off = lo_off;
+  fastdiv_init((uint32_t)cchunks, &a.fd_cc_mul, &a.fd_cc_shr);
   a.n_tiles = p->Cout / 256;
   // CTA-pair kernel (cta_group::2) unless disabled; 512-row pair tiles (two halves per CTA) unless disabled or too few tiles
   const bool two_cta = !getenv("Y2_CONV_STREAMK_1CTA") && g_num_sms >= 2;
@@ -684,21 +699,21 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
 
   CUtensorMap tmA, tmB;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
-    cuuint64_t strides[3] = {(cuuint64_t)p->Cin * 2, (cuuint64_t)p->W * p->Cin * 2, (cuuint64_t)p->H * p->W * p->Cin * 2};
+    cuuint64_t dims[4] = {(cuuint64_t)a_cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t strides[3] = {(cuuint64_t)a_cin * 2, (cuuint64_t)p->W * a_cin * 2, (cuuint64_t)p->H * p->W * a_cin * 2};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     int lower[2] = {-a.pad, -a.pad};
     int upper[2] = {a.pad - (p->ksize - 1), a.pad - (p->ksize - 1)};
     CUresult r = g_encodeIm2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), dims, strides, lower, upper,
                                 64, 128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r == CUDA_SUCCESS && g_driver_version <= 13010 && (size_t)a.M * p->Cin * 2 < 131072)
+    if (r == CUDA_SUCCESS && g_driver_version <= 13010 && (size_t)a.M * a_cin * 2 < 131072)
       reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);   // same small-tensor fix-up as conv_tcgen05.cu
     if (r != CUDA_SUCCESS) {
       set_error("conv_streamk: tensor map A encode failed (CUresult %d)", (int)r);
       return Y2_ERR_DRIVER;
     }
-    const int Kp = taps * p->Cin;
+    const int Kp = taps * b_cin;
     cuuint64_t bdims[2] = {(cuuint64_t)Kp, (cuuint64_t)p->Cout};
     cuuint64_t bstrides[1] = {(cuuint64_t)Kp * 2};
     cuuint32_t bbox[2] = {64, two_cta ? 128u : 256u};          // pair kernel: each CTA loads its half of the filters

@@ -68,6 +68,11 @@ struct ConvArgs {
   uint32_t fd_w_mul, fd_w_shr;            // a_mode 0: W         a_mode 1: tiles_w
   uint32_t fd_h_mul, fd_h_shr;            // a_mode 0: H         a_mode 1: tiles_h
   uint32_t fd_cch_mul, fd_cch_shr;        // cchunks
+  // "bf16x3" (Y2_CONV_IN_SPLIT / OUT_SPLIT, include/yolo2_b200.h): the A tensor holds [hi | lo] (a_wrap = its number of
+  // channel chunks); the K loop walks cchunks = 3/2 * a_wrap chunks per tap [hi | lo | hi] against B's [w_hi | w_hi | w_lo]
+  int a_wrap;             // channel chunks of the A tensor (== cchunks unless split)
+  int split_out;          // bf16 output as hi at column c, lo at column lo_off + c
+  int lo_off;
 };
 
 
@@ -127,13 +132,16 @@ constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 constexpr int WARP_PRODUCER = EPI_WARPS;
 constexpr int WARP_MMA = EPI_WARPS + 1;
 constexpr int MAX_STAGES = 12;
-constexpr int MAX_UNITS = 192;                     // (tap, channel-chunk) units per tile: 9 * 1280/64 = 180 (passthrough concat)
+constexpr int MAX_UNITS = 448;                     // (tap, channel-chunk) units per tile: 9 * 1280/64 = 180 (passthrough concat);
+                                                   // bf16x3: 9 * 3 * 1024/64 = 432
 
 // per-unit constants, computed once per CTA so that the single-thread roles do no index arithmetic
-struct __align__(16) UnitDesc {
-  int a_c0;      // channel coordinate of the A load
-  int kw, kh;    // filter tap (mode 2: kw, and kh = index of the kh=0 sub-block in the stationary B)
-  int b_k;       // K coordinate of the B load (mode 2: for kh = 0; + 3*cin_p per kh)
+struct __align__(8) UnitDesc {
+  uint16_t a_c0;   // channel coordinate of the A load
+  uint8_t kw;      // filter tap column
+  uint8_t pad_;
+  uint16_t kh;     // filter tap row (mode 2: index of the kh=0 sub-block in the stationary B)
+  uint16_t b_k;    // K coordinate of the B load (mode 2: for kh = 0; + 3*cin_p per kh)
 };
 
 template <int CW>
@@ -149,6 +157,21 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
   }
+}
+
+// bf16x3 output: 8 floats -> 8 bf16 hi (16 B) + 8 bf16 lo = bf16(v - hi) (16 B)
+__device__ __forceinline__ void split8_bf16(const float* f, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    l[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // One chunk of CW accumulator columns of one row: affine, leaky, (pool), convert, store.
@@ -189,6 +212,36 @@ __device__ __forceinline__ void epilogue_chunk(const ConvArgs& a, const uint32_t
 #pragma unroll
         for (int i = 0; i < CW; ++i)
           if (i < ncols) dst[i] = f[i];
+      }
+    }
+  } else if (a.split_out) {
+    // bf16x3: pool on the float32 values, then split into hi / lo halves of the output row
+    if (pool) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) {
+        f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
+        f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1 << a.tw_log2));
+      }
+    }
+    if (valid) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)orow * a.ldy + c0;
+      const int nc = min(CW, a.Cout - c0);        // (columns past Cout belong to the lo half / do not exist)
+      if (nc == CW && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (a.lo_off & 7) == 0) {
+#pragma unroll
+        for (int i = 0; i < CW / 8; ++i) {
+          uint4 hi, lo;
+          split8_bf16(f + 8 * i, hi, lo);
+          reinterpret_cast<uint4*>(dst)[i] = hi;
+          reinterpret_cast<uint4*>(dst + a.lo_off)[i] = lo;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i)
+          if (i < nc) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(f[i]);
+            dst[i] = h;
+            dst[a.lo_off + i] = __float2bfloat16_rn(f[i] - __bfloat162float(h));
+          }
       }
     }
   } else {
@@ -275,7 +328,13 @@ __device__ __forceinline__ void epilogue_chunk_pooled_bf16(const ConvArgs& a, co
     f[i] = fmaf(m8[i], fabsf(sc[i]), sh[i]);
     if (leaky_on) f[i] = fmaxf(f[i], a.alpha * f[i]);
   }
-  if (valid_px) {
+  if (valid_px && a.split_out) {
+    uint4 hi, lo;
+    split8_bf16(f, hi, lo);
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)orow * a.ldy + c0 + cb;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + a.lo_off) = lo;
+  } else if (valid_px) {
     __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
     __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)orow * a.ldy + c0 + cb;
@@ -355,12 +414,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int units = (A_MODE == 2) ? a.cchunks * 3 : a.kblocks;
       for (int u = lane; u < units; u += 32) {
         UnitDesc d;
+        d.pad_ = 0;
         if (A_MODE == 2) {
           const int cc = u / 3, kw = u - cc * 3;
-          d.a_c0 = cc * a.kchunk; d.kw = kw; d.kh = kw * a.cchunks + cc; d.b_k = kw * a.cin_p + d.a_c0;
+          const int ca = cc < a.a_wrap ? cc : cc - a.a_wrap;          // bf16x3: the third K block re-reads the hi channels
+          d.a_c0 = (uint16_t)(ca * a.kchunk); d.kw = (uint8_t)kw; d.kh = (uint16_t)(kw * a.cchunks + cc);
+          d.b_k = (uint16_t)(kw * a.cin_p + cc * a.kchunk);
         } else {
           const int tap = u / a.cchunks, cc = u - tap * a.cchunks;
-          d.a_c0 = cc * a.kchunk; d.kh = tap / a.ksize; d.kw = tap - d.kh * a.ksize; d.b_k = tap * a.cin_p + d.a_c0;
+          const int ca = cc < a.a_wrap ? cc : cc - a.a_wrap;
+          const int kh = tap / a.ksize;
+          d.a_c0 = (uint16_t)(ca * a.kchunk); d.kh = (uint16_t)kh; d.kw = (uint8_t)(tap - kh * a.ksize);
+          d.b_k = (uint16_t)(tap * a.cin_p + cc * a.kchunk);
         }
         s_units[u] = d;
       }
@@ -785,9 +850,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bulk_commit_group();
           }
           ++nstore;
-        } else if (A_MODE != 0 && pool && !out_f32 && c0 + 32 <= a.Cout && (a.ldy & 7) == 0) {
+        } else if (A_MODE != 0 && pool && !out_f32 && c0 + 32 <= a.Cout && (a.ldy & 7) == 0 && (a.lo_off & 7) == 0) {
           epilogue_chunk_pooled_bf16(a, v, my_scale, my_shift, cc, c0, valid_px, orow, leaky_on, lane);
-        } else if (c0 < a.ldy) {
+        } else if (c0 < (a.split_out ? a.Cout : a.ldy)) {
           epilogue_chunk<32>(a, v, my_scale, my_shift, cc, c0, valid, orow, pool, leaky_on, out_f32);
         }
         __syncwarp();                               // reconverge before the next .sync.aligned TMEM load
@@ -929,7 +994,11 @@ using namespace y2;
 
 extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   Y2_ARG(p != nullptr);
-  Y2_ARG(p->x && p->w_packed && p->y && p->reserved == 0);
+  Y2_ARG(p->x && p->w_packed && p->y);
+  const bool split_in = (p->flags & Y2_CONV_IN_SPLIT) != 0;
+  const bool split_out = (p->flags & Y2_CONV_OUT_SPLIT) != 0 && (p->flags & Y2_CONV_OUT_F32) == 0;
+  Y2_ARG(split_out || p->lo_off == 0);
+  if (split_in) Y2_ARG(p->Cin % 32 == 0);
   Y2_ARG(p->N > 0 && p->H > 0 && p->W > 0 && p->Cin > 0 && p->Cout > 0 && (p->ksize == 1 || p->ksize == 3));
   const bool pool = (p->flags & Y2_CONV_POOL2) != 0;
   const bool out_f32 = (p->flags & Y2_CONV_OUT_F32) != 0;
@@ -950,14 +1019,19 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   a.y = p->y;
   a.N = p->N; a.H = p->H; a.W = p->W; a.Cout = p->Cout;
   a.M = (long long)p->N * p->H * p->W;
-  a.ldy = p->ldy > 0 ? p->ldy : p->Cout;
+  a.split_out = split_out ? 1 : 0;
+  a.lo_off = split_out ? (p->lo_off > 0 ? p->lo_off : p->Cout) : 0;
+  a.ldy = p->ldy > 0 ? p->ldy : (split_out ? 2 * p->Cout : p->Cout);
   Y2_ARG(a.ldy >= p->Cout);
+  if (split_out) Y2_ARG(a.lo_off >= p->Cout && a.ldy >= a.lo_off + p->Cout);
   a.flags = p->flags;
   a.alpha = p->alpha;
   a.ksize = p->ksize;
   a.pad = p->ksize / 2;
-  a.cin_p = y2_conv_cin_padded(p->Cin);
-  Y2_ARG(a.cin_p == p->Cin || p->Cin < 8);
+  // cin_p: K extent per tap of the B operand; a_cin: channels of the A tensor (bf16x3: [w_hi|w_hi|w_lo] against [hi|lo])
+  a.cin_p = split_in ? 3 * p->Cin : y2_conv_cin_padded(p->Cin);
+  const int a_cin = split_in ? 2 * p->Cin : a.cin_p;
+  Y2_ARG(split_in || a.cin_p == p->Cin || p->Cin < 8);
   const int cout_p = (p->Cout + 15) / 16 * 16;
   const int taps = p->ksize * p->ksize;
   a.first_layer = a.cin_p == 8;
@@ -966,16 +1040,17 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
     a.kchunk = 8; a.row_bytes = 16; a.kblocks = 1; a.cchunks = 1; a.ksteps = 5;
     a.layout_type = 0;                    // no swizzle: core matrices of 8 rows x 16 B
     a.kstep_bytes = 2 * 16;               // x rows -> two 16-byte K groups per MMA (scaled by rows in-kernel)
-  } else if (a.cin_p % 64 == 0) {
+  } else if (p->Cin % 64 == 0) {
     a.kchunk = 64; a.row_bytes = 128; a.layout_type = 2; a.ksteps = 4; a.kstep_bytes = 32;
     a.cchunks = a.cin_p / 64; a.kblocks = taps * a.cchunks;
-  } else if (a.cin_p % 32 == 0) {
+  } else if (p->Cin % 32 == 0) {
     a.kchunk = 32; a.row_bytes = 64; a.layout_type = 4; a.ksteps = 2; a.kstep_bytes = 32;
     a.cchunks = a.cin_p / 32; a.kblocks = taps * a.cchunks;
   } else {
     set_error("y2_conv_fwd_bf16: Cin=%d unsupported (need 3, or a multiple of 32)", p->Cin);
     return Y2_ERR_UNSUPPORTED;
   }
+  a.a_wrap = a.first_layer ? 1 : a_cin / a.kchunk;
   a.a_mode = pool ? 1 : 0;
   if (getenv("Y2_CONV_FORCE_TILED")) a.a_mode = 1;
   // halo-patch mode for 3x3 layers on large maps: an 8 x 16 pixel tile whose (16+2)-row neighbourhood is
@@ -1114,7 +1189,7 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   // the per-chunk group barriers and the ring loses four stages -- so it keeps the direct stores.)
   const size_t STG_BYTES = 4 * 2 * 8192;
   a.tma_store = 0;
-  if (a.a_mode == 2 && !a.first_layer && !pool && !out_f32 && p->Cout % 32 == 0 && a.ldy % 8 == 0 &&
+  if (a.a_mode == 2 && !a.first_layer && !pool && !out_f32 && !split_out && p->Cout % 32 == 0 && a.ldy % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(p->y) & 15) == 0 && EPI_GROUPS == 4 && block_n == 128 && a.row_bytes == 128 && a.cta2 &&
       b_region + 3 * (size_t)stage_bytes + STG_BYTES <= SMEM_BUDGET && !getenv("Y2_CONV_NO_TMA_STORE"))
     a.tma_store = 1;
@@ -1133,8 +1208,8 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   CUtensorMap tmA, tmB;
   const CUtensorMapSwizzle sw = swizzle_for(a.row_bytes);
   {
-    cuuint64_t dims[4] = {(cuuint64_t)a.cin_p, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
-    cuuint64_t strides[3] = {(cuuint64_t)a.cin_p * 2, (cuuint64_t)p->W * a.cin_p * 2, (cuuint64_t)p->H * p->W * a.cin_p * 2};
+    cuuint64_t dims[4] = {(cuuint64_t)a_cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t strides[3] = {(cuuint64_t)a_cin * 2, (cuuint64_t)p->W * a_cin * 2, (cuuint64_t)p->H * p->W * a_cin * 2};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r;
     if (a.a_mode == 0) {
@@ -1144,7 +1219,7 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
                          (cuuint32_t)a.kchunk, (cuuint32_t)TILE_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       // same small-tensor fix-up CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp) for drivers <= 13.1
-      if (r == CUDA_SUCCESS && g_driver_version <= 13010 && (size_t)a.M * a.cin_p * 2 < 131072)
+      if (r == CUDA_SUCCESS && g_driver_version <= 13010 && (size_t)a.M * a_cin * 2 < 131072)
         reinterpret_cast<uint64_t*>(&tmA)[1] &= ~(1ull << 21);
     } else if (a.a_mode == 2 && a.first_layer) {
       // halo patch of the first layer: (8+2) px x 8 ch = 80 contiguous elements per row, 18 rows

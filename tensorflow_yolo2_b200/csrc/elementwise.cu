@@ -79,6 +79,30 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+// "bf16x3" operand (Y2_CONV_IN_SPLIT): [Cout_p][taps][3*Cin] with per tap [w_hi | w_hi | w_lo], w_hi = bf16(w),
+// w_lo = bf16(w - w_hi).  The activation side supplies [a_hi | a_lo | a_hi], so one K sweep accumulates
+// a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
+__global__ void pack_weights_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps, int Cin,
+                                          int Cout, int Cout_p) {
+  const int K3 = 3 * Cin;
+  size_t total = (size_t)Cout_p * taps * K3;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int n = (int)(i / ((size_t)taps * K3));
+    int kk = (int)(i % ((size_t)taps * K3));
+    int tap = kk / K3, j = kk % K3;
+    int part = j / Cin, c = j - part * Cin;
+    float v = 0.0f;
+    if (n < Cout) {
+      const float wv = w[((size_t)tap * Cin + c) * Cout + n];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+      v = part < 2 ? __bfloat162float(hi) : wv - __bfloat162float(hi);
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // a2  batch statistics (tf.layers.batch_normalization training=True, darknet.py:42-44):
 // per-channel mean and biased variance over M rows.  Shifted sums in float64: with the
@@ -229,7 +253,7 @@ __global__ void bn_update_moving_kernel(float* __restrict__ mm, float* __restric
 template <int VEC, bool BF16OUT>
 __global__ void affine_leaky_pool_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ sub,
                                          const float* __restrict__ scale, const float* __restrict__ shift, float alpha, int leaky_on, int pool,
-                                         void* __restrict__ out, int N, int H, int W, int C, int ldo, int s2d) {
+                                         void* __restrict__ out, int N, int H, int W, int C, int ldo, int s2d, int lo_off) {
   int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   int CV = C / VEC;
   size_t total = (size_t)N * Ho * Wo * CV;
@@ -284,6 +308,10 @@ __global__ void affine_leaky_pool_kernel(const float* __restrict__ x, int ldx, c
 #pragma unroll
         for (int v = 0; v < VEC; ++v) ob[v] = __float2bfloat16_rn(r[v]);
       }
+      if (lo_off) {                                   // bf16x3: lo = bf16(v - hi) at column lo_off + c
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) ob[lo_off + v] = __float2bfloat16_rn(r[v] - __bfloat162float(__float2bfloat16_rn(r[v])));
+      }
     } else {
       float* of = reinterpret_cast<float*>(out) + o;
       if (VEC == 4) {
@@ -296,6 +324,19 @@ __global__ void affine_leaky_pool_kernel(const float* __restrict__ x, int ldx, c
   }
 }
 
+// bf16x3: the lo halves bf16(v - hi) of 8 values whose hi halves are packed in `hi`
+__device__ __forceinline__ uint4 lo_half8(const float* y, const uint4& hi) {
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
+  uint32_t l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h[i]));
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(y[2 * i] - hf.x, y[2 * i + 1] - hf.y);
+    l[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  return make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // Fast path of the above for the batch-statistics head layers (no pool, dense rows, C % 8 == 0, bf16 out): the generic
 // kernel spends its time in 64-bit div/mod per element (30 us for 66 MB, ncu r1c).  Here a thread owns 8 channels --
 // their sub / scale / shift live in registers -- and walks rows, four rows of 2 x 16-byte streaming loads in flight,
@@ -303,7 +344,7 @@ __global__ void affine_leaky_pool_kernel(const float* __restrict__ x, int ldx, c
 __global__ void __launch_bounds__(256) affine_leaky_rows_bf16_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ sub,
                                                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                                                      float alpha, int leaky_on, __nv_bfloat16* __restrict__ out, int ldo,
-                                                                     int M, int C8) {
+                                                                     int M, int C8, int lo_off) {
   const int cx = blockIdx.y * blockDim.x + threadIdx.x;          // channel group
   if (cx >= C8) return;
   const int c0 = cx * 8;
@@ -343,6 +384,7 @@ __global__ void __launch_bounds__(256) affine_leaky_rows_bf16_kernel(const float
       pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
       pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
       *reinterpret_cast<uint4*>(out + (size_t)r * ldo + c0) = pk;
+      if (lo_off) *reinterpret_cast<uint4*>(out + (size_t)r * ldo + lo_off + c0) = lo_half8(y, pk);
     }
   }
 }
@@ -352,7 +394,7 @@ __global__ void __launch_bounds__(256) affine_leaky_rows_bf16_kernel(const float
 __global__ void __launch_bounds__(256) affine_leaky_pool_rows_bf16_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ sub,
                                                                           const float* __restrict__ scale, const float* __restrict__ shift,
                                                                           float alpha, int leaky_on, __nv_bfloat16* __restrict__ out,
-                                                                          int ldo, int H, int W, unsigned units, int C8) {
+                                                                          int ldo, int H, int W, unsigned units, int C8, int lo_off) {
   const int cx = blockIdx.y * blockDim.x + threadIdx.x;
   if (cx >= C8) return;
   const int c0 = cx * 8;
@@ -395,6 +437,7 @@ __global__ void __launch_bounds__(256) affine_leaky_pool_rows_bf16_kernel(const 
     pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
     pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
     *reinterpret_cast<uint4*>(out + (size_t)u * ldo + c0) = pk;
+    if (lo_off) *reinterpret_cast<uint4*>(out + (size_t)u * ldo + lo_off + c0) = lo_half8(r, pk);
   }
 }
 
@@ -560,6 +603,21 @@ int y2_pack_weights_bf16(const float* w_hwio, void* w_packed, int ksize, int Cin
   return Y2_OK;
 }
 
+size_t y2_conv_packed_weight_split_elems(int ksize, int Cin, int Cout) {
+  int cout_p = (Cout + 15) / 16 * 16;
+  return (size_t)cout_p * ksize * ksize * 3 * Cin;
+}
+
+int y2_pack_weights_bf16_split(const float* w_hwio, void* w_packed, int ksize, int Cin, int Cout, y2_stream_t stream) {
+  Y2_ARG(w_hwio && w_packed && (ksize == 1 || ksize == 3) && Cin > 0 && Cout > 0 && Cin % 32 == 0);
+  int cout_p = (Cout + 15) / 16 * 16;
+  size_t total = (size_t)cout_p * ksize * ksize * 3 * Cin;
+  pack_weights_split_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_hwio, (__nv_bfloat16*)w_packed,
+                                                                                    ksize * ksize, Cin, Cout, cout_p);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
 static int bn_splits(int M) {
   int s = (M + 127) / 128;
   return s > 1024 ? 1024 : (s < 1 ? 1 : s);
@@ -625,16 +683,21 @@ int y2_bn_update_moving(float* moving_mean, float* moving_var, const float* mean
 }
 
 int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const float* scale, const float* shift, float alpha,
-                            int leaky_on, int pool, void* out, int out_dtype, int ldo, int space_to_depth, int N, int H, int W,
-                            int C, y2_stream_t stream) {
-  Y2_ARG(x && out && N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && (out_dtype == 0 || out_dtype == 1));
+                            int leaky_on, int pool, void* out, int out_dtype, int ldo, int space_to_depth, int lo_off, int N, int H,
+                            int W, int C, y2_stream_t stream) {
+  Y2_ARG(x && out && N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && (out_dtype == 0 || out_dtype == 1 || out_dtype == 2));
   if (pool) Y2_ARG(H % 2 == 0 && W % 2 == 0);
-  if (ldo <= 0) ldo = C;
-  if (space_to_depth) Y2_ARG(!pool && H % 2 == 0 && W % 2 == 0 && ldo >= 4 * C);
-  else Y2_ARG(ldo >= C);
+  const bool split = out_dtype == 2;                // bf16x3: hi at column c, lo at column lo_off + c (0 -> the row's second half)
+  if (split) out_dtype = 1;
+  if (ldo <= 0) ldo = split ? 2 * C : C;
+  if (split && lo_off <= 0) lo_off = space_to_depth ? ldo / 2 : C;
+  if (!split) lo_off = 0;
+  if (space_to_depth) Y2_ARG(!pool && H % 2 == 0 && W % 2 == 0 && ldo >= (split ? lo_off + 4 * C : 4 * C));
+  else Y2_ARG(ldo >= (split ? lo_off + C : C));
+  if (split) Y2_ARG(lo_off >= C);
   cudaStream_t st = (cudaStream_t)stream;
   int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
-  if (!pool && !space_to_depth && out_dtype == 1 && C % 8 == 0 && ldx % 4 == 0 && ldo % 8 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0 &&
+  if (!pool && !space_to_depth && out_dtype == 1 && C % 8 == 0 && ldx % 4 == 0 && ldo % 8 == 0 && lo_off % 8 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0 &&
       (long long)N * H * W < (1ll << 30) && !getenv("Y2_AFFINE_GENERIC")) {
     const int M = N * H * W, C8 = C / 8;
     const int bx = C8 >= 128 ? 128 : ((C8 + 31) / 32) * 32;       // channel-group lanes per block (whole warps)
@@ -644,11 +707,11 @@ int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const flo
     if (gx > need) gx = need;
     if (gx < 1) gx = 1;
     affine_leaky_rows_bf16_kernel<<<dim3(gx, (C8 + bx - 1) / bx), dim3(bx, by), 0, st>>>(
-        x, ldx, sub, scale, shift, alpha, leaky_on, reinterpret_cast<__nv_bfloat16*>(out), ldo, M, C8);
+        x, ldx, sub, scale, shift, alpha, leaky_on, reinterpret_cast<__nv_bfloat16*>(out), ldo, M, C8, lo_off);
     Y2_LAUNCHED();
     return Y2_OK;
   }
-  if (pool && !space_to_depth && out_dtype == 1 && C % 8 == 0 && ldx % 4 == 0 && ldo % 8 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0 &&
+  if (pool && !space_to_depth && out_dtype == 1 && C % 8 == 0 && ldx % 4 == 0 && ldo % 8 == 0 && lo_off % 8 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0 &&
       (long long)N * H * W < (1ll << 31) && !getenv("Y2_AFFINE_GENERIC")) {
     const unsigned units = (unsigned)((long long)N * Ho * Wo);
     const int C8 = C / 8;
@@ -659,7 +722,7 @@ int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const flo
     if (gx > need) gx = need;
     if (gx < 1) gx = 1;
     affine_leaky_pool_rows_bf16_kernel<<<dim3((unsigned)gx, (unsigned)((C8 + bx - 1) / bx)), dim3(bx, by), 0, st>>>(
-        x, ldx, sub, scale, shift, alpha, leaky_on, reinterpret_cast<__nv_bfloat16*>(out), ldo, H, W, units, C8);
+        x, ldx, sub, scale, shift, alpha, leaky_on, reinterpret_cast<__nv_bfloat16*>(out), ldo, H, W, units, C8, lo_off);
     Y2_LAUNCHED();
     return Y2_OK;
   }
@@ -675,20 +738,20 @@ int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const flo
     Y2_LAUNCHED();
     return Y2_OK;
   }
-  bool vec4 = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  bool vec4 = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (lo_off % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)out & 15) == 0);
   size_t total = (size_t)N * Ho * Wo * (vec4 ? C / 4 : C);
   int g = grid_for(total, 256);
   const int s2d = space_to_depth ? 1 : 0;
   if (vec4) {
     if (out_dtype == 1)
-      affine_leaky_pool_kernel<4, true><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d);
+      affine_leaky_pool_kernel<4, true><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d, lo_off);
     else
-      affine_leaky_pool_kernel<4, false><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d);
+      affine_leaky_pool_kernel<4, false><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d, lo_off);
   } else {
     if (out_dtype == 1)
-      affine_leaky_pool_kernel<1, true><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d);
+      affine_leaky_pool_kernel<1, true><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d, lo_off);
     else
-      affine_leaky_pool_kernel<1, false><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d);
+      affine_leaky_pool_kernel<1, false><<<g, 256, 0, st>>>(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, N, H, W, C, ldo, s2d, lo_off);
   }
   Y2_LAUNCHED();
   return Y2_OK;
@@ -696,7 +759,7 @@ int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const flo
 
 int y2_affine_leaky_pool(const float* x, int ldx, const float* sub, const float* scale, const float* shift, float alpha, int leaky_on,
                          int pool, void* out, int out_dtype, int N, int H, int W, int C, y2_stream_t stream) {
-  return y2_affine_leaky_pool_ex(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, out_dtype, C, 0, N, H, W, C, stream);
+  return y2_affine_leaky_pool_ex(x, ldx, sub, scale, shift, alpha, leaky_on, pool, out, out_dtype, 0, 0, 0, N, H, W, C, stream);
 }
 
 int y2_maxpool2x2_bf16(const void* x, void* y, int N, int H, int W, int C, y2_stream_t stream) {

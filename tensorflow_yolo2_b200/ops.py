@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ConvParams, Y2_CONV_LEAKY, Y2_CONV_POOL2, Y2_CONV_OUT_F32, check
+from ._lib import ConvParams, Y2_CONV_LEAKY, Y2_CONV_POOL2, Y2_CONV_OUT_F32, Y2_CONV_IN_SPLIT, Y2_CONV_OUT_SPLIT, check
 
 ALPHA = 0.1        # yolo2_nets/darknet.py:5
 BN_EPS = 1e-3      # tf.layers.batch_normalization default
@@ -88,24 +88,40 @@ def pack_weights_bf16(w_hwio, out=None):
     return out
 
 
+def pack_weights_bf16_split(w_hwio, out=None):
+    """bf16x3 operand of conv_fwd_bf16(split_in=True): per tap [w_hi | w_hi | w_lo] (include/yolo2_b200.h)."""
+    k, _, Cin, Cout = w_hwio.shape
+    n = int(_lib.load().y2_conv_packed_weight_split_elems(k, Cin, Cout))
+    if out is None:
+        out = torch.empty((n,), dtype=torch.bfloat16, device=w_hwio.device)
+    assert out.numel() >= n
+    check(_lib.load().y2_pack_weights_bf16_split(_p(w_hwio, torch.float32), _p(out), k, Cin, Cout, _stream()),
+          'y2_pack_weights_bf16_split')
+    return out
+
+
 def conv_fwd_bf16(x, w_packed, ksize, cin, cout, scale=None, shift=None, leaky=True, pool=False, out_f32=False,
-                  ldy=None, out=None, alpha=ALPHA, out_col=0):
-    """x bf16 [N,H,W,Cin_p]; returns bf16 [N,Ho,Wo,Cout] or (out_f32) f32 [N*H*W, ldy]."""
+                  ldy=None, out=None, alpha=ALPHA, out_col=0, split_in=False, split_out=False, lo_off=0):
+    """x bf16 [N,H,W,Cin_p]; returns bf16 [N,Ho,Wo,Cout] or (out_f32) f32 [N*H*W, ldy].
+    bf16x3 mode: split_in -> x is [N,H,W,2*Cin] = [hi | lo] and w_packed comes from pack_weights_bf16_split;
+    split_out -> the bf16 result is [N,Ho,Wo,2*Cout] = [hi | lo] (lo at column lo_off or Cout of a row of stride ldy)."""
     N, H, W, cin_p = x.shape
-    assert cin_p == conv_cin_padded(cin), (cin_p, cin)
+    assert cin_p == (2 * cin if split_in else conv_cin_padded(cin)), (cin_p, cin, split_in)
     _ensure_conv_workspace(x.device)
-    flags = (Y2_CONV_LEAKY if leaky else 0) | (Y2_CONV_POOL2 if pool else 0) | (Y2_CONV_OUT_F32 if out_f32 else 0)
-    ld = int(ldy) if ldy else cout
+    split_out = bool(split_out) and not out_f32
+    flags = (Y2_CONV_LEAKY if leaky else 0) | (Y2_CONV_POOL2 if pool else 0) | (Y2_CONV_OUT_F32 if out_f32 else 0) | \
+        (Y2_CONV_IN_SPLIT if split_in else 0) | (Y2_CONV_OUT_SPLIT if split_out else 0)
+    ld = int(ldy) if ldy else (2 * cout if split_out else cout)
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
     if out is None:
         if out_f32:
             out = torch.empty((N * Ho * Wo, ld), dtype=torch.float32, device=x.device)
         else:
-            assert ld == cout
-            out = torch.empty((N, Ho, Wo, cout), dtype=torch.bfloat16, device=x.device)
+            assert ld == (2 * cout if split_out else cout)
+            out = torch.empty((N, Ho, Wo, ld), dtype=torch.bfloat16, device=x.device)
     prm = ConvParams(x=_p(x, torch.bfloat16), w_packed=_p(w_packed, torch.bfloat16), scale=_p(scale, torch.float32),
                      shift=_p(shift, torch.float32), y=_p_off(out, out_col), N=N, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize,
-                     flags=flags, alpha=alpha, ldy=ld, reserved=0)
+                     flags=flags, alpha=alpha, ldy=ld, lo_off=int(lo_off) if split_out else 0)
     check(_lib.load().y2_conv_fwd_bf16(C.byref(prm), _stream()), 'y2_conv_fwd_bf16')
     return out
 
@@ -153,15 +169,27 @@ def pack_weights_conv1_u8(w_hwio, scale=None, out=None):
     return out
 
 
-def conv1_u8_pool(img_u8, w_packed_c1, shift, out=None, alpha=ALPHA):
-    """uint8 [N,H,W,3] BGR -> bf16 [N,H/2,W/2,32]: preprocessing + conv1 + BN(scale folded, +shift) + leaky + pool."""
+def pack_weights_conv1_u8_split(w_hwio, scale=None, out=None):
+    """bf16x3 operand of conv1_u8_pool(split=True): hi + lo halves of the weights with x = v*2/255 - 1 folded in."""
+    assert tuple(w_hwio.shape) == (3, 3, 3, 32), 'the fused first layer is Darknet19\'s 3x3 3->32 conv'
+    n = 2 * int(_lib.load().y2_conv1_u8_packed_weight_elems())
+    if out is None:
+        out = torch.empty((n,), dtype=torch.bfloat16, device=w_hwio.device)
+    check(_lib.load().y2_pack_weights_conv1_u8_split(_p(w_hwio, torch.float32), _p(scale, torch.float32), _p(out), _stream()),
+          'y2_pack_weights_conv1_u8_split')
+    return out
+
+
+def conv1_u8_pool(img_u8, w_packed_c1, shift, out=None, alpha=ALPHA, split=False):
+    """uint8 [N,H,W,3] BGR -> bf16 [N,H/2,W/2,32]: preprocessing + conv1 + BN(scale folded, +shift) + leaky + pool.
+    split=True (bf16x3): w_packed_c1 from pack_weights_conv1_u8_split, result [N,H/2,W/2,64] = [hi | lo]."""
     N, H, W, c = img_u8.shape
     assert c == 3
     if out is None:
-        out = torch.empty((N, H // 2, W // 2, 32), dtype=torch.bfloat16, device=img_u8.device)
-    check(_lib.load().y2_conv1_u8_pool_fwd(_p(img_u8, torch.uint8), _p(w_packed_c1, torch.bfloat16),
-                                           _p(shift, torch.float32), _p(out, torch.bfloat16), N, H, W, alpha, _stream()),
-          'y2_conv1_u8_pool_fwd')
+        out = torch.empty((N, H // 2, W // 2, 64 if split else 32), dtype=torch.bfloat16, device=img_u8.device)
+    fn = _lib.load().y2_conv1_u8_pool_fwd_split if split else _lib.load().y2_conv1_u8_pool_fwd
+    check(fn(_p(img_u8, torch.uint8), _p(w_packed_c1, torch.bfloat16), _p(shift, torch.float32), _p(out, torch.bfloat16),
+             N, H, W, alpha, _stream()), 'y2_conv1_u8_pool_fwd')
     return out
 
 
@@ -242,20 +270,24 @@ def _p_off(t, col):
 
 
 def affine_leaky_pool(x, N, H, W, C_, ldx=None, sub=None, scale=None, shift=None, leaky=True, pool=False,
-                      out_bf16=False, alpha=ALPHA, out=None, ldo=None, out_col=0, space_to_depth=False):
+                      out_bf16=False, alpha=ALPHA, out=None, ldo=None, out_col=0, space_to_depth=False, split_out=False,
+                      lo_off=0):
     """x f32 rows [N*H*W, ldx] (or [N,H,W,C]); y = leaky((x-sub)*scale+shift), optional 2x2 pool.
     ldo / out_col: write into channels [out_col, out_col+C) of rows of stride ldo (`out` = the whole wider tensor);
     space_to_depth: the passthrough reorg (block 2) folded into the store address (out = [N,H/2,W/2,ldo])."""
     ldx = ldx or C_
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    split_out = bool(split_out) and out_bf16          # bf16x3: [hi | lo] rows (lo at column lo_off, default C / ldo/2)
     if out is None:
         assert not ldo and not space_to_depth
-        out = torch.empty((N, Ho, Wo, C_), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+        out = torch.empty((N, Ho, Wo, 2 * C_ if split_out else C_), dtype=torch.bfloat16 if out_bf16 else torch.float32,
+                          device=x.device)
     assert out.dtype == (torch.bfloat16 if out_bf16 else torch.float32)
     check(_lib.load().y2_affine_leaky_pool_ex(_p(x, torch.float32), ldx, _p(sub, torch.float32), _p(scale, torch.float32),
                                               _p(shift, torch.float32), alpha, 1 if leaky else 0, 1 if pool else 0,
-                                              _p_off(out, out_col), 1 if out_bf16 else 0, int(ldo or C_),
-                                              1 if space_to_depth else 0, N, H, W, C_, _stream()),
+                                              _p_off(out, out_col), 2 if split_out else (1 if out_bf16 else 0),
+                                              int(ldo or (2 * C_ if split_out else C_)), 1 if space_to_depth else 0,
+                                              int(lo_off) if split_out else 0, N, H, W, C_, _stream()),
           'y2_affine_leaky_pool_ex')
     return out
 
