@@ -41,6 +41,8 @@ const char* y2_last_error(void);
 /* Number of kernels this library has launched from the calling process since load (all threads).
  * bench.py reports the delta over the timed region as "gpu_launches". */
 unsigned long long y2_launch_count(void);
+/* The Y2_* environment switches (A/B and debug knobs of the launchers) are read once per process; this re-reads them. */
+int y2_reload_env(void);
 
 /* ---- a10: input preprocessing ------------------------------------------------------------
  * pascal_detect_darknet.py:36-37, img_dataset/pascal_voc.py:62-64:  x = (u8 / 255.0) * 2.0 - 1.0
@@ -106,8 +108,10 @@ int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream);
 /* Scratch for the stream-K variant of y2_conv_fwd_bf16 (256x256 tiles whose K range is split between two CTAs: the
  * partial accumulators travel through this buffer).  Register a device buffer of y2_conv_workspace_bytes() bytes
  * (256-byte aligned) per calling thread; convolutions issued concurrently on different streams need different
- * buffers.  Without a workspace (or with NULL) every layer runs on the 128-row-tile kernel -- same results up to the
- * float32 summation order. */
+ * buffers (the Python front end keeps one per (device, stream) and one per engine / trainer).  The first 4096 bytes
+ * (hand-over flags) must be ZERO when the buffer is registered; every launch leaves them zero again.  Without a
+ * workspace (or with NULL) every layer runs on the 128-row-tile kernel -- same results up to the float32 summation
+ * order. */
 size_t y2_conv_workspace_bytes(void);
 int y2_conv_set_workspace(void* workspace, size_t bytes);
 
@@ -229,6 +233,10 @@ int y2_loss_v1_fwd_bwd(const float* net, const float* labels, int N, int S, int 
                        float image_size, float lambda_coord, float lambda_noobj, float* terms,
                        float* ious, float* object_mask, float* dnet,
                        void* workspace, size_t workspace_bytes, y2_stream_t stream);
+/* net_utils.py:337-342,366-369: the UNMASKED box deltas the reference logs as histograms ('boxes_delta_x/y/w/h'):
+ * predicted (x, y, sqrt w, sqrt h) minus the cell-relative ground truth, every cell and predictor.  deltas [N,S,S,B,4]. */
+int y2_loss_v1_box_deltas(const float* net, const float* labels, int N, int S, int B, int C, float image_size, float* deltas,
+                          y2_stream_t stream);
 
 /* ---- a': YOLOv2 region loss forward + backward, one kernel (absent from the reference) ---
  * net [N,S,S,A*(5+C)] f32; anchors [A,2] (cell units); gt_boxes [N,G,4] normalised (cx,cy,w,h), 16-byte aligned;

@@ -27,6 +27,7 @@ _SIGNATURES = {
     'y2_version': (C.c_int, []),
     'y2_last_error': (C.c_char_p, []),
     'y2_launch_count': (C.c_ulonglong, []),
+    'y2_reload_env': (C.c_int, []),
     'y2_preprocess_u8': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'y2_pad_cast_f32_to_bf16c8': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'y2_conv_fwd_f32': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
@@ -62,6 +63,7 @@ _SIGNATURES = {
     'y2_iou': (_i, [_vp, _vp, _vp, _sz, _vp]),
     'y2_loss_v1_workspace_bytes': (_sz, [_i, _i]),
     'y2_loss_v1_fwd_bwd': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'y2_loss_v1_box_deltas': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     'y2_region_loss_workspace_bytes': (_sz, [_i, _i]),
     'y2_region_loss_fwd_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     'y2_bn_bwd_workspace_bytes': (_sz, [_i, _i]),

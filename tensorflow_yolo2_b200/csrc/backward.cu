@@ -529,7 +529,7 @@ int y2_bn_leaky_pool_bwd(const float* h_raw, int ldh, const void* dy, int dy_dty
   Y2_LAUNCHED();
   const bool vec4 = (ld_dh % 4 == 0) && (ldh % 4 == 0) && (((uintptr_t)h_raw & 15) == 0) && (((uintptr_t)dh_bf16 & 7) == 0);
   const float invM = 1.0f / (float)M;
-  if (vec4 && C % 4 == 0 && units < (1ull << 31) && (((uintptr_t)dy) & 15) == 0 && !getenv("Y2_BN_BWD_GENERIC")) {
+  if (vec4 && C % 4 == 0 && units < (1ull << 31) && (((uintptr_t)dy) & 15) == 0 && !env().bn_bwd_generic) {
     const int cg = ld_dh / 4;
     const int bx = cg >= 64 ? 64 : (cg >= 32 ? 32 : (cg >= 16 ? 16 : 8));        // channel-group lanes per block
     const int by = 256 / bx;

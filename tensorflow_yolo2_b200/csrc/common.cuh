@@ -14,6 +14,19 @@ namespace y2 {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Debug / A-B switches (environment variables Y2_*), read ONCE per process (a launch used to pay ~10 getenv() calls);
+// y2_reload_env() re-reads them (tests and A/B runs that flip a switch inside one process).
+struct EnvSwitches {
+  bool bn_bwd_generic, conv_no_streamk, conv_streamk_1cta, conv_streamk_512, conv_force_streamk, conv_force_tiled,
+      conv_no_patch, conv_force_patch, conv_no_cta2, conv_no_cta2_generic, conv_cluster, conv_no_bstat, conv_no_kwmerge,
+      conv_no_tma_store, affine_generic, no_pdl;
+  int conv_streamk_min_ksteps;   // -1 = unset
+  int conv_block_n;              // 0 = unset
+  int conv1_debug;               // 0 = unset
+  int wgrad_splits;              // 0 = unset
+};
+const EnvSwitches& env();
+
 #define Y2_ARG(cond)                                                              \
   do {                                                                            \
     if (!(cond)) {                                                                \
@@ -60,8 +73,7 @@ static inline int fill_launch_attrs(cudaLaunchAttribute* attr, unsigned cluster)
   attr[n].val.clusterDim.y = 1;
   attr[n].val.clusterDim.z = 1;
   ++n;
-  static const bool no_pdl = getenv("Y2_NO_PDL") != nullptr;
-  if (!no_pdl) {
+  if (!env().no_pdl) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

@@ -422,7 +422,7 @@ static int conv1_u8_pool_launch(const uint8_t* img, const void* w_packed, const 
   Y2_ARG(total < (1ll << 31) - 1024);
   a.total_tiles = (int)total;
   a.alpha = alpha;
-  a.debug = getenv("Y2_CONV1_DEBUG") ? atoi(getenv("Y2_CONV1_DEBUG")) : 0;
+  a.debug = env().conv1_debug;
   CUtensorMap tmImg;
   {
     cuuint64_t dims[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)N};

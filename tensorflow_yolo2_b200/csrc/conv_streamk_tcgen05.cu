@@ -629,7 +629,6 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 static thread_local void* g_sk_ws = nullptr;
-static thread_local bool g_sk_flags_zeroed = false;             // first launch after registration clears the flags once
 static thread_local size_t g_sk_ws_bytes = 0;
 constexpr size_t SK_FLAG_BYTES = 4096;
 
@@ -638,7 +637,7 @@ static size_t sk_workspace_bytes(int sms) { return SK_FLAG_BYTES + (size_t)sms *
 // returns Y2_OK and sets *handled = 1 when the layer was issued on this path
 int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   *handled = 0;
-  if (getenv("Y2_CONV_NO_STREAMK") || g_sk_ws == nullptr) return Y2_OK;
+  if (env().conv_no_streamk || g_sk_ws == nullptr) return Y2_OK;
   if ((p->flags & Y2_CONV_POOL2) != 0) return Y2_OK;
   if (!(p->ksize == 1 || p->ksize == 3) || p->Cin % 64 != 0 || p->Cout % 256 != 0) return Y2_OK;
   if (p->H >= 64 && p->W >= 64) return Y2_OK;                   // large maps: the halo-patch mode of conv_tc_kernel wins
@@ -654,7 +653,7 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   const int lo_off = split_out ? (p->lo_off > 0 ? p->lo_off : p->Cout) : 0;
   if (split_out && ((lo_off & 7) != 0 || ldy < lo_off + p->Cout)) return Y2_OK;
   int min_ksteps = 18;                                          // short K: the epilogue starts to show
-  if (const char* e = getenv("Y2_CONV_STREAMK_MIN_KSTEPS")) min_ksteps = atoi(e);
+  if (env().conv_streamk_min_ksteps >= 0) min_ksteps = env().conv_streamk_min_ksteps;
   if (ksteps < min_ksteps || ksteps > SK_MAX_UNITS) return Y2_OK;
   int rc = load_driver_entry_points();
   if (rc != Y2_OK) return rc;
@@ -675,16 +674,16 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   fastdiv_init((uint32_t)cchunks, &a.fd_cc_mul, &a.fd_cc_shr);
   a.n_tiles = p->Cout / 256;
   // CTA-pair kernel (cta_group::2) unless disabled; 512-row pair tiles (two halves per CTA) unless disabled or too few tiles
-  const bool two_cta = !getenv("Y2_CONV_STREAMK_1CTA") && g_num_sms >= 2;
+  const bool two_cta = !env().conv_streamk_1cta && g_num_sms >= 2;
   int halves = 1;
   // 512-row pair tiles are opt-in (Y2_CONV_STREAMK_512=1): measured SLOWER on B200 (L19 149 vs 137 us, L6 116 vs 89 us) --
   // the un-overlapped epilogue, the shallower 4-stage ring and the coarser tile quantisation cost more than the 1.33x
   // fewer delivered bytes per flop bring
-  if (two_cta && getenv("Y2_CONV_STREAMK_512")) halves = 2;
+  if (two_cta && env().conv_streamk_512) halves = 2;
   const long long m_tiles = (a.M + 256 * halves - 1) / (256 * halves);
   a.tiles = (int)(m_tiles * a.n_tiles);
   a.units = (long long)a.tiles * ksteps;
-  if ((a.tiles < g_num_sms / 2 && !getenv("Y2_CONV_FORCE_STREAMK")) || a.units >= (1ll << 31) || a.M + 256 >= (1ll << 31)) return Y2_OK;
+  if ((a.tiles < g_num_sms / 2 && !env().conv_force_streamk) || a.units >= (1ll << 31) || a.M + 256 >= (1ll << 31)) return Y2_OK;
   // every CTA's range must be at least one tile long (a tile is then shared by at most two CTAs)
   // 74 pairs, every pair's range at least one tile long
   const int npairs = a.tiles < g_num_sms / 2 ? a.tiles : g_num_sms / 2;
@@ -726,11 +725,7 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
       return Y2_ERR_DRIVER;
     }
   }
-  if (!g_sk_flags_zeroed) {
-    // once per registered workspace: afterwards every launch leaves the flags zero (no memset node per layer)
-    Y2_CUDA(cudaMemsetAsync(a.ws_flags, 0, SK_FLAG_BYTES, st));
-    g_sk_flags_zeroed = true;
-  }
+  // (the flag area was zero when the workspace was registered -- the caller's contract -- and every launch leaves it zero)
   if (two_cta) {
     const size_t smem = (size_t)Sk2Cfg<1>::STAGES * Sk2Cfg<1>::STAGE + 8 * SK_STG_WARP + 1024;     // same for both variants
     static_assert(Sk2Cfg<1>::STAGES * Sk2Cfg<1>::STAGE == Sk2Cfg<2>::STAGES * Sk2Cfg<2>::STAGE, "operand smem");
@@ -782,6 +777,5 @@ extern "C" int y2_conv_set_workspace(void* workspace, size_t bytes) {
   Y2_ARG(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
   g_sk_ws = workspace;
   g_sk_ws_bytes = workspace ? bytes : 0;
-  g_sk_flags_zeroed = false;
   return Y2_OK;
 }

@@ -880,7 +880,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 PFN_encodeTiled g_encodeTiled = nullptr;
 PFN_encodeIm2col g_encodeIm2col = nullptr;
-int g_num_sms = 0;
+int num_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cache[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
+  }
+  return cache[dev];
+}
 int g_driver_version = 0;
 static std::mutex g_mu;
 
@@ -902,9 +913,6 @@ int load_driver_entry_points() {
     return Y2_ERR_DRIVER;
   }
   g_encodeIm2col = (PFN_encodeIm2col)fn;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDriverGetVersion(&g_driver_version);
   return Y2_OK;
 }
@@ -1052,11 +1060,11 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   }
   a.a_wrap = a.first_layer ? 1 : a_cin / a.kchunk;
   a.a_mode = pool ? 1 : 0;
-  if (getenv("Y2_CONV_FORCE_TILED")) a.a_mode = 1;
+  if (env().conv_force_tiled) a.a_mode = 1;
   // halo-patch mode for 3x3 layers on large maps: an 8 x 16 pixel tile whose (16+2)-row neighbourhood is
   // loaded once per horizontal tap (first layer: once in total) instead of once per tap
-  if (p->ksize == 3 && p->H >= 64 && p->W >= 64 && !getenv("Y2_CONV_NO_PATCH")) a.a_mode = 2;
-  if (getenv("Y2_CONV_FORCE_PATCH") && p->ksize == 3) a.a_mode = 2;
+  if (p->ksize == 3 && p->H >= 64 && p->W >= 64 && !env().conv_no_patch) a.a_mode = 2;
+  if (env().conv_force_patch && p->ksize == 3) a.a_mode = 2;
   int TW = 1, TH = 1, NB = 128;
   if (a.a_mode == 2) {
     TW = 8; TH = 16; NB = 1;
@@ -1085,8 +1093,8 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   }
   // halo-patch mode keeps three taps of B per stage: 256-wide tiles would leave room for a single stage
   if (a.a_mode == 2 && block_n == 256) block_n = 128;
-  if (const char* e = getenv("Y2_CONV_BLOCK_N")) {
-    int v = atoi(e);
+  if (env().conv_block_n) {
+    int v = env().conv_block_n;
     if ((v == 128 || v == 256) && cout_p >= v && !a.first_layer) block_n = v;
   }
   a.n_tiles = (cout_p + block_n - 1) / block_n;
@@ -1139,7 +1147,7 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   // pair each SM fetches its own A rows and HALF of the filters (80 / 96 clk).  Each CTA keeps half of the resident bank.
   a.cta2 = 0;
   if (a.a_mode == 2 && !a.first_layer && a.n_tiles == 1 && a.m_tiles >= 2 && block_n >= 64 && block_n <= 128 &&
-      ((block_n / 2) * a.row_bytes) % 1024 == 0 && !getenv("Y2_CONV_NO_CTA2")) {
+      ((block_n / 2) * a.row_bytes) % 1024 == 0 && !env().conv_no_cta2) {
     const uint32_t half = (uint32_t)(block_n / 2) * a.row_bytes;
     if ((size_t)a.kblocks * half + 4 * (size_t)a.a_stage_bytes <= SMEM_BUDGET) {
       a.cta2 = 1;
@@ -1149,8 +1157,8 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   }
   // ... and for the im2col / tiled-box modes with 128-byte rows and >= 128-wide tiles (pooled 52x52 / 26x26 layers, the
   // 1x1 layers): the filter tile is streamed, each CTA fetching its half of the rows per stage
-  if (a.a_mode != 2 && !a.first_layer && a.row_bytes == 128 && block_n >= 128 && a.m_tiles >= 2 && !getenv("Y2_CONV_NO_CTA2") &&
-      !getenv("Y2_CONV_NO_CTA2_GENERIC") && !getenv("Y2_CONV_CLUSTER")) {
+  if (a.a_mode != 2 && !a.first_layer && a.row_bytes == 128 && block_n >= 128 && a.m_tiles >= 2 && !env().conv_no_cta2 &&
+      !env().conv_no_cta2_generic && !env().conv_cluster) {
     a.cta2 = 1;
     a.b_sub_bytes = (uint32_t)(block_n / 2) * a.row_bytes;
     a.b_stage_bytes = (uint32_t)a.sps * a.b_sub_bytes;
@@ -1158,12 +1166,12 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   // B-stationary: with a single N tile and a small filter bank, every tile of the CTA needs the same B
   a.b_total_bytes = a.first_layer ? a.b_sub_bytes : (uint32_t)a.kblocks * a.b_sub_bytes;
   a.b_stationary = (a.n_tiles == 1 && a.b_total_bytes + 4 * (size_t)a.a_stage_bytes <= SMEM_BUDGET &&
-                    !getenv("Y2_CONV_NO_BSTAT")) ? 1 : 0;
+                    !env().conv_no_bstat) ? 1 : 0;
   // halo-patch mode with a resident filter bank and a single channel chunk (layer 2: Cin = 32): the three
   // horizontally shifted patches share ONE stage, so the MMA warp issues all 9 taps behind one barrier round trip.
   // With one patch per stage that warp's ~800 clk of per-stage bookkeeping hid 192 clk of tensor work (ncu, r1c).
   if (a.a_mode == 2 && !a.first_layer && a.b_stationary && a.cchunks == 1 &&
-      a.b_total_bytes + 3 * (size_t)(3 * a.a_sub_bytes) <= SMEM_BUDGET && !getenv("Y2_CONV_NO_KWMERGE")) {
+      a.b_total_bytes + 3 * (size_t)(3 * a.a_sub_bytes) <= SMEM_BUDGET && !env().conv_no_kwmerge) {
     a.kw_merge = 1;
     a.a_stage_bytes = 3 * a.a_sub_bytes;
     a.stages_per_tile = 1;
@@ -1178,7 +1186,7 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
     return Y2_ERR_UNSUPPORTED;
   }
   if (!a.first_layer && !a.b_stationary && a.m_tiles >= 2 && (a.b_sub_bytes / 2) % 1024 == 0 && block_n >= 64 &&
-      getenv("Y2_CONV_CLUSTER"))
+      env().conv_cluster)
     a.cluster = 2;
   // stages: B-stage must stay 1024-byte aligned for the 128B swizzle atoms
   uint32_t stage_bytes = a.a_stage_bytes + (a.b_stationary ? 0u : a.b_stage_bytes);
@@ -1191,7 +1199,7 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   a.tma_store = 0;
   if (a.a_mode == 2 && !a.first_layer && !pool && !out_f32 && !split_out && p->Cout % 32 == 0 && a.ldy % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(p->y) & 15) == 0 && EPI_GROUPS == 4 && block_n == 128 && a.row_bytes == 128 && a.cta2 &&
-      b_region + 3 * (size_t)stage_bytes + STG_BYTES <= SMEM_BUDGET && !getenv("Y2_CONV_NO_TMA_STORE"))
+      b_region + 3 * (size_t)stage_bytes + STG_BYTES <= SMEM_BUDGET && !env().conv_no_tma_store)
     a.tma_store = 1;
   const size_t stg_bytes = a.tma_store ? STG_BYTES : 0;
   int stages = (int)((SMEM_BUDGET - b_region - stg_bytes) / stage_bytes);

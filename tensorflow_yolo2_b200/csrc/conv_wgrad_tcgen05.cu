@@ -278,7 +278,7 @@ extern "C" int y2_conv_wgrad_bf16(const void* x, const void* dh, int ld_dh, floa
   int max_splits = a.kstages / 8;
   if (max_splits < 1) max_splits = 1;
   if (splits > max_splits) splits = max_splits;
-  if (const char* e = getenv("Y2_WGRAD_SPLITS")) { int v = atoi(e); if (v >= 1 && v <= a.kstages) splits = v; }
+  if (env().wgrad_splits) { int v = env().wgrad_splits; if (v >= 1 && v <= a.kstages) splits = v; }
   a.splits = splits;
   fastdiv_init((uint32_t)W, &a.fd_w_mul, &a.fd_w_shr);
   fastdiv_init((uint32_t)H, &a.fd_h_mul, &a.fd_h_shr);

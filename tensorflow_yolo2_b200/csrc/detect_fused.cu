@@ -253,11 +253,9 @@ extern "C" int y2_detect_fused(const float* net, const float* anchors, int N, in
   const size_t smem = df_smem_bytes(nbox, cells_per_chunk, A * (5 + C), C);
   Y2_ARG(smem <= 200 * 1024);
   cudaStream_t st = (cudaStream_t)stream;
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  // (a per-DEVICE function attribute: set on every launch that needs it -- one thread may drive several GPUs)
+  if (smem > 48 * 1024)
     Y2_CUDA(cudaFuncSetAttribute(detect_fused_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   detect_fused_kernel<20><<<N, DF_THREADS, smem, st>>>(net, anchors, S, A, score_thresh, iou_thresh, boxes, scores, keep_idx,
                                                        keep_count, keep_score, max_keep, cells_per_chunk, smem);
   Y2_LAUNCHED();

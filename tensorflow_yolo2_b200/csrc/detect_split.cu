@@ -338,11 +338,8 @@ extern "C" int y2_detect_split(const float* net, const float* anchors, int N, in
   int P = 1;
   while (P < nbox) P <<= 1;
   const size_t smem = (size_t)P * 8 + (size_t)nbox * sizeof(Corner) + 16 + 16 * 1024;   // small: three CTAs per SM
-  static thread_local size_t configured = 0;
-  if (smem > 32 * 1024 && smem > configured) {                  // static (10 KB) + dynamic beyond 48 KB needs the opt-in
-    Y2_CUDA(cudaFuncSetAttribute(detect_nms_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (smem > 32 * 1024)                                         // static (10 KB) + dynamic beyond 48 KB needs the opt-in
+    Y2_CUDA(cudaFuncSetAttribute(detect_nms_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
   detect_nms_kernel<20><<<N, DS_NMS_THREADS, smem, st>>>(boxes, scores, keys, cnt, nbox, score_thresh, iou_thresh, keep_idx,
                                                           keep_count, keep_score, max_keep, smem);
   Y2_LAUNCHED();

@@ -698,7 +698,7 @@ int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const flo
   cudaStream_t st = (cudaStream_t)stream;
   int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   if (!pool && !space_to_depth && out_dtype == 1 && C % 8 == 0 && ldx % 4 == 0 && ldo % 8 == 0 && lo_off % 8 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0 &&
-      (long long)N * H * W < (1ll << 30) && !getenv("Y2_AFFINE_GENERIC")) {
+      (long long)N * H * W < (1ll << 30) && !env().affine_generic) {
     const int M = N * H * W, C8 = C / 8;
     const int bx = C8 >= 128 ? 128 : ((C8 + 31) / 32) * 32;       // channel-group lanes per block (whole warps)
     const int by = 256 / bx;                                      // row lanes per block
@@ -712,7 +712,7 @@ int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const flo
     return Y2_OK;
   }
   if (pool && !space_to_depth && out_dtype == 1 && C % 8 == 0 && ldx % 4 == 0 && ldo % 8 == 0 && lo_off % 8 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0 &&
-      (long long)N * H * W < (1ll << 31) && !getenv("Y2_AFFINE_GENERIC")) {
+      (long long)N * H * W < (1ll << 31) && !env().affine_generic) {
     const unsigned units = (unsigned)((long long)N * Ho * Wo);
     const int C8 = C / 8;
     const int bx = C8 >= 32 ? 32 : (C8 >= 16 ? 16 : (C8 >= 8 ? 8 : 4));
@@ -727,7 +727,7 @@ int y2_affine_leaky_pool_ex(const float* x, int ldx, const float* sub, const flo
     return Y2_OK;
   }
   if (!pool && !space_to_depth && out_dtype == 0 && C <= 256 && (C % 4 != 0 || ldx % 4 != 0 || ldo % 4 != 0) &&
-      (long long)N * H * W < (1ll << 30) && !getenv("Y2_AFFINE_GENERIC")) {
+      (long long)N * H * W < (1ll << 30) && !env().affine_generic) {
     const int M = N * H * W;
     const int bx = ((C + 31) / 32) * 32, by = 256 / bx > 0 ? 256 / bx : 1;
     int gx = g_sms_elementwise() * 8;

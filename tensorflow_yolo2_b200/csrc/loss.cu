@@ -189,6 +189,27 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partials, int nb
   if (q == 0) terms[4] = (float)(s[0] + s[2] + s[3] + s[1]);   // :372 class + object + noobject + coord
 }
 
+// net_utils.py:337-342: the UNMASKED box deltas the reference logs as histograms (tf.summary.histogram('boxes_delta_x' ..
+// 'boxes_delta_h'), :366-369): predict (x, y, sqrt w, sqrt h) minus the cell-relative ground truth (:330-334), for every
+// cell and predictor.  deltas [N,S,S,B,4].
+__global__ void loss_v1_box_deltas_kernel(const float* __restrict__ net, const float* __restrict__ labels, int total, int S, int B,
+                                          int C, float image_size, float* __restrict__ deltas) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int b = t % B, cell = t / B;
+  const int j = cell % S, i = (cell / S) % S;
+  const float* p = net + (size_t)cell * (C + 5 * B) + C + B + 4 * b;
+  const float* lb = labels + (size_t)cell * (5 + C);
+  const float fS = (float)S;
+  const float gcx = lb[1] / image_size, gcy = lb[2] / image_size, gw = lb[3] / image_size, gh = lb[4] / image_size;
+  float4 d;
+  d.x = p[0] - (gcx * fS - (float)j);
+  d.y = p[1] - (gcy * fS - (float)i);
+  d.z = p[2] - sqrtf(gw);
+  d.w = p[3] - sqrtf(gh);
+  reinterpret_cast<float4*>(deltas)[t] = d;
+}
+
 }  // namespace y2
 
 using namespace y2;
@@ -234,4 +255,15 @@ int y2_loss_v1_fwd_bwd(const float* net, const float* labels, int N, int S, int 
   return Y2_OK;
 }
 
+int y2_loss_v1_box_deltas(const float* net, const float* labels, int N, int S, int B, int C, float image_size, float* deltas,
+                          y2_stream_t stream) {
+  Y2_ARG(net && labels && deltas && N > 0 && S > 0 && B > 0 && C > 0 && image_size > 0.0f);
+  Y2_ARG((reinterpret_cast<uintptr_t>(deltas) & 15) == 0);
+  const long long total = (long long)N * S * S * B;
+  Y2_ARG(total < (1ll << 31));
+  loss_v1_box_deltas_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(net, labels, (int)total, S, B, C,
+                                                                                              image_size, deltas);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
 }  // extern "C"

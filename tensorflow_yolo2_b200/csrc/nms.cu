@@ -57,11 +57,9 @@ int y2_nms(const float* boxes, const float* scores, int N, int nbox, int C, floa
     set_error("y2_nms: nbox=%d needs %zu B of shared memory (> 200 KB)", nbox, smem);
     return Y2_ERR_UNSUPPORTED;
   }
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  // (a per-DEVICE function attribute: set on every launch that needs it -- one thread may drive several GPUs)
+  if (smem > 48 * 1024)
     Y2_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   nms_kernel<<<N * C, NMS_THREADS, smem, (cudaStream_t)stream>>>(boxes, scores, nbox, C, score_thresh, iou_thresh,
                                                                  keep_idx, keep_count, max_keep, P);
   Y2_LAUNCHED();

@@ -234,7 +234,8 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 extern PFN_encodeTiled g_encodeTiled;
 extern PFN_encodeIm2col g_encodeIm2col;
-extern int g_num_sms;
+int num_sms();                    // SM count of the CURRENT device (cached per device ordinal)
+#define g_num_sms (::y2::num_sms())
 extern int g_driver_version;
 
 int load_driver_entry_points();   // defined in conv_tcgen05.cu

@@ -133,6 +133,8 @@ class Yolo2Engine:
                     max_ws = max(max_ws, ops.bn_stats_workspace_bytes(N * Hin * Hin, L['cout']))
                 H = Ho
             self.ws = torch.empty((max_ws,), dtype=torch.uint8, device=dev)
+            # this engine's own stream-K scratch (zero-filled flags): engines / trainers on other streams have theirs
+            self.conv_ws = ops.new_conv_workspace(dev)
             if decode == 'region':
                 assert self.OF % (5 + self.C) == 0
                 self.A = self.OF // (5 + self.C)
@@ -179,6 +181,10 @@ class Yolo2Engine:
 
     # ------------------------------------------------------------------------------------------
     def _enqueue(self):
+        with ops.conv_workspace_scope(self.conv_ws):
+            self._enqueue_body()
+
+    def _enqueue_body(self):
         st = self.store
         if self.fused_conv1:
             pass                                     # the first conv reads self.in_u8 directly

@@ -126,36 +126,67 @@ def conv_fwd_bf16(x, w_packed, ksize, cin, cout, scale=None, shift=None, leaky=T
     return out
 
 
-_conv_ws = {}
-
-
-def conv_workspace(device=None):
-    """Allocate (once per device) and register the stream-K scratch of y2_conv_fwd_bf16 for the calling thread."""
-    device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
-    ws = _conv_ws.get(device)
-    if ws is None:
-        with torch.cuda.device(device):
-            ws = torch.empty((int(_lib.load().y2_conv_workspace_bytes()),), dtype=torch.uint8, device=device)
-        _conv_ws[device] = ws
-    check(_lib.load().y2_conv_set_workspace(_p(ws), ws.numel()), 'y2_conv_set_workspace')
-    return ws
-
-
-def conv_clear_workspace():
-    _tls.conv_ws_device = None
-    check(_lib.load().y2_conv_set_workspace(None, 0), 'y2_conv_set_workspace')
-
-
+import contextlib as _contextlib
 import threading as _threading
 
+_conv_ws = {}
 _tls = _threading.local()
 
 
+def new_conv_workspace(device=None):
+    """A fresh, zero-filled stream-K scratch buffer (hand-over flags + partial accumulators) for y2_conv_fwd_bf16.  The
+    kernels leave the flags zero after every launch, so one buffer serves any number of launches -- as long as they are
+    serialised: launches that may run CONCURRENTLY (different streams, an engine next to a trainer) need different buffers."""
+    device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+    with torch.cuda.device(device):
+        return torch.zeros((int(_lib.load().y2_conv_workspace_bytes()),), dtype=torch.uint8, device=device)
+
+
+def _register_conv_workspace(ws):
+    """The C ABI keeps the registered scratch per calling thread."""
+    key = None if ws is None else (ws.data_ptr(), ws.numel())
+    if getattr(_tls, 'conv_ws_key', False) != key:
+        check(_lib.load().y2_conv_set_workspace(_p(ws), ws.numel() if ws is not None else 0), 'y2_conv_set_workspace')
+        _tls.conv_ws_key = key
+
+
+def conv_workspace(device=None):
+    """The default scratch of the calling context: one zero-filled buffer per (device, stream), registered for the thread."""
+    device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _conv_ws.get(key)
+    if ws is None:
+        ws = new_conv_workspace(device)
+        _conv_ws[key] = ws
+    _register_conv_workspace(ws)
+    return ws
+
+
+@_contextlib.contextmanager
+def conv_workspace_scope(ws):
+    """Issue the convolutions of the block with `ws` (from new_conv_workspace) as their scratch -- an engine or a trainer
+    owns one, whatever stream (or CUDA-graph capture) it is enqueued on."""
+    prev = getattr(_tls, 'conv_ws_pinned', None)
+    _tls.conv_ws_pinned = ws
+    _register_conv_workspace(ws)
+    try:
+        yield ws
+    finally:
+        _tls.conv_ws_pinned = prev
+        if prev is not None:
+            _register_conv_workspace(prev)
+
+
+def reload_env():
+    """Re-read the Y2_* environment switches of the launchers (they are cached once per process)."""
+    check(_lib.load().y2_reload_env(), 'y2_reload_env')
+
+
 def _ensure_conv_workspace(device):
-    """The C ABI keeps the registered scratch per calling thread: register this device's buffer once per thread."""
-    if getattr(_tls, 'conv_ws_device', None) != device:
+    if getattr(_tls, 'conv_ws_pinned', None) is not None:
+        _register_conv_workspace(_tls.conv_ws_pinned)
+    else:
         conv_workspace(device)
-        _tls.conv_ws_device = device
 
 
 def pack_weights_conv1_u8(w_hwio, scale=None, out=None):
@@ -456,6 +487,16 @@ def loss_v1(net, labels, S, B, C_, image_size, lambda_coord=5.0, lambda_noobj=0.
                                  lambda_coord, lambda_noobj, _p(terms), _p(ious), _p(object_mask), _p(dnet), _p(ws),
                                  ws.numel(), _stream()), 'y2_loss_v1_fwd_bwd')
     return terms, ious, object_mask, dnet
+
+
+def loss_v1_box_deltas(net, labels, S, B, C_, image_size, out=None):
+    """[N,S,S,B,4] unmasked (dx, dy, dw, dh) of get_loss (net_utils.py:337-342) -- the histogram summaries of :366-369."""
+    N = net.shape[0]
+    if out is None:
+        out = torch.empty((N, S, S, B, 4), dtype=torch.float32, device=net.device)
+    check(_lib.load().y2_loss_v1_box_deltas(_p(net, torch.float32), _p(labels, torch.float32), N, S, B, C_, float(image_size),
+                                            _p(out, torch.float32), _stream()), 'y2_loss_v1_box_deltas')
+    return out
 
 
 def region_loss(net, anchors, gt_boxes, gt_classes, gt_counts, C_=20, lambda_coord=1.0, lambda_obj=5.0, lambda_noobj=1.0,

@@ -27,7 +27,8 @@ from tensorflow_yolo2_b200.yolo2_nets.net_utils import (restore_checkpoint, rest
 from tensorflow_yolo2_b200.yolo2_nets.darknet import darknet19_core, darknet19_detection    # noqa: E402
 
 
-def main(argv):
+def main(argv, return_predicts=False):
+    """return_predicts=True also returns the [1,S,S,5B+C] network output the detections were decoded from (tests)."""
     image_path = argv[1] if len(argv) > 1 else os.path.join(cfg.ROOT_DIR, 'tests', 'golden', 'testImg2.jpg')
     IMAGE_SIZE, S, B = cfg.IMAGE_SIZE, cfg.S, cfg.B
     # create database instance (the reference needs VOCdevkit on disk even for detection, pascal_voc.py:36-39; the
@@ -59,7 +60,8 @@ def main(argv):
     grid_net = final_conv_layer.reshape(-1, S, S, 5 * B + NUM_CLASS)
 
     predicts = grid_net.float().cpu().numpy()
-    return show_yolo_detection(image_path, predicts, imdb, show='--no-show' not in argv)
+    dets = show_yolo_detection(image_path, predicts, imdb, show='--no-show' not in argv)
+    return (dets, predicts) if return_predicts else dets
 
 
 if __name__ == '__main__':

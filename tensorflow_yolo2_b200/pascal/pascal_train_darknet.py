@@ -25,7 +25,8 @@ from tensorflow_yolo2_b200.img_dataset.pascal_voc import pascal_voc             
 from tensorflow_yolo2_b200.trainer import Yolo2Trainer                                      # noqa: E402
 from tensorflow_yolo2_b200.utils.timer import Timer                                         # noqa: E402
 from tensorflow_yolo2_b200.variables import default_store                                   # noqa: E402
-from tensorflow_yolo2_b200.yolo2_nets.net_utils import restore_darknet19_variables, save_checkpoint   # noqa: E402
+from tensorflow_yolo2_b200.yolo2_nets.net_utils import (latest_checkpoint, restore_darknet19_variables,   # noqa: E402
+                                                       save_checkpoint)
 
 # set hyper parameters (:23-28)
 ADD_ITER = 80000
@@ -36,9 +37,9 @@ SNAPSHOT_EVERY = 40000
 class _SyntheticVoc(pascal_voc):
     """Random batches with the label layout of pascal_voc.load_pascal_annotation (pascal_voc.py:125-165)."""
 
-    def __init__(self, batch_size):
+    def __init__(self, batch_size, rank=0):
         pascal_voc.__init__(self, 'trainval', batch_size=batch_size, require_data=False)
-        self._rs = np.random.RandomState(0)
+        self._rs = np.random.RandomState(rank)           # every rank draws its own batches
 
     def get(self):
         IS, S = self.image_size, self.cell_size
@@ -59,6 +60,7 @@ class _SyntheticVoc(pascal_voc):
 
 def main(argv):
     add_iter = int(argv[argv.index('--iters') + 1]) if '--iters' in argv else ADD_ITER
+    snapshot_every = int(argv[argv.index('--snapshot-every') + 1]) if '--snapshot-every' in argv else SNAPSHOT_EVERY
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -67,7 +69,17 @@ def main(argv):
         torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local))
     IMAGE_SIZE, S, B = cfg.IMAGE_SIZE, cfg.S, cfg.B
     # create database instance
-    imdb = _SyntheticVoc(BATCH_SIZE) if '--synthetic' in argv else pascal_voc('trainval', batch_size=BATCH_SIZE, rebuild=cfg.REBUILD)
+    if '--synthetic' in argv:
+        imdb = _SyntheticVoc(BATCH_SIZE, rank)
+    else:
+        # data parallel: one common-seed shuffle, then rank r takes records r, r + world, ... (disjoint shards; the
+        # reference is single-process and reshuffles with the global, unseeded np.random -- pascal_voc.py:56,84)
+        if world > 1:
+            np.random.seed(cfg.__dict__.get('SHUFFLE_SEED', 0))
+        imdb = pascal_voc('trainval', batch_size=BATCH_SIZE, rebuild=cfg.REBUILD)
+        if world > 1:
+            imdb.gt_labels = imdb.gt_labels[rank::world]
+            np.random.seed(cfg.__dict__.get('SHUFFLE_SEED', 0) + 1 + rank)
     NUM_CLASS = imdb.num_class
     CKPTS_DIR = cfg.get_ckpts_dir('darknet19', imdb.name)
 
@@ -77,6 +89,11 @@ def main(argv):
                            lambda_coord=float(cfg.LAMBDA_COORD), lambda_noobj=float(cfg.LAMBDA_NOOBJ),
                            device=torch.device('cuda', local))
     last_iter_num = restore_darknet19_variables(None, imdb, net_name='darknet19', save_epoch=False)
+    if last_iter_num > 0:
+        # tf.train.Saver() restores every global variable (:54,83): Adam's slots and beta powers come back with the weights
+        slots = trainer.load_optimizer_state(latest_checkpoint(imdb, 'darknet19', save_epoch=False) + '.npz', iteration=last_iter_num)
+        if not slots and rank == 0:
+            print('snapshot holds no optimizer state: Adam restarts from zero moments at t = %d' % last_iter_num)
 
     writer = None
     if rank == 0:
@@ -103,10 +120,12 @@ def main(argv):
             _time = T.toc(average=False)
             print('iter {:d}/{:d}, total loss: {:.3}, take {:.2}s'.format(i, TOTAL_ITER, float(t[4]), _time))
             T.tic()
-        if i % SNAPSHOT_EVERY == 0 and rank == 0:
-            save_path = save_checkpoint(os.path.join(CKPTS_DIR, cfg.TRAIN_SNAPSHOT_PREFIX + '_iter_' + str(i) + '.ckpt'),
-                                        store)
-            print("Model saved in file: %s" % save_path)
+        if i % snapshot_every == 0:
+            trainer.sync_moving_statistics()                   # (a collective: every rank takes part)
+            if rank == 0:
+                save_path = save_checkpoint(os.path.join(CKPTS_DIR, cfg.TRAIN_SNAPSHOT_PREFIX + '_iter_' + str(i) + '.ckpt'),
+                                            store, extra=trainer.optimizer_state())
+                print("Model saved in file: %s" % save_path)
     if world > 1:
         torch.distributed.destroy_process_group()
     return trainer

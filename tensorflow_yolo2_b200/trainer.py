@@ -154,6 +154,7 @@ class Yolo2Trainer:
                 (int(ops._lib.load().y2_conv_packed_weight_dgrad_elems(k, cin, ld_dh)),), **bf16))
             H = Ho
         self.ws = torch.empty((max_ws,), dtype=torch.uint8, device=dev)
+        self.conv_ws = ops.new_conv_workspace(dev)          # this trainer's own stream-K scratch (see ops.conv_workspace_scope)
         self.dh = torch.empty((max_dh,), **bf16)
         self.dx = [torch.empty((max_dx,), **bf16), torch.empty((max_dx,), **bf16)]
         S = self.S
@@ -270,11 +271,62 @@ class Yolo2Trainer:
                 if self.in_f32 is None:
                     self.in_f32 = torch.empty((self.N, self.IS, self.IS, 3), dtype=torch.float32, device=self.device)
                 self.in_f32.copy_(t.to(torch.float32), non_blocking=True)
-        self.forward()
-        self.loss()
-        self.backward(capture)
-        self.update()
+        with ops.conv_workspace_scope(self.conv_ws):
+            self.forward()
+            self.loss()
+            self.backward(capture)
+            self.update()
         return self.terms
+
+    # ---- checkpoint state beyond the variables (tf.train.Saver() saves ALL global variables: pascal_train_darknet.py:54,111) ----
+    def optimizer_state(self):
+        """Adam's slot variables under the names TF gives them (`<var>/Adam` = m, `<var>/Adam_1` = v) plus `beta1_power`,
+        `beta2_power` -- what the reference's Saver writes next to the weights -- and the iteration count.  Pass the dict as
+        `extra=` to net_utils.save_checkpoint; `load_optimizer_state` is the inverse.  Without them a resumed run would
+        restart Adam from zero moments and a bias correction at t = 1."""
+        out = {}
+        for li, L in enumerate(self.layers):
+            sl = self.slots[li]
+            for key, nm in zip(('W', 'b', 'gamma', 'beta'), (L['W'], L['b'], L['bn']['gamma'], L['bn']['beta'])):
+                o, n, shp = sl[key]
+                out[nm + '/Adam'] = self.adam_m[o:o + n].view(shp).detach().cpu().numpy()
+                out[nm + '/Adam_1'] = self.adam_v[o:o + n].view(shp).detach().cpu().numpy()
+        out['beta1_power'] = np.float32(self.beta1 ** (self.iteration + 1))      # TF holds beta^(t+1) after t updates
+        out['beta2_power'] = np.float32(self.beta2 ** (self.iteration + 1))
+        out['y2_iteration'] = np.int64(self.iteration)
+        return out
+
+    def load_optimizer_state(self, npz_path, iteration=None):
+        """Restore what optimizer_state() saved.  Returns the list of slot names found; slots absent from the file (a
+        warm start from an ImageNet snapshot, a weights-only file) keep their zero initial value."""
+        data = np.load(npz_path)
+        found = []
+        for li, L in enumerate(self.layers):
+            sl = self.slots[li]
+            for key, nm in zip(('W', 'b', 'gamma', 'beta'), (L['W'], L['b'], L['bn']['gamma'], L['bn']['beta'])):
+                o, n, shp = sl[key]
+                for suffix, arena in (('/Adam', self.adam_m), ('/Adam_1', self.adam_v)):
+                    if nm + suffix in data.files:
+                        arena[o:o + n].view(shp).copy_(torch.as_tensor(data[nm + suffix], dtype=torch.float32))
+                        found.append(nm + suffix)
+        if iteration is not None:
+            self.iteration = int(iteration)
+        elif 'y2_iteration' in data.files:
+            self.iteration = int(data['y2_iteration'])
+        elif 'beta1_power' in data.files:
+            self.iteration = int(round(np.log(float(data['beta1_power'])) / np.log(self.beta1))) - 1
+        return found
+
+    def sync_moving_statistics(self):
+        """Average the BN moving means / variances over the ranks (each rank tracks its own shard's statistics; the
+        reference is single-device, so any consistent choice is an extension).  Called before rank 0 writes a snapshot."""
+        if self.world <= 1:
+            return
+        for L in self.layers:
+            for nm in (L['bn']['moving_mean'], L['bn']['moving_variance']):
+                t = self.store[nm]
+                torch.distributed.all_reduce(t, group=self.pg)
+                t.mul_(1.0 / self.world)
 
     # helpers for tests / checkpoints
     def gradient(self, li, key):

@@ -69,6 +69,7 @@ class VariableStore:
     def reset_name_counters(self):
         """Start a `reuse=True` pass: the same call sequence regenerates the same names."""
         self._counters = {}
+        self._scope_uses = {}        # (parent prefix, scope name) -> times entered without reuse (TF opens name_1, name_2, ...)
 
     # -- creation -------------------------------------------------------------------------
     def get_or_create(self, name, init_fn):

@@ -206,15 +206,26 @@ def conv_bn_layer(x, filter_size, input_chl, output_chl, stride, is_training, _p
 # builders (darknet.py:126-201)
 # ---------------------------------------------------------------------------------------------
 class _variable_scope:
-    """tf.variable_scope(scope, default, [inputs], reuse=reuse): reuse=True replays the same
-    auto-generated names so the existing variables are found."""
+    """tf.variable_scope(scope, default, [inputs], reuse=reuse) for the reference's UNNAMED variables (tf.Variable(initial),
+    darknet.py:12,17), whose names come from the name scope: entering the same scope a second time without reuse opens
+    `<scope>_1/` in TF (so a second darknet19_core call creates darknet19_1/Variable, ...), and so it does here.
+    reuse=True replays the auto-generated names of the first pass so that the existing variables are found (the
+    drop-in scripts build once, restore the checkpoint, then run with reuse=True)."""
 
     def __init__(self, name, reuse=None):
         self.name, self.reuse = name, reuse
         self.store = default_store()
 
     def __enter__(self):
-        self.ctx = self.store.scope(self.name)
+        name = self.name
+        if not self.reuse:
+            uses = self.store.__dict__.setdefault('_scope_uses', {})
+            full = (self.store._prefix(), name)
+            k = uses.get(full, 0)
+            uses[full] = k + 1
+            if k:
+                name = '%s_%d' % (name, k)
+        self.ctx = self.store.scope(name)
         self.ctx.__enter__()
         if self.reuse:
             prefix = self.store._prefix()

@@ -61,6 +61,12 @@ def restore_checkpoint(path, store=None):
     return store.load_npz(path + '.npz')
 
 
+def latest_checkpoint(imdb, net_name='darknet19', save_epoch=True):
+    """Path (without .npz) of the newest snapshot restore_darknet19_variables would pick, or None."""
+    sfiles = get_ordered_ckpts(None, imdb, net_name, save_epoch=save_epoch)
+    return str(sfiles[-1]) if sfiles else None
+
+
 def restore_darknet19_variables(sess, imdb, net_name='darknet19', save_epoch=True):
     """net_utils.py:64-110.  No snapshot for this dataset -> warm-start from the newest ImageNet
     snapshot by variable-name intersection (the rest keep their initial values) and return 0;

@@ -31,3 +31,17 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _y2_env_switches_reloaded():
+    """The library caches its Y2_* environment switches once per process; tests that flip one call ops.reload_env().  This
+    runs after monkeypatch has restored the environment and brings the cache back in line with it."""
+    yield
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from tensorflow_yolo2_b200 import ops
+            ops.reload_env()
+    except Exception:
+        pass

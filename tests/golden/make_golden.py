@@ -309,6 +309,16 @@ def gen_labels(cfg, out):
         res['image_%d_checksum' % IS] = np.array([images.sum(), np.abs(images).sum(), images[0, 5, 7, 1]])
         if IS == 224:
             res['image_224'] = images[0].astype(np.float32)
+        if IS == 416:
+            # cfg.FLIPPED = True (config.py:47 ships False): prepare() appends the mirrored records (pascal_voc.py:69-86)
+            cfg.FLIPPED = True
+            imdb_f = pv.pascal_voc('trainval', batch_size=1, rebuild=True)
+            cfg.FLIPPED = False
+            rec = [r for r in imdb_f.gt_labels if r['flipped']]
+            assert len(imdb_f.gt_labels) == 2 and len(rec) == 1
+            res['label_416_13_flipped'] = rec[0]['label']
+            im_f = imdb_f.image_read(rec[0]['imname'], True)
+            res['image_416_flipped_checksum'] = np.array([im_f.sum(), np.abs(im_f).sum(), im_f[5, 7, 1]])
         shutil.rmtree(d)
     np.savez_compressed(os.path.join(out, 'ref_labels.npz'), **res)
     set_grid(cfg, 224, 7, 2)

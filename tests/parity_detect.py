@@ -47,14 +47,40 @@ def oracle_end_to_end(img_u8, core_p, head_p, score_thresh, iou_thresh, chunk=8,
             if want_inter:
                 inter.append(h.to(torch.float32).numpy())
     net = h.numpy()
-    boxes, sthr, _ = O.region_decode_v2(net.astype(np.float32), O.VOC_ANCHORS, 20, score_thresh)
+    boxes, sthr, sraw = O.region_decode_v2(net.astype(np.float32), O.VOC_ANCHORS, 20, score_thresh)
     # decode from the float64 net (region_decode_v2 computes in float64 from float32 input; feed the rounded net so the
     # oracle's own decode input is what a float32 TF graph would hold)
     keeps = [O.nms_per_class(boxes[n], sthr[n], iou_thresh, score_thresh) for n in range(N)]
-    return dict(net=net, boxes=boxes, scores=sthr, keeps=keeps, inter=inter)
+    return dict(net=net, boxes=boxes, scores=sthr, scores_raw=sraw, keeps=keeps, inter=inter, score_thresh=score_thresh,
+                iou_thresh=iou_thresh)
 
 
-def compare(engine_out, oracle_out, num_class=20):
+def _explain_diff(n, k, got, want, oracle_out, edge):
+    """Why do two keep lists differ?  Every box in the symmetric difference must be (a) a score within `edge` (relative)
+    of the score threshold, (b) a box whose IoU with some kept box of the class is within `edge` of the IoU threshold, or
+    (c) a consequence: it overlaps (IoU > threshold) another box of the difference (kept / dropped because that one
+    flipped).  Returns the number of boxes with none of these explanations."""
+    thr, ithr = oracle_out['score_thresh'], oracle_out['iou_thresh']
+    boxes = oracle_out['boxes'][n]
+    diff = sorted(set(got) ^ set(want))
+    union = sorted(set(got) | set(want))
+    unexplained = 0
+    for b in diff:
+        s0 = float(oracle_out['scores_raw'][n, b, k])
+        if abs(s0 - thr) <= edge * thr:
+            continue
+        others = [u for u in union if u != b]
+        if others:
+            iou = O.get_iou(np.broadcast_to(boxes[b], (len(others), 4)), boxes[others])
+            if np.any(np.abs(iou - ithr) <= edge):
+                continue
+            if any(o in diff and i > ithr for o, i in zip(others, iou)):
+                continue
+        unexplained += 1
+    return unexplained
+
+
+def compare(engine_out, oracle_out, num_class=20, edge=2e-3):
     """engine_out: dict(net, boxes, scores, keep_idx, keep_count) numpy; oracle_out from oracle_end_to_end."""
     net, wnet = engine_out['net'].astype(np.float64), oracle_out['net']
     N = net.shape[0]
@@ -64,6 +90,7 @@ def compare(engine_out, oracle_out, num_class=20):
     inter_n = union_n = 0
     s_err, b_err = [], []
     n_or = n_en = 0
+    unexplained = 0
     for n in range(N):
         for k in range(num_class):
             got = [int(v) for v in ki[n, k, :kc[n, k]]]
@@ -75,6 +102,8 @@ def compare(engine_out, oracle_out, num_class=20):
             lists_total += 1
             lists_same += int(got == want)
             sg, sw = set(got), set(want)
+            if sg != sw:
+                unexplained += _explain_diff(n, k, got, want, oracle_out, edge)
             inter_n += len(sg & sw)
             union_n += len(sg | sw)
             for b in sg & sw:
@@ -86,6 +115,7 @@ def compare(engine_out, oracle_out, num_class=20):
     res.update(detections_oracle=n_or, detections_engine=n_en, nonempty_lists=lists_total,
                keep_lists_identical=(lists_same / lists_total) if lists_total else 1.0,
                detections_jaccard=(inter_n / union_n) if union_n else 1.0, matched=int(len(s_err)),
+               unexplained_list_differences=int(unexplained),
                score_rel_max=float(s_err.max()) if len(s_err) else 0.0,
                score_rel_rms=float(np.sqrt(np.mean(s_err ** 2))) if len(s_err) else 0.0,
                box_rel_max=float(b_err.max()) if len(b_err) else 0.0,

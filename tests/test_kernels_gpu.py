@@ -95,6 +95,7 @@ def test_conv_halo_pair_vs_single_cta_and_oracle(ops, monkeypatch, N, H, W, Cin,
     kw = dict(scale=cu(sc), shift=cu(b), leaky=True, pool=pool)
     got = ops.conv_fwd_bf16(xb, wp, 3, Cin, Cout, **kw)
     monkeypatch.setenv('Y2_CONV_NO_CTA2', '1')
+    ops.reload_env()                     # the launchers cache the Y2_* switches
     ref = ops.conv_fwd_bf16(xb, wp, 3, Cin, Cout, **kw)
     torch.cuda.synchronize()
     assert torch.equal(got, ref)
@@ -123,8 +124,10 @@ def test_conv_generic_pair_vs_single_cta(ops, monkeypatch, N, S, Cin, Cout, k, p
     kw = dict(scale=None if out_f32 else sc, shift=cu(rs.randn(Cout).astype(np.float32)), leaky=not out_f32, pool=pool,
               out_f32=out_f32, ldy=ld if out_f32 else None)
     monkeypatch.setenv('Y2_CONV_NO_STREAMK', '1')
+    ops.reload_env()                     # the launchers cache the Y2_* switches
     got = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw)
     monkeypatch.setenv('Y2_CONV_NO_CTA2', '1')
+    ops.reload_env()                     # the launchers cache the Y2_* switches
     ref = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw)
     torch.cuda.synchronize()
     g, r = got.reshape(-1, got.shape[-1])[:, :Cout], ref.reshape(-1, ref.shape[-1])[:, :Cout]
@@ -153,11 +156,13 @@ def test_conv_streamk_vs_generic_and_oracle(ops, monkeypatch, N, S, Cin, Cout, k
     wp = ops.pack_weights_bf16(cu(w))
     kw = dict(scale=None if sc is None else cu(sc), shift=cu(b), leaky=not out_f32, out_f32=out_f32)
     monkeypatch.setenv('Y2_CONV_NO_STREAMK', '1')
+    ops.reload_env()                     # the launchers cache the Y2_* switches
     ref = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw).float().cpu().numpy().reshape(-1, Cout)
     monkeypatch.delenv('Y2_CONV_NO_STREAMK')
     monkeypatch.setenv('Y2_CONV_FORCE_STREAMK', '1')           # small test shapes have fewer tiles than the auto rule wants
     if S == 19:
         monkeypatch.setenv('Y2_CONV_STREAMK_512', '1')         # ... and exercise the two-halves variant on a small shape too
+    ops.reload_env()                         # the launchers cache the Y2_* switches
     got1 = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw)
     got2 = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, **kw)
     torch.cuda.synchronize()
@@ -205,6 +210,7 @@ def test_affine_rows_fast_path_equals_generic(ops, monkeypatch, C, ld, ldo, col)
     for generic in (False, True):
         if generic:
             monkeypatch.setenv('Y2_AFFINE_GENERIC', '1')
+            ops.reload_env()                     # the launchers cache the Y2_* switches
         out = torch.zeros((N, S, S, ldo or C), dtype=torch.bfloat16, device='cuda')
         ops.affine_leaky_pool(x, N, S, S, C, ldx=ld, sub=sub, scale=sc, shift=sh, leaky=True, out_bf16=True, out=out,
                               ldo=ldo, out_col=col)
@@ -487,3 +493,42 @@ def test_detect_fused_overflow_falls_back_to_bitmatrix_kernel(ops, impl):
     _, _, _, kc2, _ = detect(cu(net), an, 20, 1e-12, 0.45, max_keep=845, want_scores=False)
     torch.cuda.synchronize()
     assert (kc2.cpu().numpy()[0] == -1).all()
+
+
+# ---------------------------------------------------------------------------------- a7 standalone + histogram deltas
+def test_iou_vs_reference_golden(ops, golden_dir):
+    """y2_iou / ops.iou / net_utils.get_iou against the golden emitted by the reference's own get_iou (net_utils.py:222-260)
+    -- including the SURVEY 8c KATs baked into the fixture (1.0, 0.25, 0.0, 1/3, zero area)."""
+    from tensorflow_yolo2_b200.yolo2_nets import net_utils as nu
+    g = np.load(os.path.join(golden_dir, 'ref_iou.npz'))
+    b1, b2 = g['boxes1'].astype(np.float32), g['boxes2'].astype(np.float32)
+    got = ops.iou(cu(b1), cu(b2)).cpu().numpy()
+    assert got.shape == g['iou'].shape
+    np.testing.assert_allclose(got, g['iou'], atol=2e-6)                     # golden is the float64 graph
+    want32 = O.get_iou(b1, b2)                                               # same op order in float32: bit-exact
+    np.testing.assert_array_equal(got, want32)
+    assert got[0, 0, 0, 0] == 1.0 and got[0, 0, 2, 0] == 0.0 and got[0, 1, 1, 0] == 0.0
+    assert abs(got[0, 0, 1, 0] - 0.25) < 1e-6 and abs(got[0, 1, 0, 0] - 1.0 / 3.0) < 1e-6
+    got2 = nu.get_iou(cu(b1), cu(b2)).cpu().numpy()                          # the drop-in entry point
+    np.testing.assert_array_equal(got2, got)
+    # a big ragged batch: 1e6 random pairs, property = oracle bit-exactness on a strided sample + range
+    rs = np.random.RandomState(3)
+    a, b = rs.uniform(0, 1, (1000003, 4)).astype(np.float32), rs.uniform(0, 1, (1000003, 4)).astype(np.float32)
+    big = ops.iou(cu(a), cu(b)).cpu().numpy()
+    assert big.min() >= 0.0 and big.max() <= 1.0
+    np.testing.assert_array_equal(big[::997], O.get_iou(a[::997], b[::997]))
+
+
+def test_loss_box_deltas_histogram_inputs(ops, golden_dir):
+    """y2_loss_v1_box_deltas = the tensors behind tf.summary.histogram('boxes_delta_x' .. 'boxes_delta_h')
+    (net_utils.py:337-342,366-369), against a NumPy restatement of those lines."""
+    g = np.load(os.path.join(golden_dir, 'ref_loss.npz'))
+    net, lab = g['rand13_net'].astype(np.float32), g['rand13_labels'].astype(np.float32)
+    N, S, B, C, IS = net.shape[0], 13, 5, 20, 416.0
+    got = ops.loss_v1_box_deltas(cu(net), cu(lab), S, B, C, IS).cpu().numpy()
+    pb = net[..., C + B:].reshape(N, S, S, B, 4)
+    gt = np.tile((lab[..., 1:5] / np.float32(IS))[:, :, :, None, :], (1, 1, 1, B, 1))
+    off = np.tile(np.arange(S, dtype=np.float32)[None, None, :, None], (N, S, 1, B))      # offset[y, x, b] = x
+    want = np.stack([pb[..., 0] - (gt[..., 0] * S - off), pb[..., 1] - (gt[..., 1] * S - off.transpose(0, 2, 1, 3)),
+                     pb[..., 2] - np.sqrt(gt[..., 2]), pb[..., 3] - np.sqrt(gt[..., 3])], axis=-1)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)

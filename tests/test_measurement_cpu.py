@@ -32,6 +32,7 @@ def test_algorithmic_flops_match_survey(bench):
 
 def test_bench_config_follows_image_size(bench):
     cfg = bench.make_config(2)
+    assert cfg['precision'] == 'bf16' and bench.make_config(1, 'bf16x3')['precision'] == 'bf16x3'
     assert cfg['image_size'] == 416 and cfg['global_batch'] == 128 and 'configs[1]' in cfg['workload']
     bench.IMAGE_SIZE, bench.BATCH_PER_GPU = 608, 32
     cfg = bench.make_config(1)
@@ -63,6 +64,7 @@ def test_launch_list_condenser(tmp_path):
     assert d['conv_launches_per_step'] == 2 and d['launches_per_step'] == 3
     assert d['conv_dram_bytes_per_step'] == 1000 + 2000 + 3000 + 4000
     assert abs(d['conv_share_of_step_under_ncu'] - 0.8) < 1e-9
-    step = (tmp_path / 'x_launches_bench_step.csv').read_text().splitlines()
+    assert d['precision'] == 'bf16'
+    step = (tmp_path / 'x_launches_bench_step_bf16.csv').read_text().splitlines()
     assert step[0].startswith('id,kernel') and len(step) == 1 + 5
     assert '"conv_streamk2_kernel<1>"' in step[3]

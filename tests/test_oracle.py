@@ -108,10 +108,6 @@ def test_decode_golden(golden_dir, name, S, B):
     assert texts == [str(t) for t in g[name + '_texts']]
 
 
-def _params_from_store(store_names_vals, plan, scope_fn):
-    raise NotImplementedError
-
-
 def build_params(output_filter, seed=0):
     """Create variables in the reference's order through the product's VariableStore and hand
     them to the oracle as torch tensors."""

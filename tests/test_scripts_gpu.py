@@ -41,3 +41,67 @@ def test_train_script_synthetic_three_iterations(fresh_env, capsys):
     assert 'iter 10/10, total loss:' in out
     assert tr.iteration == 10 and tr.N == 24 and tr.OF == 30
     assert np.isfinite(float(tr.terms[4]))
+
+
+def test_detect_script_detections_equal_oracle_decode_of_its_own_net(fresh_env, golden_dir):
+    """The detect script end to end (image read / resize / preprocess, builders, reshape, show_yolo_detection) against the
+    oracle's restatement of net_utils.py:393-421 (decode + the reference's integer draw arithmetic) on the script's own
+    network output: same boxes, classes and confidences, in the reference's loop order."""
+    from PIL import Image
+    from oracle import yolo2_oracle as O
+    from tensorflow_yolo2_b200 import config as cfg
+    from tensorflow_yolo2_b200.pascal import pascal_detect_darknet as script
+    img = os.path.join(golden_dir, 'testImg2.jpg')
+    dets, predicts = script.main(['pascal_detect_darknet.py', img, '--no-show'], return_predicts=True)
+    assert predicts.shape == (1, cfg.S, cfg.S, 5 * cfg.B + 20)
+    im_w, im_h = Image.open(img).size
+    for thresh in (0.5, 0.0):
+        from tensorflow_yolo2_b200.yolo2_nets.net_utils import decode_yolo_detection
+        got = decode_yolo_detection(predicts, im_w, im_h, 20, cfg.S, cfg.B, object_thresh=thresh)
+        want = O.draw_list_ref_v1(O.decode_ref_v1(predicts[0], cfg.S, cfg.B, 20, thresh), im_w, im_h)
+        assert len(got) == len(want)
+        if thresh == 0.5:
+            assert [tuple(d[:5]) for d in dets] == [tuple(int(v) for v in w[:5]) for w in want]
+        for g, w in zip(got, want):
+            assert tuple(g[:5]) == tuple(int(v) for v in w[:5])          # integer pixel arithmetic: exact
+            assert np.float32(g[5]) == np.float32(w[5])
+    assert len(got) > 0                                                  # thresh 0 -> every predictor with conf > 0
+
+
+def test_train_script_snapshot_and_resume_restores_adam_state(fresh_env, capsys):
+    """pascal_train_darknet.py:83-86,111-114: snapshot at iteration N, then a second run resumes at N + 1 with the weights,
+    BN moving statistics AND Adam's slot variables / step count the Saver would have restored."""
+    from tensorflow_yolo2_b200 import variables
+    from tensorflow_yolo2_b200.pascal import pascal_train_darknet as script
+    tr = script.main(['pascal_train_darknet.py', '--synthetic', '--iters', '4', '--snapshot-every', '4'])
+    torch.cuda.synchronize()
+    assert 'Model saved in file' in capsys.readouterr().out
+    params, m, v = tr.params.clone(), tr.adam_m.clone(), tr.adam_v.clone()
+    mm = tr.store[tr.layers[3]['bn']['moving_mean']].clone()
+    assert float(m.abs().sum()) > 0 and float(v.abs().sum()) > 0
+    variables.reset_default_store(seed=123)                                # a fresh process: different initial weights
+    tr2 = script.main(['pascal_train_darknet.py', '--synthetic', '--iters', '0'])
+    out = capsys.readouterr().out
+    assert 'Restored.' in out
+    assert tr2.iteration == 4
+    assert torch.equal(tr2.params, params) and torch.equal(tr2.adam_m, m) and torch.equal(tr2.adam_v, v)
+    assert torch.equal(tr2.store[tr2.layers[3]['bn']['moving_mean']], mm)
+    # and the next step is bit-identical to continuing the first run (same batch, same state)
+    img = np.random.RandomState(5).uniform(-1, 1, (tr.N, tr.IS, tr.IS, 3))
+    lab = np.zeros((tr.N, tr.S, tr.S, 25))
+    lab[:, 3, 3, 0] = 1
+    lab[:, 3, 3, 1:5] = [100, 100, 50, 60]
+    lab[:, 3, 3, 7] = 1
+    for t in (tr, tr2):
+        t.set_labels(lab)
+        t.step(img)
+    torch.cuda.synchronize()
+    assert tr.iteration == tr2.iteration == 5
+    # (the weight-gradient kernel reduces its split-K partials with float atomics, so two runs agree to rounding, not bits)
+    assert float((tr.params - params).abs().max()) > 5e-4                  # the step moved the weights by ~lr ...
+    assert float((tr.params - tr2.params).abs().max()) < 5e-5              # ... the same way in both runs
+    fresh = script.Yolo2Trainer(tr.N, tr.IS, tr.OF, store=variables.VariableStore(seed=0), loss='v1', B=tr.B)
+    fresh.params.copy_(params)                                             # same weights but NO optimizer state: differs
+    fresh.set_labels(lab)
+    fresh.step(img)
+    assert float((fresh.params - tr.params).abs().max()) > 2e-4

@@ -293,6 +293,7 @@ def test_bn_bwd_apply_rows_equals_generic(ops, monkeypatch, pool, dy_bf16, C, ld
         if generic:
             monkeypatch.setenv('Y2_BN_BWD_GENERIC', '1')
             monkeypatch.setenv('Y2_AFFINE_GENERIC', '1')
+            ops.reload_env()                     # the launchers cache the Y2_* switches
         dg, db, dh = ops.bn_leaky_pool_bwd(h, dy, mean, var, gamma, beta, N, H, W, C, ldh=ld, leaky=True, pool=pool, ld_dh=ld)
         fwd = None
         if C % 8 == 0:

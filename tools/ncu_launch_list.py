@@ -2,20 +2,24 @@
 """Condense an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list of
 `bench.py --no-graph` into the two files profiles/ keeps per round:
 
-    python tools/ncu_launch_list.py gpurun_out/launches_infer.csv profiles/r1c
+    python tools/ncu_launch_list.py gpurun_out/launches_infer.csv profiles/r2a [bf16|bf16x3]
 
-writes  <prefix>_launches_bench_step.csv   one bench step (flush memset .. next flush memset): id, kernel, us, DRAM bytes
-        <prefix>_traffic.json              DRAM bytes of the conv launches of that step (bench.py's roofline.traffic) and
-                                           the convs' share of the step under ncu
+writes  <prefix>_launches_bench_step_<precision>.csv   one bench step (flush memset .. next flush memset): id, kernel, us, DRAM bytes
+        <prefix>_traffic_<precision>.json              DRAM bytes of the conv launches of that step (bench.py's
+                                                       roofline.traffic), the convs' share of the step under ncu, and the
+                                                       git HEAD the library was built from (env Y2_HEAD, set by
+                                                       tools/profile_step.sh)
 """
 import csv
 import json
+import os
 import re
 import sys
 
 
 def main():
     src, prefix = sys.argv[1], sys.argv[2]
+    precision = sys.argv[3] if len(sys.argv) > 3 else 'bf16'
     rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
     hdr = rows[0]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -46,9 +50,14 @@ def main():
     # one step = from a flush memset (FillFunctor<unsigned char>) to the next one, taking the LAST complete step
     flushes = [i for i, l in enumerate(seq) if 'FillFunctor<unsigned char>' in l['kernel']]
     assert len(flushes) >= 2, 'need two L2-flush launches to delimit a step'
-    a, b = flushes[-2], flushes[-1]
+    # intervals between consecutive flushes; some hold several steps (bench.py's e2e loop does not flush): take the LAST
+    # interval of the most common length, i.e. exactly one step
+    spans = [(flushes[i], flushes[i + 1]) for i in range(len(flushes) - 1) if flushes[i + 1] - flushes[i] > 2]
+    lengths = [y - x for x, y in spans]
+    mode = max(set(lengths), key=lambda v: (lengths.count(v), -v))
+    a, b = [sp for sp in spans if sp[1] - sp[0] == mode][-1]
     step = seq[a:b + 1]
-    with open(prefix + '_launches_bench_step.csv', 'w') as f:
+    with open(prefix + '_launches_bench_step_%s.csv' % precision, 'w') as f:
         f.write('id,kernel,grid_time_us,dram_read_bytes,dram_write_bytes\n')
         for l in step:
             f.write('%d,"%s",%.3f,%d,%d\n' % (l['id'], l['kernel'], l['us'], l.get('dram__bytes_read.sum', 0),
@@ -59,10 +68,11 @@ def main():
     t_conv = sum(l['us'] for l in convs)
     out = dict(conv_dram_bytes_per_step=sum(l.get('dram__bytes_read.sum', 0) + l.get('dram__bytes_write.sum', 0) for l in convs),
                conv_launches_per_step=len(convs), launches_per_step=len(body), step_us_under_ncu=t_all,
-               conv_share_of_step_under_ncu=t_conv / t_all,
-               source='%s_launches_bench_step.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,'
-                      'dram__bytes_write.sum --clock-control none, python bench.py --steps 3 --warmup 3 --no-graph)' % prefix)
-    json.dump(out, open(prefix + '_traffic.json', 'w'), indent=1)
+               conv_share_of_step_under_ncu=t_conv / t_all, precision=precision, head=os.environ.get('Y2_HEAD'),
+               source='%s_launches_bench_step_%s.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,'
+                      'dram__bytes_write.sum --clock-control none, python bench.py --steps 3 --warmup 3 --no-graph '
+                      '--single-mode --precision %s)' % (os.path.basename(prefix), precision, precision))
+    json.dump(out, open(prefix + '_traffic_%s.json' % precision, 'w'), indent=1)
     print(json.dumps(out))
 
 
