@@ -405,6 +405,223 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# --mode train: BASELINE.json configs[4] -- one training step (forward with batch-statistics BN in all 22 layers, the
+# reference's get_loss, backward, [N > 1: bucketed NCCL gradient all-reduce overlapped with backward], Adam)
+# ------------------------------------------------------------------------------------------------
+TRAIN_METRIC = 'images/sec Darknet19-YOLO2 416x416 training step (fwd+loss+bwd+allreduce+Adam)'
+
+
+def train_config(world, loss):
+    return dict(workload='Darknet19-YOLO2 %dx%d training step, fused %s loss fwd/bwd, synthetic uint8 batch %d per GPU, '
+                         'data-parallel NCCL gradient all-reduce (BASELINE.json configs[4])'
+                         % (IMAGE_SIZE, IMAGE_SIZE, 'YOLO (net_utils.get_loss, C+5B = 45 channels)' if loss == 'v1' else 'region (125 channels)',
+                            BATCH_PER_GPU),
+                global_batch=world * BATCH_PER_GPU, image_size=IMAGE_SIZE, loss=loss, optimizer='Adam (TF defaults)',
+                bn='batch statistics in all 22 layers, per-rank', l2='flushed (256 MiB memset) between timed steps',
+                parallelism='data parallel x%d' % world, precision='bf16')
+
+
+def synthetic_labels(rs, N, S, IS, loss, max_gt=32):
+    """per image 1-3 GT boxes, cx,cy ~ U(0,IS), w,h ~ U(20,300), class ~ U{0..19}."""
+    import numpy as np
+    if loss == 'v1':
+        lab = np.zeros((N, S, S, 25), dtype=np.float32)
+        for n in range(N):
+            for _ in range(rs.randint(1, 4)):
+                cx, cy = rs.uniform(0, IS, 2)
+                w, h = rs.uniform(20, 300, 2)
+                j, i = min(int(cx * S / IS), S - 1), min(int(cy * S / IS), S - 1)
+                if lab[n, i, j, 0] == 0:                       # first object wins a cell (pascal_voc.py:159-160)
+                    lab[n, i, j, 0] = 1
+                    lab[n, i, j, 1:5] = [cx, cy, w, h]
+                    lab[n, i, j, 5 + rs.randint(0, 20)] = 1
+        return lab
+    cnt = rs.randint(1, 4, N).astype(np.int32)
+    bx = np.zeros((N, max_gt, 4), dtype=np.float32)
+    bx[:, :3] = np.stack([rs.uniform(0.05, 0.95, (N, 3)), rs.uniform(0.05, 0.95, (N, 3)), rs.uniform(0.05, 0.7, (N, 3)),
+                          rs.uniform(0.05, 0.7, (N, 3))], axis=-1)
+    return bx, rs.randint(0, 20, (N, max_gt)).astype(np.int32), cnt
+
+
+def cpu_train_step(batch, threads, reps=1, seed=0):
+    """The oracle's restatement of one reference training iteration (forward is_training=True, get_loss, autograd backward;
+    pascal_train_darknet.py:96-102) on torch-CPU float32 -- cpu_baseline / --impl reference only."""
+    import numpy as np
+    import torch
+    from oracle import yolo2_oracle as O
+    from tests.helpers import make_store, oracle_params
+    torch.set_num_threads(threads)
+    S = IMAGE_SIZE // 32
+    st, layers = make_store(45, seed=seed, tame=True)
+    core_p, head_p = oracle_params(st, layers)
+    rs = np.random.RandomState(seed)
+    img = rs.randint(0, 256, (batch, IMAGE_SIZE, IMAGE_SIZE, 3)).astype(np.uint8)
+    lab = torch.tensor(synthetic_labels(rs, batch, S, IMAGE_SIZE, 'v1'))
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.train_step_reference(O.preprocess_u8(img), core_p, head_p,
+                               lambda net: O.loss_v1_graph(net, lab.to(net.dtype), 20, batch, IMAGE_SIZE, S, 5)[0],
+                               bf16_operands=False, dtype=torch.float32)
+        times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference_train(args):
+    if int(os.environ.get('RANK', 0)) != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_batch = 4
+    t_all, threads = cpu_train_step(sample_batch, cores, reps=args.warmup + args.steps)
+    timed = t_all[args.warmup:]
+    value = sample_batch * len(timed) / sum(timed)
+    sample = 'batch %d of %dx%d per step (bounded sample of the batch-%d step), torch-CPU fp32 autograd restatement' % (
+        sample_batch, IMAGE_SIZE, IMAGE_SIZE, BATCH_PER_GPU)
+    line = dict(metric=TRAIN_METRIC.replace('416x416', '%dx%d' % (IMAGE_SIZE, IMAGE_SIZE)), value=value, unit='images/s',
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * sum(timed) / len(timed),
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                config=train_config(max(args.gpus, 1), args.loss),
+                cpu_baseline=dict(value=value, unit='images/s', cores=threads, kind='port', sample=sample),
+                e2e=dict(value=value, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def run_train(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tensorflow_yolo2_b200 import ops
+    from tensorflow_yolo2_b200.trainer import Yolo2Trainer
+    from tests.helpers import make_store
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    N, IS = BATCH_PER_GPU, IMAGE_SIZE
+    S = IS // 32
+    of = 45 if args.loss == 'v1' else 125
+    st, _ = make_store(of, tame=True)                 # He-scaled weights: a training run that does not overflow in step 1
+    tr = Yolo2Trainer(N, IS, of, store=st, loss=args.loss, B=5, device=dev, use_cuda_graph=not args.no_graph)
+    rs = np.random.RandomState(1234 + rank)
+    host_imgs = [torch.tensor(rs.randint(0, 256, (N, IS, IS, 3)).astype(np.uint8)).pin_memory() for _ in range(2)]
+    dev_imgs = [b.to(dev) for b in host_imgs]
+    labs = synthetic_labels(rs, N, S, IS, args.loss)
+    if args.loss == 'v1':
+        host_lab = torch.tensor(labs).pin_memory()
+        tr.set_labels(host_lab)
+    else:
+        tr.set_ground_truth(*labs)
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(ms):
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def one_step(i, timed):
+        tr.in_u8.copy_(dev_imgs[i % 2])
+        flush.zero_()
+        if not timed:
+            tr.step()
+            return None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        tr.step()
+        e1.record(stream)
+        return e0, e1
+
+    for i in range(max(args.warmup, 3)):
+        one_step(i, False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count()
+    t_wall0 = time.perf_counter()
+    evs = [one_step(i, True) for i in range(args.steps)]
+    launches = ops.launch_count() - n0
+    barrier()
+    timed_region_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = allmax(sum(a.elapsed_time(b) for a, b in evs))
+    ms_per_step = t_ms / args.steps
+    value = world * N * args.steps / (t_ms * 1e-3)
+
+    # ---- e2e: pinned host images (+ labels) -> H2D -> step -> D2H of the five loss terms, every step ----
+    terms_host = torch.empty((5,), dtype=torch.float32).pin_memory()
+    h2d = host_imgs[0].numel() + (host_lab.numel() * 4 if args.loss == 'v1' else 0)
+
+    def e2e_step(i):
+        if args.loss == 'v1':
+            tr.labels.copy_(host_lab, non_blocking=True)
+        terms = tr.step(host_imgs[i % 2])
+        terms_host.copy_(terms, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record(stream)
+    barrier()
+    e2e_value = world * N * args.steps / (allmax(e0.elapsed_time(e1)) * 1e-3)
+    final_loss = float(terms_host[4])
+
+    # ---- phases (eager, events between them) and the exposed part of the all-reduce ----
+    phases = tr.phase_times(iters=3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    flops_img, _ = conv_flops_per_image(IS, of)
+    alg = 3.0 * N * flops_img                                   # forward + data gradient + weight gradient
+    regime = 'burst' if timed_region_s < 1.0 else 'sustained'
+    achieved = alg / (ms_per_step * 1e-3) / 1e12
+    roofline = dict(bound='tensor', achieved=achieved, peak=peaks[regime], unit='TFLOP/s', frac=achieved / peaks[regime], regime=regime,
+                    frac_vs_burst=achieved / peaks['burst'], frac_vs_sustained=achieved / peaks['sustained'],
+                    peak_source=peaks['which'] + ' ' + regime + ' bf16', traffic=None,
+                    algorithmic_flops_per_step=alg,
+                    kernel='conv_tc / conv_streamk2 (forward + dgrad) + conv_wgrad_tc; whole step in the denominator',
+                    note='achieved = 3 x forward conv FLOPs of the batch / device-timed step (BN, loss, Adam and the all-reduce included)')
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            times, threads = cpu_train_step(2, os.cpu_count() or 1, reps=2)
+            cpu = dict(value=2 / min(times), unit='images/s', cores=threads, kind='port',
+                       sample='batch 2 of %dx%d, one training iteration (fwd + get_loss + autograd bwd), best of 2, torch-CPU fp32' % (IS, IS))
+        except Exception as e:  # noqa: BLE001
+            cpu = dict(value=None, unit='images/s', cores=os.cpu_count(), kind='port', sample='failed: %r' % (e,))
+    line = dict(metric=TRAIN_METRIC.replace('416x416', '%dx%d' % (IS, IS)), value=value, unit='images/s', n_gpus=world,
+                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='bf16', data='synthetic', config=train_config(world, args.loss),
+                e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=20),
+                gpu_launches=int(tr.launches_per_step * args.steps if tr.graph is not None else launches),
+                launches_per_step=int(tr.launches_per_step if tr.graph is not None else launches // max(args.steps, 1)),
+                cuda_graph=tr.graph is not None, roofline=roofline, cpu_baseline=cpu, clocks=clocks, phases_ms=phases,
+                allreduce=dict(bytes_per_step=int(tr.arena_elems * 4) if world > 1 else 0, buckets=len(tr.buckets) if world > 1 else 0,
+                               exposed_ms=phases.get('allreduce_exposed')),
+                final_loss=final_loss)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def conv_share_live(eng, ops, flush, iters=5):
     """Share of the step spent in the 22 conv launches, measured live: the step is captured into a CUDA graph with
     event-record NODES (torch.cuda.Event(external=True)) before and after every conv launch and at both ends, replayed
@@ -460,6 +677,9 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help='infer: the headline metric (BASELINE configs[1]/[3]); train: one training step (configs[4])')
+    ap.add_argument('--loss', default='v1', choices=['v1', 'region'], help='--mode train: the reference get_loss (45 ch) or the region loss (125 ch)')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3'],
                     help="mode that produces value / e2e / roofline (config.precision); the other mode is timed too and "
                          "reported under precision_modes unless --single-mode")
@@ -475,7 +695,9 @@ def main():
         IMAGE_SIZE = args.image_size
     if args.batch:
         BATCH_PER_GPU = args.batch
-    if args.impl == 'reference':
+    if args.mode == 'train':
+        (run_reference_train if args.impl == 'reference' else run_train)(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)

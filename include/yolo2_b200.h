@@ -177,6 +177,11 @@ int y2_maxpool2x2_bf16(const void* x, void* y, int N, int H, int W, int C, y2_st
 /* tf.nn.avg_pool / tf.layers.average_pooling2d with ksize == stride, evenly divisible map (darknet.py:28-29,116: the
  * 7x7 global pool of the darknet19 classifier).  x NHWC (x_dtype 0 = f32, 1 = bf16) -> y f32 [N,H/k,W/k,C]. */
 int y2_avgpool(const void* x, int x_dtype, float* y, int N, int H, int W, int C, int k, y2_stream_t stream);
+/* dtype plumbing of the drop-in builders: x_dtype / y_dtype 0 = float32, 1 = bf16 (they must differ); n elements. */
+int y2_cast(const void* x, int x_dtype, void* y, int y_dtype, size_t n, y2_stream_t stream);
+/* y = x * (*scalar), scalar in DEVICE memory -- the chain rule of get_loss's backward (d loss/d net times the upstream
+ * gradient of the scalar loss) without a host synchronisation. */
+int y2_scale_by_device_scalar(const float* x, const float* scalar, float* y, size_t n, y2_stream_t stream);
 
 /* ---- a8: grid decode of show_yolo_detection (yolo2_nets/net_utils.py:393-407,418) -----------
  * net [N,S,S,C+5B] f32.  boxes [N,S,S,B,4] = ((x+j)/S, (y+i)/S, w^2, h^2); conf [N,S,S,B];
@@ -281,6 +286,12 @@ int y2_sum_rows_bf16(const void* a_bf16, int ld, size_t M, int C, float* out, y2
  * p -= lr_t * m / (sqrt(v) + eps), lr_t = lr * sqrt(1-b2^t)/(1-b1^t) computed by the caller. */
 int y2_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1,
                  float beta2, float eps, y2_stream_t stream);
+/* The training step's form: g is scaled by grad_scale on the fly (1/world of the data-parallel mean), the step size comes
+ * from device memory when lr_t_dev != NULL (a CUDA graph of the step then carries no iteration-dependent constant), and
+ * with zero_grad != 0 the gradient arena is cleared behind the read (the weight-gradient kernels accumulate into it).
+ * n % 4 == 0, all pointers 16-byte aligned. */
+int y2_adam_step_ex(float* p, float* g, float* m, float* v, size_t n, float lr_t, const float* lr_t_dev, float beta1,
+                    float beta2, float eps, float grad_scale, int zero_grad, y2_stream_t stream);
 
 #ifdef __cplusplus
 }

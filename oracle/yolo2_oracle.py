@@ -411,22 +411,22 @@ def get_loss_torch(net, labels, num_class, batch_size, image_size, S, B,
     return float(loss), net.grad.numpy()
 
 
-def train_step_reference(x_nhwc, params_core, params_head, loss_fn, bf16_operands=True):
+def train_step_reference(x_nhwc, params_core, params_head, loss_fn, bf16_operands=True, dtype=torch.float64):
     """One iteration of pascal_train_darknet.py:96-102 up to the gradients: forward with is_training=True in
     every layer (:36,39-40 feed is_training=True), loss, backward (TF autodiff == torch autograd on the same
     graph).  loss_fn(net float64 tensor) -> scalar tensor.  Returns (loss, grads) with grads a list (layer order)
     of dict(W, b, gamma, beta) float64 numpy arrays, plus the per-layer batch (mean, var)."""
     leaves = []
     for p in list(params_core) + list(params_head):
-        q = {k: torch.as_tensor(np.asarray(v), dtype=torch.float64).clone() for k, v in p.items()}
+        q = {k: torch.as_tensor(np.asarray(v), dtype=dtype).clone() for k, v in p.items()}
         for k in ('W', 'b', 'gamma', 'beta'):
             q[k].requires_grad_(True)
         leaves.append(q)
     nc = len(params_core)
-    x = torch.as_tensor(np.asarray(x_nhwc), dtype=torch.float64)
+    x = torch.as_tensor(np.asarray(x_nhwc), dtype=dtype)
     stats = []
     for li, q in enumerate(leaves):
-        x, h, _ = conv_bn_layer(x, q, True, torch.float64, bf16_operands)
+        x, h, _ = conv_bn_layer(x, q, True, dtype, bf16_operands)
         stats.append((h.detach().mean(dim=(0, 1, 2)).numpy(), h.detach().var(dim=(0, 1, 2), unbiased=False).numpy()))
         if li < nc and CORE_PLAN[li][3]:
             x = max_pool_2x2(x)

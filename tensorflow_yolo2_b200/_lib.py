@@ -53,6 +53,8 @@ _SIGNATURES = {
     'y2_affine_leaky_pool_ex': (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'y2_maxpool2x2_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'y2_avgpool': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    'y2_cast': (_i, [_vp, _i, _vp, _i, _sz, _vp]),
+    'y2_scale_by_device_scalar': (_i, [_vp, _vp, _vp, _sz, _vp]),
     'y2_decode_ref_v1': (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     'y2_decode_region': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     'y2_nms_workspace_bytes': (_sz, [_i, _i, _i]),
@@ -75,6 +77,7 @@ _SIGNATURES = {
     'y2_conv_wgrad_c3': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'y2_sum_rows_bf16': (_i, [_vp, _i, _sz, _i, _vp, _vp]),
     'y2_adam_step': (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _vp]),
+    'y2_adam_step_ex': (_i, [_vp, _vp, _vp, _vp, _sz, _f, _vp, _f, _f, _f, _f, _i, _vp]),
 }
 
 _lib = None

@@ -532,6 +532,58 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// The training step's form of the same update, 16 bytes per access: the gradient is scaled on the fly (the 1/world of the
+// data-parallel mean: the all-reduce delivers the SUM), the step size may come from device memory (so that a CUDA graph
+// of the step does not bake the bias correction of one iteration in), and the gradient arena is cleared behind the read
+// (the weight-gradient kernels accumulate into it, and this kernel is its last reader) -- no separate 193 MB memset / scale.
+__global__ void __launch_bounds__(256) adam_ex_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                                      float4* __restrict__ v, size_t n4, float lr_t, const float* __restrict__ lr_dev,
+                                                      float b1, float b2, float eps, float gscale, int zero_grad) {
+  const float lr = lr_dev ? *lr_dev : lr_t;
+  const float c1 = 1.0f - b1, c2 = 1.0f - b2;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
+    gi.x *= gscale; gi.y *= gscale; gi.z *= gscale; gi.w *= gscale;
+    mi.x = b1 * mi.x + c1 * gi.x; mi.y = b1 * mi.y + c1 * gi.y; mi.z = b1 * mi.z + c1 * gi.z; mi.w = b1 * mi.w + c1 * gi.w;
+    vi.x = b2 * vi.x + c2 * gi.x * gi.x; vi.y = b2 * vi.y + c2 * gi.y * gi.y;
+    vi.z = b2 * vi.z + c2 * gi.z * gi.z; vi.w = b2 * vi.w + c2 * gi.w * gi.w;
+    pi.x -= lr * mi.x / (sqrtf(vi.x) + eps); pi.y -= lr * mi.y / (sqrtf(vi.y) + eps);
+    pi.z -= lr * mi.z / (sqrtf(vi.z) + eps); pi.w -= lr * mi.w / (sqrtf(vi.w) + eps);
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// dtype plumbing of the drop-in builders (float32 <-> bf16, 8 elements per thread where aligned) and the chain-rule scale of
+// get_loss's backward (dnet * upstream scalar, the scalar read from device memory: no host sync)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8, stride = (size_t)gridDim.x * blockDim.x * 8;
+  for (; i < n; i += stride) {
+    if (i + 8 <= n && ((((uintptr_t)(x + i)) & 15) == 0) && ((((uintptr_t)(y + i)) & 15) == 0)) {
+      const float4 a = *reinterpret_cast<const float4*>(x + i), b = *reinterpret_cast<const float4*>(x + i + 4);
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+      *reinterpret_cast<uint4*>(y + i) = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                                    *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+    } else {
+      for (size_t j = i; j < n && j < i + 8; ++j) y[j] = __float2bfloat16_rn(x[j]);
+    }
+  }
+}
+
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = __bfloat162float(x[i]);
+}
+
+__global__ void scale_by_device_scalar_kernel(const float* __restrict__ x, const float* __restrict__ s, float* __restrict__ y, size_t n) {
+  const float sv = *s;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = x[i] * sv;
+}
+
 static int g_sms_elementwise() {
   static int sms = 0;
   if (!sms) {
@@ -780,10 +832,36 @@ int y2_avgpool(const void* x, int x_dtype, float* y, int N, int H, int W, int C,
   return Y2_OK;
 }
 
+int y2_cast(const void* x, int x_dtype, void* y, int y_dtype, size_t n, y2_stream_t stream) {
+  Y2_ARG(x && y && n > 0 && (x_dtype == 0 || x_dtype == 1) && (y_dtype == 0 || y_dtype == 1) && x_dtype != y_dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == 0) cast_f32_bf16_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, n);
+  else cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, n);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_scale_by_device_scalar(const float* x, const float* scalar, float* y, size_t n, y2_stream_t stream) {
+  Y2_ARG(x && scalar && y && n > 0);
+  scale_by_device_scalar_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, scalar, y, n);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
 int y2_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
                  float eps, y2_stream_t stream) {
   Y2_ARG(p && g && m && v && n > 0);
   adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_t, beta1, beta2, eps);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_adam_step_ex(float* p, float* g, float* m, float* v, size_t n, float lr_t, const float* lr_t_dev, float beta1,
+                    float beta2, float eps, float grad_scale, int zero_grad, y2_stream_t stream) {
+  Y2_ARG(p && g && m && v && n > 0 && n % 4 == 0);
+  Y2_ARG(((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0);
+  adam_ex_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n / 4, lr_t,
+                                                                         lr_t_dev, beta1, beta2, eps, grad_scale, zero_grad);
   Y2_LAUNCHED();
   return Y2_OK;
 }

@@ -345,6 +345,28 @@ def avg_pool(x, k):
     return out
 
 
+def cast(x, dtype):
+    """float32 <-> bfloat16 through y2_cast (the builders' dtype plumbing; no library kernel on the path)."""
+    if x.dtype == dtype:
+        return x
+    code = {torch.float32: 0, torch.bfloat16: 1}
+    if x.dtype not in code or dtype not in code:
+        raise _lib.Y2Error('cast: only float32 <-> bfloat16')
+    x = x if x.is_contiguous() else x.contiguous()
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    check(_lib.load().y2_cast(_p(x), code[x.dtype], _p(out), code[dtype], x.numel(), _stream()), 'y2_cast')
+    return out
+
+
+def scale_by_device_scalar(x, scalar, out=None):
+    """x * scalar with the scalar (a 0-d / 1-element float32 CUDA tensor) read on the device."""
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().y2_scale_by_device_scalar(_p(x, torch.float32), _p(scalar.reshape(1), torch.float32), _p(out, torch.float32),
+                                                x.numel(), _stream()), 'y2_scale_by_device_scalar')
+    return out
+
+
 # ---- a8 / a' -------------------------------------------------------------------------------
 def decode_ref_v1(net, S, B, C_, thresh=0.5):
     N = net.shape[0]
@@ -601,3 +623,16 @@ def adam_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
     lr_t = lr * (1.0 - b2 ** step) ** 0.5 / (1.0 - b1 ** step)
     check(_lib.load().y2_adam_step(_p(p, torch.float32), _p(g, torch.float32), _p(m, torch.float32),
                                    _p(v, torch.float32), p.numel(), lr_t, b1, b2, eps, _stream()), 'y2_adam_step')
+
+
+def adam_lr_t(step, lr=1e-3, b1=0.9, b2=0.999):
+    """TF's AdamOptimizer step size at iteration `step` (1-based): lr * sqrt(1 - b2^t) / (1 - b1^t)."""
+    return lr * (1.0 - b2 ** step) ** 0.5 / (1.0 - b1 ** step)
+
+
+def adam_step_ex(p, g, m, v, lr_t=0.0, lr_t_dev=None, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, zero_grad=False):
+    """y2_adam_step_ex: Adam with the gradient scaled on the fly, the step size optionally read from a device scalar, and the
+    gradient arena cleared behind the read."""
+    check(_lib.load().y2_adam_step_ex(_p(p, torch.float32), _p(g, torch.float32), _p(m, torch.float32), _p(v, torch.float32),
+                                      p.numel(), float(lr_t), _p(lr_t_dev, torch.float32), b1, b2, eps, float(grad_scale),
+                                      1 if zero_grad else 0, _stream()), 'y2_adam_step_ex')

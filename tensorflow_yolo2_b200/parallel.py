@@ -57,11 +57,13 @@ class BucketedAllReduce:
             self.works.append(dist.all_reduce(self.flat[b['start']:b['end']], group=self.group, async_op=True))
             self.next += 1
 
-    def finish(self):
-        """Wait for all buckets and turn the sums into means."""
+    def finish(self, scale=True):
+        """Wait for all buckets; scale=True turns the sums into means here (one pass over the arena), scale=False leaves the
+        SUMS for a consumer that applies 1/world itself (the trainer's update kernel does, y2_adam_step_ex's grad_scale)."""
         if self.world <= 1:
             return
         assert self.next == len(self.buckets), 'not every bucket was launched'
         for w in self.works:
             w.wait()
-        self.flat.mul_(1.0 / self.world)
+        if scale:
+            self.flat.mul_(1.0 / self.world)

@@ -25,8 +25,8 @@ from tensorflow_yolo2_b200.img_dataset.pascal_voc import pascal_voc             
 from tensorflow_yolo2_b200.trainer import Yolo2Trainer                                      # noqa: E402
 from tensorflow_yolo2_b200.utils.timer import Timer                                         # noqa: E402
 from tensorflow_yolo2_b200.variables import default_store                                   # noqa: E402
-from tensorflow_yolo2_b200.yolo2_nets.net_utils import (latest_checkpoint, restore_darknet19_variables,   # noqa: E402
-                                                       save_checkpoint)
+from tensorflow_yolo2_b200.yolo2_nets.net_utils import (add_summary, latest_checkpoint, merged_summary,   # noqa: E402
+                                                       restore_darknet19_variables, save_checkpoint)
 
 # set hyper parameters (:23-28)
 ADD_ITER = 80000
@@ -61,6 +61,7 @@ class _SyntheticVoc(pascal_voc):
 def main(argv):
     add_iter = int(argv[argv.index('--iters') + 1]) if '--iters' in argv else ADD_ITER
     snapshot_every = int(argv[argv.index('--snapshot-every') + 1]) if '--snapshot-every' in argv else SNAPSHOT_EVERY
+    summary_every = int(argv[argv.index('--summary-every') + 1]) if '--summary-every' in argv else 1     # the reference: every iteration
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -111,11 +112,12 @@ def main(argv):
         image, gt_labels = imdb.get()
         trainer.set_labels(gt_labels)
         terms = trainer.step(image)
-        if writer is not None or i % 10 == 0:
+        if writer is not None and i % summary_every == 0:
+            # summary = sess.run(merged): 5 scalars + 5 histograms (net_utils.py:361-370, :47); add_summary every iteration (:104)
+            summary = merged_summary(trainer.acts[-1], trainer.labels, terms, trainer.ious, NUM_CLASS, IMAGE_SIZE, S, B)
+            add_summary(writer, summary, i)
+        if i % 10 == 0:
             t = terms.cpu().numpy()                            # class, coord, object, noobject, total (:361-364)
-        if writer is not None:
-            for name, v in zip(('class_loss', 'coord_loss', 'object_loss', 'noobject_loss', 'total_loss'), t):
-                writer.add_scalar(name, float(v), i)
         if i % 10 == 0 and rank == 0:
             _time = T.toc(average=False)
             print('iter {:d}/{:d}, total loss: {:.3}, take {:.2}s'.format(i, TOTAL_ITER, float(t[4]), _time))
@@ -126,6 +128,8 @@ def main(argv):
                 save_path = save_checkpoint(os.path.join(CKPTS_DIR, cfg.TRAIN_SNAPSHOT_PREFIX + '_iter_' + str(i) + '.ckpt'),
                                             store, extra=trainer.optimizer_state())
                 print("Model saved in file: %s" % save_path)
+    if writer is not None:
+        writer.close()
     if world > 1:
         torch.distributed.destroy_process_group()
     return trainer

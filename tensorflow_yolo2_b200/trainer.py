@@ -42,7 +42,8 @@ def _round_up(v, m):
 class Yolo2Trainer:
     def __init__(self, batch, image_size=416, output_filter=None, store=None, loss='v1', num_class=20, B=5,
                  anchors=VOC_ANCHORS, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, lambda_coord=None, lambda_noobj=None,
-                 max_gt=32, device=None, seed=0, process_group=None, bucket_bytes=48 << 20, update_moving=True):
+                 max_gt=32, device=None, seed=0, process_group=None, bucket_bytes=48 << 20, update_moving=True,
+                 use_cuda_graph=False):
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.N, self.IS = int(batch), int(image_size)
         assert self.IS % 32 == 0
@@ -74,6 +75,12 @@ class Yolo2Trainer:
         self.store = store if store is not None else VariableStore(seed=seed)
         self.layers = create_variables(self.store, self.OF)
         self.iteration = 0
+        # the whole step (forward, loss, backward, Adam: ~290 launches) replayed as ONE CUDA graph; single-process only --
+        # with world > 1 the NCCL buckets are issued eagerly on NCCL's stream so that they overlap the backward kernels
+        self.use_cuda_graph = bool(use_cuda_graph) and self.world == 1
+        self.graph = None
+        self.launches_per_step = 0
+        self._grads_clean = True                    # the gradient arena is all zero (fresh, or cleared by the last update)
         dev = self.device
         with torch.cuda.device(dev):
             self._build_arenas()
@@ -159,6 +166,8 @@ class Yolo2Trainer:
         self.dx = [torch.empty((max_dx,), **bf16), torch.empty((max_dx,), **bf16)]
         S = self.S
         self.terms = torch.zeros((5,), **f32)
+        self.lr_dev = torch.zeros((1,), **f32)              # Adam step size of the current iteration (read by the update kernel)
+        self._lr_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
         self.dnet = torch.empty((N, S, S, self.OF), **f32)
         if self.loss_kind == 'v1':
             self.labels = torch.zeros((N, S, S, 5 + self.C), **f32)
@@ -227,7 +236,9 @@ class Yolo2Trainer:
 
     def backward(self, capture=None):
         """capture: optional dict; receives {layer index: clone of the gradient w.r.t. that layer's output} (tests)."""
-        self.grads.zero_()
+        if not self._grads_clean:                   # (only when backward runs twice without an update in between: the
+            self.grads.zero_()                      #  update kernel leaves the arena cleared)
+        self._grads_clean = False
         nl = len(self.layers)
         dy = self.dnet
         self.reducer.begin()
@@ -251,13 +262,29 @@ class Yolo2Trainer:
                                   shift=None, leaky=False, pool=False, out=dx)
                 dy = dx
             self.reducer.layer_done(li)
-        self.reducer.finish()
+        self.reducer.finish(scale=False)            # sums; the 1/world of the mean is applied inside the update kernel
 
-    def update(self):
-        self.iteration += 1
-        ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.iteration, lr=self.lr, b1=self.beta1,
-                      b2=self.beta2, eps=self.eps)
+    def _set_lr(self):
+        """TF's bias-corrected step size of iteration self.iteration -> device scalar (a 4-byte async copy, outside the graph)."""
+        self._lr_host[0] = ops.adam_lr_t(self.iteration, self.lr, self.beta1, self.beta2)
+        self.lr_dev.copy_(self._lr_host, non_blocking=True)
+
+    def update(self, _lr_set=False, zero_grad=True):
+        """Adam on the (summed) gradients scaled by 1/world; clears the gradient arena behind the read (zero_grad=False keeps
+        the gradients readable -- tests; the next backward then clears the arena itself)."""
+        if not _lr_set:
+            self.iteration += 1
+            self._set_lr()
+        ops.adam_step_ex(self.params, self.grads, self.adam_m, self.adam_v, lr_t_dev=self.lr_dev, b1=self.beta1, b2=self.beta2,
+                         eps=self.eps, grad_scale=1.0 / self.world, zero_grad=zero_grad)
+        self._grads_clean = bool(zero_grad)
         self.store.version += 1
+
+    def _enqueue_step(self):
+        self.forward()
+        self.loss()
+        self.backward()
+        self.update(_lr_set=True)
 
     def step(self, images=None, capture=None):
         """One training iteration on the current stream.  images: uint8 [N,IS,IS,3] BGR (host or device) or None
@@ -271,12 +298,90 @@ class Yolo2Trainer:
                 if self.in_f32 is None:
                     self.in_f32 = torch.empty((self.N, self.IS, self.IS, 3), dtype=torch.float32, device=self.device)
                 self.in_f32.copy_(t.to(torch.float32), non_blocking=True)
+        self.iteration += 1
+        self._set_lr()
         with ops.conv_workspace_scope(self.conv_ws):
-            self.forward()
-            self.loss()
-            self.backward(capture)
-            self.update()
+            if not self.use_cuda_graph or capture is not None:
+                self.forward()
+                self.loss()
+                self.backward(capture)
+                self.update(_lr_set=True, zero_grad=capture is None)      # (a capturing caller reads the gradients afterwards)
+                return self.terms
+            if self.graph is None:
+                if not self._grads_clean:
+                    self.grads.zero_()
+                    self._grads_clean = True
+                # warm-up outside the capture (function attributes, workspaces), then restore what it changed: the weights,
+                # the Adam moments and the BN moving statistics must see this iteration exactly once
+                snap = [t.clone() for t in self._graph_state()]
+                s = torch.cuda.Stream(device=self.device)
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._enqueue_step()
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize(self.device)
+                for t, c in zip(self._graph_state(), snap):
+                    t.copy_(c)
+                n0 = ops.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_step()
+                self.launches_per_step = ops.launch_count() - n0
+                for t, c in zip(self._graph_state(), snap):       # (capture does not execute, but keep the invariant explicit)
+                    t.copy_(c)
+                self.graph = g
+            self.graph.replay()
+            self._grads_clean = True
+            self.store.version += 1
         return self.terms
+
+    def _graph_state(self):
+        st = [self.params, self.adam_m, self.adam_v, self.grads]
+        for L in self.layers:
+            st += [self.store[L['bn']['moving_mean']], self.store[L['bn']['moving_variance']]]
+        return st
+
+    def phase_times(self, iters=3):
+        """Device time (ms) of the phases of one eager step -- forward / loss / backward (+ all-reduce) / update -- and, with
+        world > 1, the part of the all-reduce that the overlap with backward does NOT hide (backward timed with and without
+        the collectives).  Weights / moments are restored afterwards."""
+        snap = [t.clone() for t in self._graph_state()]
+        it0 = self.iteration
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        acc = np.zeros(4)
+        bwd_local = 0.0
+        with ops.conv_workspace_scope(self.conv_ws):
+            for k in range(iters + 1):
+                self.iteration += 1
+                self._set_lr()
+                ev[0].record(); self.forward(); ev[1].record(); self.loss(); ev[2].record(); self.backward(); ev[3].record()
+                self.update(_lr_set=True); ev[4].record()
+                ev[4].synchronize()
+                if k:
+                    acc += [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+            out = dict(zip(('forward', 'loss', 'backward', 'update'), (acc / iters).round(4).tolist()))
+            if self.world > 1:
+                w = self.reducer.world
+                self.reducer.world = 1                  # same kernels, no collectives
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for k in range(iters + 1):
+                    self.forward(); self.loss()
+                    if torch.distributed.is_initialized():
+                        torch.cuda.synchronize()
+                        torch.distributed.barrier(group=self.pg)
+                    e0.record(); self.backward(); e1.record()
+                    e1.synchronize()
+                    self.grads.zero_(); self._grads_clean = True
+                    if k:
+                        bwd_local += e0.elapsed_time(e1) / iters
+                self.reducer.world = w
+                out['backward_without_allreduce'] = round(bwd_local, 4)
+                out['allreduce_exposed'] = round(out['backward'] - bwd_local, 4)
+        for t, c in zip(self._graph_state(), snap):
+            t.copy_(c)
+        self.iteration = it0
+        return out
+
 
     # ---- checkpoint state beyond the variables (tf.train.Saver() saves ALL global variables: pascal_train_darknet.py:54,111) ----
     def optimizer_state(self):

@@ -11,7 +11,10 @@ eagerly; variables live in a VariableStore that reproduces TF's auto-generated n
 found again under `reuse=True`.
 
 Compute path (config.COMPUTE): 'bf16' -> tcgen05 implicit-GEMM conv with BN/leaky/pool fused in the
-epilogue; 'fp32' -> exact FFMA conv + separate BN/leaky/pool kernels.  No CPU / cuDNN fallback.
+epilogue; 'bf16x3' -> the same kernels on hi + lo bf16 operand pairs (three MMAs per K step; activations travel as
+[N,H,W,2C] = [hi | lo] bf16 tensors) -- the mode that meets the 1e-3 detections bar; 'fp32' -> exact FFMA conv +
+separate BN/leaky/pool kernels.  No CPU / cuDNN fallback, and no torch library kernel on the path (casts, pools,
+concat and space_to_depth are y2_* kernels / store addresses).
 """
 from __future__ import annotations
 
@@ -98,19 +101,25 @@ def bias_variable(shape):
     return _as_param(store, name)
 
 
+def _f32(x):
+    """float32, contiguous view of an activation (bf16 -> float32 through y2_cast)."""
+    x = x if x.dtype == torch.float32 else ops.cast(x, torch.float32)
+    return x if x.is_contiguous() else x.contiguous()
+
+
 def conv2d(x, W, stride):
     """darknet.py:20-21: SAME, stride 1 cross-correlation (exact fp32 kernel, no bias)."""
     assert stride == 1
-    return ops.conv_fwd_f32(x.float().contiguous(), W, None)
+    return ops.conv_fwd_f32(_f32(x), W, None)
 
 
 def max_pool(x, pool_size, stride):
     """darknet.py:24-25: 2x2/2 max-pool."""
     assert pool_size == 2 and stride == 2
     N, H, W, C = x.shape
-    out_bf16 = x.dtype == torch.bfloat16
-    xf = x if x.dtype == torch.float32 else x.float()
-    return ops.affine_leaky_pool(xf.contiguous(), N, H, W, C, leaky=False, pool=True, out_bf16=out_bf16)
+    if x.dtype == torch.bfloat16 and C % 8 == 0:
+        return ops.maxpool2x2_bf16(x if x.is_contiguous() else x.contiguous())
+    return ops.affine_leaky_pool(_f32(x), N, H, W, C, leaky=False, pool=True, out_bf16=x.dtype == torch.bfloat16)
 
 
 def avg_pool(x, pool_size, stride):
@@ -127,9 +136,10 @@ def fc_layer(x, input_dim, output_dim, flat=False, linear=False):
     if flat:
         x = x.reshape(-1, input_dim)
     n = x.shape[0]
-    h = ops.conv_fwd_f32(x.float().contiguous().view(n, 1, 1, input_dim), W_fc.view(1, 1, input_dim, output_dim), b_fc)
-    h = h.view(n, output_dim)
-    return h if linear else torch.maximum(alpha * h, h)
+    h = ops.conv_fwd_f32(_f32(x).view(n, 1, 1, input_dim), W_fc.view(1, 1, input_dim, output_dim), b_fc)
+    if not linear:                                     # tf.maximum(alpha * h, h) (darknet.py:57)
+        h = ops.affine_leaky_pool(h, n, 1, 1, output_dim, leaky=True, pool=False, out_bf16=False)
+    return h.view(n, output_dim)
 
 
 def conv_layer(x, filter_size, input_chl, output_chl, stride):
@@ -137,15 +147,30 @@ def conv_layer(x, filter_size, input_chl, output_chl, stride):
     assert stride == 1
     W_conv = weight_variable([filter_size, filter_size, input_chl, output_chl])
     b_conv = bias_variable([output_chl])
-    return ops.conv_fwd_f32(x.float().contiguous(), W_conv, b_conv)
+    return ops.conv_fwd_f32(_f32(x), W_conv, b_conv)
 
 
-def conv_bn_layer(x, filter_size, input_chl, output_chl, stride, is_training, _pool=False, _out_f32=None):
+def _packed_split(store, wname):
+    key = (id(store), wname, 'x3')
+    hit = _pack_cache.get(key)
+    w = _as_param(store, wname)
+    if hit is None or hit[0] != store.version or hit[1] != w.data_ptr():
+        hit = (store.version, w.data_ptr(), ops.pack_weights_bf16_split(w))
+        _pack_cache[key] = hit
+    return hit[2]
+
+
+def conv_bn_layer(x, filter_size, input_chl, output_chl, stride, is_training, _pool=False, _out_f32=None, _out=None,
+                  _ldo=None, _col=0, _s2d=False):
     """darknet.py:39-46: conv + bias -> batch norm -> leaky(0.1).
 
-    `_pool` fuses the 2x2 max-pool that follows the layer in the builders (darknet.py:151,154,...);
-    `_out_f32` forces a float32 result (the detection output).  Both are extensions with defaults
-    that reproduce the reference call."""
+    Extensions (defaults reproduce the reference call): `_pool` fuses the 2x2 max-pool that follows the layer in the
+    builders (darknet.py:151,154,...); `_out_f32` forces a float32 result (the detection output); `_out` / `_ldo` /
+    `_col` / `_s2d` write the activation into channels [_col, _col + output_chl) of a wider (concatenated) tensor of
+    row stride `_ldo`, optionally through tf.space_to_depth(2) -- the passthrough branch, never a copy.
+
+    config.COMPUTE: 'fp32' exact FFMA conv; 'bf16' one tcgen05.mma per K step on bf16-rounded operands; 'bf16x3' hi + lo
+    bf16 pairs, three MMAs per K step (activations then travel as [N,H,W,2C] = [hi | lo] bf16 tensors between layers)."""
     assert stride == 1
     store = default_store()
     wname, _ = store.weight_variable([filter_size, filter_size, input_chl, output_chl])
@@ -157,8 +182,16 @@ def conv_bn_layer(x, filter_size, input_chl, output_chl, stride, is_training, _p
     training = bool(is_training)
     N, H, Wd, _ = x.shape
     mode = cfg.COMPUTE
-    if mode == 'fp32':
-        h = ops.conv_fwd_f32(x.float().contiguous(), W, b)
+    if mode not in ('fp32', 'bf16', 'bf16x3'):
+        raise ValueError('config.COMPUTE must be "fp32", "bf16" or "bf16x3"')
+    x3 = mode == 'bf16x3'
+    if x3 and (_out is not None or _s2d):
+        raise NotImplementedError('the passthrough branch has no bf16x3 path yet')
+    out_f32 = bool(_out_f32) or mode == 'fp32'
+    # the exact FFMA route: the fp32 mode, and the first layer of the bf16x3 mode when it is fed float32 pixels (the batch
+    # engine's fused uint8 first layer is the fast bf16x3 route; this eager path keeps the 16-bit accuracy with no tensor core)
+    if mode == 'fp32' or (x3 and x.dtype == torch.float32 and input_chl == 3):
+        h = ops.conv_fwd_f32(_f32(x), W, b)
         if training:
             mean, var = ops.bn_stats(h.view(-1, output_chl), output_chl)
             if UPDATE_MOVING_AVERAGES:
@@ -167,39 +200,43 @@ def conv_bn_layer(x, filter_size, input_chl, output_chl, stride, is_training, _p
             mean, var = mm, mv
         scale, shift = ops.bn_fold(gamma, beta, _zeros(output_chl), var, None)      # shift == beta
         return ops.affine_leaky_pool(h, N, H, Wd, output_chl, sub=mean, scale=scale, shift=shift, leaky=True,
-                                     pool=_pool, out_bf16=False)
-    if mode != 'bf16':
-        raise ValueError('config.COMPUTE must be "bf16" or "fp32"')
+                                     pool=_pool, out_bf16=not out_f32, out=_out, ldo=_ldo, out_col=_col, space_to_depth=_s2d,
+                                     split_out=x3 and not out_f32)
     # ---- tensor-core path ----
     if x.dtype == torch.float32:
         if input_chl == 3:
             xb = ops.pad_cast_f32_to_bf16c8(x.contiguous())
+        elif x3:                                     # float32 fed mid-network: split it into the [hi | lo] pair
+            xb = ops.affine_leaky_pool(x.contiguous(), N, H, Wd, input_chl, leaky=False, pool=False, out_bf16=True, split_out=True)
         else:
-            xb = x.to(torch.bfloat16).contiguous()
+            xb = ops.cast(x, torch.bfloat16)
     else:
         xb = x
-    wp = _packed(store, wname)
-    out_f32 = bool(_out_f32)
+    if x3:
+        assert xb.shape[-1] == 2 * input_chl, 'bf16x3: expected a [hi | lo] activation with %d channels' % (2 * input_chl)
+    wp = _packed_split(store, wname) if x3 else _packed(store, wname)
     if not training:
         scale, shift = ops.bn_fold(gamma, beta, mm, mv, b)          # bias folded: acc has no bias
-        if out_f32:
+        if out_f32 or _s2d:
             ld = (output_chl + 31) // 32 * 32
             raw = ops.conv_fwd_bf16(xb, wp, filter_size, input_chl, output_chl, scale=scale, shift=shift, leaky=True,
-                                    pool=_pool, out_f32=True, ldy=ld)
-            Ho, Wo = (H // 2, Wd // 2) if _pool else (H, Wd)
-            return raw.view(N, Ho, Wo, ld)[..., :output_chl].contiguous() if ld != output_chl else raw.view(N, Ho, Wo, ld)
+                                    pool=False, out_f32=True, ldy=ld, split_in=x3)
+            # compact the padded rows / pool / scatter them space-to-depth into the concat buffer
+            return ops.affine_leaky_pool(raw, N, H, Wd, output_chl, ldx=ld, leaky=False, pool=_pool, out_bf16=not out_f32,
+                                         out=_out, ldo=_ldo, out_col=_col, space_to_depth=_s2d)
         return ops.conv_fwd_bf16(xb, wp, filter_size, input_chl, output_chl, scale=scale, shift=shift, leaky=True,
-                                 pool=_pool)
+                                 pool=_pool, out=_out, ldy=_ldo, out_col=_col, split_in=x3, split_out=x3)
     # batch statistics: raw fp32 conv+bias, stats, then normalise + leaky (+ pool)
     ld = (output_chl + 31) // 32 * 32
     raw = ops.conv_fwd_bf16(xb, wp, filter_size, input_chl, output_chl, scale=None, shift=b, leaky=False, pool=False,
-                            out_f32=True, ldy=ld)
+                            out_f32=True, ldy=ld, split_in=x3)
     mean, var = ops.bn_stats(raw, output_chl, ld=ld)
     if UPDATE_MOVING_AVERAGES:
         ops.bn_update_moving(mm, mv, mean, var)
     scale, shift = ops.bn_fold(gamma, beta, _zeros(output_chl), var, None)
     return ops.affine_leaky_pool(raw, N, H, Wd, output_chl, ldx=ld, sub=mean, scale=scale, shift=shift, leaky=True,
-                                 pool=_pool, out_bf16=not out_f32)
+                                 pool=_pool, out_bf16=not out_f32, out=_out, ldo=_ldo, out_col=_col, space_to_depth=_s2d,
+                                 split_out=x3 and not out_f32)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -257,6 +294,8 @@ def darknet19_core(inputs, num_classes=None, is_training=True, global_pool=True,
     output of layer 13 (darknet.py:170), the source of the YOLOv2 passthrough branch: -> (net, passthrough)."""
     net = inputs
     pt = None
+    if return_passthrough and cfg.COMPUTE == 'bf16x3':
+        raise NotImplementedError('the passthrough branch has no bf16x3 path yet')
     with _variable_scope(scope, reuse=reuse):
         for li, (k, cin, cout, pool) in enumerate(CORE_PLAN):
             if return_passthrough and li == PASSTHROUGH_LAYER:
@@ -276,7 +315,7 @@ def darknet19(inputs, num_classes=None, is_training=True, global_pool=True, outp
     with _variable_scope(scope, reuse=reuse):
         for (k, cin, cout, pool) in CORE_PLAN:
             net = conv_bn_layer(net, k, cin, cout, 1, is_training, _pool=pool)
-        net = conv_bn_layer(net, 1, 1024, 1000, 1, is_training)
+        net = conv_bn_layer(net, 1, 1024, 1000, 1, is_training, _out_f32=(cfg.COMPUTE == 'bf16x3'))
         assert net.shape[1] == 7 and net.shape[2] == 7, 'darknet19 classifier expects a 224x224 input (darknet.py:116)'
         logits = avg_pool(net, 7, 7).reshape(-1, 1000)
     return logits
@@ -295,14 +334,23 @@ def darknet19_detection(net, output_filter, is_training=True, scope='darknet19_d
     with _variable_scope(scope, reuse=reuse):
         with _variable_scope('conv1'):
             net = conv_bn_layer(net, 3, 1024, 1024, 1, is_training)
-        with _variable_scope('conv2'):
-            net = conv_bn_layer(net, 3, 1024, 1024, 1, is_training)
         cat = 1024
-        if passthrough is not None:
+        if passthrough is None:
+            with _variable_scope('conv2'):
+                net = conv_bn_layer(net, 3, 1024, 1024, 1, is_training)
+        else:
+            # conv2's 1024 channels and the reorganised passthrough's 4 * filters share ONE [N,S,S,cat] tensor: the concat
+            # and tf.space_to_depth are the two producers' store addresses (as in the batch engine), never a copy
+            N, S = int(net.shape[0]), int(net.shape[1])
+            cat = 1024 + 4 * passthrough_filters
+            fp32 = cfg.COMPUTE == 'fp32'
+            buf = torch.empty((N, S, S, cat), dtype=torch.float32 if fp32 else torch.bfloat16, device=net.device)
+            with _variable_scope('conv2'):
+                conv_bn_layer(net, 3, 1024, 1024, 1, is_training, _out=buf, _ldo=cat, _col=0)
             with _variable_scope('passthrough'):
-                pt = conv_bn_layer(passthrough, 1, int(passthrough.shape[-1]), passthrough_filters, 1, is_training)
-            net = torch.cat([net, space_to_depth(pt.to(net.dtype))], dim=-1)
-            cat += 4 * passthrough_filters
+                conv_bn_layer(passthrough, 1, int(passthrough.shape[-1]), passthrough_filters, 1, is_training, _out=buf,
+                              _ldo=cat, _col=1024, _s2d=True)
+            net = buf
         with _variable_scope('conv3'):
             net = conv_bn_layer(net, 3, cat, 1024, 1, is_training)
         with _variable_scope('output'):

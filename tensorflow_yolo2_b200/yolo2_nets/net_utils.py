@@ -103,21 +103,79 @@ class LossResult(tuple):
     dnet = None
 
 
+class _YoloLossV1(torch.autograd.Function):
+    """get_loss as one autograd node: forward and the analytic gradient come out of the SAME fused kernel (loss.cu); backward
+    hands out d loss / d net scaled by the upstream gradient of the scalar loss -- so the reference's
+    `optimizer.minimize(loss)` pattern (pascal_train_darknet.py:44-51) composes with torch autograd.  `ious` and
+    `object_mask` are non-differentiable outputs (TF: the masks come from a comparison + cast; the IoU path's gradient is
+    already inside d loss / d net)."""
+
+    @staticmethod
+    def forward(ctx, net, labels, S, B, num_class, image_size, lambda_coord, lambda_noobj):
+        terms, ious, mask, dnet = ops.loss_v1(net, labels, S, B, num_class, image_size, lambda_coord, lambda_noobj)
+        ctx.save_for_backward(dnet)
+        ctx.mark_non_differentiable(ious, mask, terms, dnet)
+        return terms[4].clone(), ious, mask, terms, dnet
+
+    @staticmethod
+    def backward(ctx, g_loss, g_ious, g_mask, g_terms, g_dnet):
+        (dnet,) = ctx.saved_tensors
+        g = g_loss.detach().to(torch.float32).contiguous()
+        return ops.scale_by_device_scalar(dnet, g), None, None, None, None, None, None, None
+
+
 def get_loss(net, labels, num_class, batch_size, image_size, S, B, OFFSET=None, scope='loss_layer'):
-    """net_utils.py:263-372.  Returns (loss, ious, object_mask); the gradient w.r.t. `net` that TF's
-    autodiff would produce comes out of the same kernel (`.dnet`).  OFFSET must be the standard
+    """net_utils.py:263-372.  Returns (loss, ious, object_mask), differentiable w.r.t. `net`: `loss.backward()` (or
+    torch.autograd.grad) delivers the gradient TF's autodiff would produce -- it comes out of the same fused kernel as the
+    forward (also available directly as `.dnet`, with the five loss terms as `.terms`).  OFFSET must be the standard
     config.YOLO_GRID_OFFSET (offset[y,x,b] = x); it is generated in-kernel."""
     if OFFSET is not None:
         exp = cfg._grid_offset(S, B)
         if np.asarray(OFFSET).shape != exp.shape or not np.array_equal(np.asarray(OFFSET), exp):
             raise ValueError('get_loss: only the standard YOLO_GRID_OFFSET is supported')
-    net = net.reshape(batch_size, S, S, num_class + 5 * B).float().contiguous()
-    labels = torch.as_tensor(labels, device=net.device).reshape(batch_size, S, S, 5 + num_class).float().contiguous()
-    terms, ious, mask, dnet = ops.loss_v1(net, labels, S, B, num_class, image_size, float(cfg.LAMBDA_COORD),
-                                          float(cfg.LAMBDA_NOOBJ))
-    res = LossResult((terms[4], ious, mask))
+    net4 = net.reshape(batch_size, S, S, num_class + 5 * B)
+    if net4.dtype != torch.float32:
+        net4 = ops.cast(net4.detach(), torch.float32)
+    net4 = net4 if net4.is_contiguous() else net4.contiguous()
+    if not isinstance(labels, torch.Tensor):      # pascal_voc.get() hands out float64 numpy; the placeholder is float32 (:35)
+        labels = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.float32))
+    labels = labels.to(net.device).reshape(batch_size, S, S, 5 + num_class)
+    labels = (labels if labels.dtype == torch.float32 else labels.float()).contiguous()
+    loss, ious, mask, terms, dnet = _YoloLossV1.apply(net4, labels, S, B, num_class, float(image_size),
+                                                      float(cfg.LAMBDA_COORD), float(cfg.LAMBDA_NOOBJ))
+    res = LossResult((loss, ious, mask))
     res.terms, res.dnet = terms, dnet
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# summaries: tf.summary.scalar / tf.summary.histogram of get_loss (net_utils.py:361-370) + 'total_loss'
+# (pascal_train_darknet.py:47), merged by tf.summary.merge_all() (:87) and written every iteration (:104)
+# ---------------------------------------------------------------------------------------------
+SUMMARY_SCALARS = ('class_loss', 'object_loss', 'noobject_loss', 'coord_loss', 'total_loss')
+SUMMARY_HISTOGRAMS = ('boxes_delta_x', 'boxes_delta_y', 'boxes_delta_w', 'boxes_delta_h', 'iou')
+
+
+def merged_summary(net, labels, terms, ious, num_class, image_size, S, B):
+    """What `sess.run(merged)` evaluates in the reference's training loop: the five loss scalars and the five histogram
+    tensors (unmasked box deltas of every cell / predictor, and the IoUs).  net [N,S,S,C+5B] and labels [N,S,S,5+C] are the
+    CUDA tensors get_loss saw; terms = (class, coord, object, noobject, total) from the loss kernel.  Returns
+    dict(scalars={name: float}, histograms={name: float32 ndarray}) -- one device->host copy of ~N*S*S*B*5 floats."""
+    deltas = ops.loss_v1_box_deltas(net.float().contiguous(), labels.float().contiguous(), S, B, num_class, image_size)
+    t = terms.detach().cpu().numpy()
+    d = deltas.cpu().numpy()
+    return dict(scalars=dict(class_loss=float(t[0]), coord_loss=float(t[1]), object_loss=float(t[2]),
+                             noobject_loss=float(t[3]), total_loss=float(t[4])),
+                histograms=dict(boxes_delta_x=d[..., 0], boxes_delta_y=d[..., 1], boxes_delta_w=d[..., 2],
+                                boxes_delta_h=d[..., 3], iou=ious.detach().cpu().numpy()))
+
+
+def add_summary(writer, summary, step):
+    """train_writer.add_summary(summary, i) (pascal_train_darknet.py:104) on a torch.utils.tensorboard SummaryWriter."""
+    for name, v in summary['scalars'].items():
+        writer.add_scalar(name, v, step)
+    for name, v in summary['histograms'].items():
+        writer.add_histogram(name, v, step)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -427,6 +427,27 @@ def test_adam_step(ops):
     np.testing.assert_allclose(vt.cpu().numpy(), wv, rtol=1e-5, atol=1e-7)
 
 
+def test_adam_step_ex_scale_zero_and_device_lr(ops):
+    """y2_adam_step_ex == Adam on grad_scale * g, with the step size read from device memory and g cleared behind the read."""
+    rs = np.random.RandomState(6)
+    n = 4096 * 5
+    p, g, m, v = rs.randn(n).astype(np.float32), rs.randn(n).astype(np.float32) * 4, \
+        rs.randn(n).astype(np.float32) * 0.1, rs.uniform(0, 1, n).astype(np.float32)
+    wp, wm, wv = O.adam_step(p.astype(np.float64), 0.25 * g.astype(np.float64), m.astype(np.float64), v.astype(np.float64), 7)
+    for dev_lr in (False, True):
+        pt, gt, mt, vt = cu(p), cu(g), cu(m), cu(v)
+        lr_t = ops.adam_lr_t(7)
+        lr_dev = torch.tensor([lr_t], dtype=torch.float32).cuda() if dev_lr else None
+        ops.adam_step_ex(pt, gt, mt, vt, lr_t=0.0 if dev_lr else lr_t, lr_t_dev=lr_dev, grad_scale=0.25, zero_grad=True)
+        np.testing.assert_allclose(pt.cpu().numpy(), wp, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(mt.cpu().numpy(), wm, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(vt.cpu().numpy(), wv, rtol=1e-5, atol=1e-7)
+        assert float(gt.abs().max()) == 0.0
+    gt = cu(g)
+    ops.adam_step_ex(cu(p), gt, cu(m), cu(v), lr_t=1e-3, zero_grad=False)
+    assert torch.equal(gt, cu(g))
+
+
 # ---- fused decode + NMS ---------------------------------------------------------------------------
 @pytest.mark.parametrize('impl', ['detect_fused', 'detect_split'])
 @pytest.mark.parametrize('N,S,thr', [(7, 13, 0.3), (3, 19, 0.2), (2, 13, 0.01), (2, 7, 0.3), (64, 13, 0.1)])

@@ -134,6 +134,62 @@ def test_affine_split_output(ops, C, pool):
     np.testing.assert_allclose(join_pair(got.cpu()).numpy(), ref.cpu().numpy(), rtol=2e-5, atol=1e-30)
 
 
+# ---- the drop-in builders in the bf16x3 mode (config.COMPUTE = 'bf16x3') -------------------------------------------------
+@pytest.mark.parametrize('tame', [True, False])
+def test_builders_bf16x3_vs_oracle(tame):
+    """yolo2_nets.darknet.darknet19_core / darknet19_detection with config.COMPUTE = 'bf16x3' (float32 pixels in: exact FFMA
+    first layer, then hi + lo pairs through the tensor-core kernels) against the float64 oracle -- no bf16-mirroring."""
+    from tensorflow_yolo2_b200 import config, variables
+    from tensorflow_yolo2_b200.yolo2_nets.darknet import darknet19_core, darknet19_detection
+    from tests.helpers import make_store, oracle_params
+    st, layers = make_store(125, tame=tame)
+    core_p, head_p = oracle_params(st, layers)
+    variables._DEFAULT_STORE = st
+    st.reset_name_counters()
+    x = np.random.RandomState(3).uniform(-1, 1, (4, 128, 128, 3)).astype(np.float32)
+    want, inter = O.darknet19_forward(torch.tensor(x), core_p, head_p, dtype=torch.float64, return_intermediates=True)
+    old = config.COMPUTE
+    config.COMPUTE = 'bf16x3'
+    try:
+        core = darknet19_core(torch.tensor(x).cuda(), is_training=False)
+        out = darknet19_detection(core, 125)
+    finally:
+        config.COMPUTE = old
+        variables.reset_default_store(seed=0)
+    assert core.dtype == torch.bfloat16 and core.shape == (4, 4, 4, 2048)            # [hi | lo]
+    assert out.dtype == torch.float32 and out.shape == (4, 4, 4, 125)
+    e_core = rel_l2(join_pair(core.cpu()).numpy(), inter[17].numpy())
+    e_out = rel_l2(out.cpu().numpy(), want.numpy())
+    print('bf16x3 builders vs float64 oracle: tame=%s core rel_l2=%.3g out rel_l2=%.3g' % (tame, e_core, e_out))
+    assert e_core < 2e-4 and e_out < 5e-4
+
+
+def test_get_loss_is_differentiable_like_tf_minimize(ops, golden_dir):
+    """net_utils.get_loss as a torch.autograd node: loss.backward() / autograd.grad deliver the golden d loss / d net (the
+    reference graph + autodiff, tests/golden/ref_loss.npz), scaled by the upstream gradient -- the minimize(loss) pattern
+    of pascal_train_darknet.py:44-51."""
+    from tensorflow_yolo2_b200 import config as cfg
+    from tensorflow_yolo2_b200.yolo2_nets import net_utils as nu
+    g = np.load(os.path.join(golden_dir, 'ref_loss.npz'))
+    net = cu(g['rand7_net'].astype(np.float32)).requires_grad_(True)
+    lab = g['rand7_labels']
+    N = net.shape[0]
+    loss, ious, mask = nu.get_loss(net, lab, 20, N, 224, 7, 2, cfg._grid_offset(7, 2))
+    assert loss.requires_grad and not ious.requires_grad and not mask.requires_grad
+    np.testing.assert_allclose(float(loss), float(g['rand7_loss']), rtol=1e-5)
+    (3.0 * loss).backward()
+    np.testing.assert_allclose(net.grad.cpu().numpy(), 3.0 * g['rand7_dnet'], rtol=1e-3, atol=1e-6)
+    # composes with further torch ops upstream of net
+    w = torch.ones_like(net, requires_grad=True)
+    loss2 = nu.get_loss(net.detach() * w, lab, 20, N, 224, 7, 2)[0]
+    (gw,) = torch.autograd.grad(loss2, w)
+    np.testing.assert_allclose(gw.cpu().numpy(), g['rand7_dnet'] * g['rand7_net'], rtol=1e-3, atol=1e-6)
+    # no grad required: plain forward, .dnet still available
+    r = nu.get_loss(net.detach(), lab, 20, N, 224, 7, 2)
+    assert not r[0].requires_grad
+    np.testing.assert_allclose(r.dnet.cpu().numpy(), g['rand7_dnet'], rtol=1e-3, atol=1e-6)
+
+
 # ---- end to end: engine (network + decode + NMS) vs the float64 oracle end to end ----------------------------------------
 _ORACLE_CACHE = {}
 _REPORT = []

@@ -105,3 +105,22 @@ def test_train_script_snapshot_and_resume_restores_adam_state(fresh_env, capsys)
     fresh.set_labels(lab)
     fresh.step(img)
     assert float((fresh.params - tr.params).abs().max()) > 2e-4
+
+
+def test_train_script_writes_scalar_and_histogram_summaries(fresh_env):
+    """pascal_train_darknet.py:47,87-91,104 + net_utils.py:361-370: five scalars and five histograms per iteration."""
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    from tensorflow_yolo2_b200.pascal import pascal_train_darknet as script
+    from tensorflow_yolo2_b200.yolo2_nets.net_utils import SUMMARY_HISTOGRAMS, SUMMARY_SCALARS
+    script.main(['pascal_train_darknet.py', '--synthetic', '--iters', '3'])
+    torch.cuda.synchronize()
+    tb_dir, _ = fresh_env.get_output_tb_dir('darknet19', 'voc_2007', val=False)
+    acc = EventAccumulator(tb_dir, size_guidance={'histograms': 0, 'scalars': 0})
+    acc.Reload()
+    tags = acc.Tags()
+    assert set(SUMMARY_SCALARS) <= set(tags['scalars'])
+    assert set(SUMMARY_HISTOGRAMS) <= set(tags['histograms'])
+    assert [e.step for e in acc.Scalars('total_loss')] == [1, 2, 3]
+    h = acc.Histograms('iou')
+    assert len(h) == 3 and h[0].histogram_value.num == 24 * 7 * 7 * 2          # every cell and predictor (unmasked)
+    assert 0.0 <= h[0].histogram_value.min and h[0].histogram_value.max <= 1.0

@@ -259,6 +259,36 @@ def test_training_loss_decreases(ops):
     assert losses[-1] < 0.7 * losses[0]
 
 
+def test_training_step_cuda_graph_equals_eager(ops):
+    """Yolo2Trainer(use_cuda_graph=True): the captured step (forward, loss, backward, Adam with the step size read from
+    device memory) replays to the same weights as eager launches -- three iterations, so the bias correction really changes
+    between replays -- up to the float atomics of the split-K weight gradient."""
+    from tensorflow_yolo2_b200.trainer import Yolo2Trainer
+    N, IS = 4, 96
+    S = IS // 32
+    rs = np.random.RandomState(4)
+    img = torch.tensor(rs.randint(0, 256, (N, IS, IS, 3)).astype(np.uint8))
+    lab = _labels_v1(rs, N, S, IS)
+    res = []
+    for graph in (False, True):
+        st, _ = make_store(45, tame=True)
+        tr = Yolo2Trainer(N, IS, 45, store=st, loss='v1', B=5, device='cuda:0', use_cuda_graph=graph)
+        tr.set_labels(lab)
+        losses = [float(tr.step(img)[4]) for _ in range(3)]
+        torch.cuda.synchronize()
+        assert (tr.graph is not None) == graph and tr.iteration == 3
+        assert float(tr.grads.abs().max()) == 0.0                      # cleared by the update kernel
+        res.append((losses, tr.params.clone(), tr.adam_v.clone(), st[tr.layers[5]['bn']['moving_mean']].clone()))
+        if graph:
+            assert tr.launches_per_step > 200
+    (l0, p0, v0, mm0), (l1, p1, v1, mm1) = res
+    print(l0, l1)
+    np.testing.assert_allclose(l0, l1, rtol=2e-2)
+    # Adam's first steps move every weight by ~lr whatever the gradient's size, so agreement is judged against that scale
+    assert float((p0 - p1).abs().mean()) < 3e-4 and float((p0 - p1).abs().max()) < 1e-2
+    np.testing.assert_allclose(mm0.cpu().numpy(), mm1.cpu().numpy(), rtol=2e-2, atol=1e-3)
+
+
 def test_ddp_two_gpus_matches_mean_of_shard_gradients():
     """World-size-2 NCCL run of tools/ddp_check.py (skipped on a single-GPU box)."""
     import subprocess

@@ -43,12 +43,17 @@ def main():
     ddp = Yolo2Trainer(N, IS, 45, store=st_b, loss='v1', B=5, device=dev, bucket_bytes=8 << 20)
     assert ddp.world == world and len(ddp.buckets) > 1
     ddp.set_labels(lab)
-    ddp.step(img)
+    ddp.in_u8.copy_(img)
+    ddp.iteration += 1
+    ddp._set_lr()
+    ddp.forward(); ddp.loss(); ddp.backward()          # the arena now holds the all-reduced SUM (1/world lives in the update kernel)
     torch.cuda.synchronize()
     want = local_grads.clone()
     dist.all_reduce(want)
-    want /= world
     err = float((ddp.grads - want).norm() / want.norm())
+    ddp.update(_lr_set=True)
+    torch.cuda.synchronize()
+    assert float(ddp.grads.abs().max()) == 0.0         # cleared behind the read
     # atomics in split-K make bitwise equality impossible; fp32 reduction order noise only
     ok = err < 1e-5
     p = ddp.params.clone()
