@@ -77,7 +77,11 @@ class Yolo2Trainer:
         self.iteration = 0
         # the whole step (forward, loss, backward, Adam: ~290 launches) replayed as ONE CUDA graph; single-process only --
         # with world > 1 the NCCL buckets are issued eagerly on NCCL's stream so that they overlap the backward kernels
+        # (capturing the NCCL buckets into the graph as well was tried on 2 GPUs: the capture dead-locks -- not offered)
+        import os as _os
         self.use_cuda_graph = bool(use_cuda_graph) and self.world == 1
+        if _os.environ.get('Y2_BUCKET_MB'):
+            bucket_bytes = int(float(_os.environ['Y2_BUCKET_MB']) * (1 << 20))
         self.graph = None
         self.launches_per_step = 0
         self._grads_clean = True                    # the gradient arena is all zero (fresh, or cleared by the last update)

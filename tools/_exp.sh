@@ -1,4 +1,7 @@
-mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_training_gpu.py tests/test_scripts_gpu.py tests/test_parity_gpu.py tests/test_kernels_gpu.py tests/test_e2e_gpu.py -q -x -k "not detections_baseline" 2>&1 | tail -12
-timeout 600 python bench.py --mode train --steps 10 --warmup 3 > gpurun_out/r2d_train_graph.json 2> gpurun_out/r2d_train_graph.err; tail -3 gpurun_out/r2d_train_graph.err; cat gpurun_out/r2d_train_graph.json | cut -c1-2500
-timeout 600 python bench.py --mode train --steps 10 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/r2d_train_eager.json 2> gpurun_out/r2d_train_eager.err; tail -3 gpurun_out/r2d_train_eager.err; cat gpurun_out/r2d_train_eager.json | cut -c1-1200
+N=4; TAG=r2e
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+timeout 200 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_infer_${N}gpu.json 2> gpurun_out/${TAG}_infer_${N}gpu.err
+timeout 200 $TR bench.py --mode train --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_train_${N}gpu.json 2> gpurun_out/${TAG}_train_${N}gpu.err
+timeout 100 $TR tools/bench_detect.py --shard strong > gpurun_out/${TAG}_bench_detect_strong_${N}gpu.json 2> gpurun_out/${TAG}_detect_${N}gpu.err
+timeout 100 $TR tools/bench_detect.py --shard weak > gpurun_out/${TAG}_bench_detect_weak_${N}gpu.json 2> gpurun_out/${TAG}_detect_${N}gpu.err
+echo done
