@@ -281,6 +281,7 @@ def measure_mode(precision, args, world, rank, dev, dist, sampler_index):
     e0.record(stream)
     for i in range(args.steps):
         eng.submit(host_batches[i % 2], res_host)
+    eng.wait_outputs()                                            # the last batch's results have reached the host buffers
     e1.record(stream)
     barrier()
     e2e_value = world * N * args.steps / (allmax(e0.elapsed_time(e1)) * 1e-3)

@@ -37,6 +37,7 @@ static void env_read() {
   e.conv_no_tma_store = on("Y2_CONV_NO_TMA_STORE");
   e.affine_generic = on("Y2_AFFINE_GENERIC");
   e.no_pdl = on("Y2_NO_PDL");
+  e.conv_streamk_x3_generic = on("Y2_CONV_STREAMK_X3_GENERIC");
   e.conv_streamk_min_ksteps = num("Y2_CONV_STREAMK_MIN_KSTEPS", -1);
   e.conv_block_n = num("Y2_CONV_BLOCK_N", 0);
   e.conv1_debug = num("Y2_CONV1_DEBUG", 0);

@@ -366,16 +366,23 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   waiting on TMA), so fewer delivered bytes per flop is what is left; the price is an un-overlapped epilogue (~150 k clk
 //   of MMAs per drain at K = 9 x 1024, so a few per cent).  MEASURED: slower (see the launcher) -- kept as an opt-in.
 constexpr uint32_t SK2_A_BYTES = 128 * 128;
-template <int HALVES> struct Sk2Cfg {
-  static constexpr uint32_t STAGE = (HALVES + 1) * SK2_A_BYTES;          // per CTA: HALVES x (128 px x 128 B) + 128 filters x 128 B
-  static constexpr int STAGES = HALVES == 1 ? 6 : 4;                     // 192 KB of operands either way
+// X3 (the bf16x3 precision mode, HALVES == 1 only): one pipeline stage holds BOTH halves of a 64-channel chunk of the pixels
+// (hi, lo) and of the filters (w_hi, w_lo) -- 64 KB per CTA -- and feeds three MMAs per K = 16 slice (hi*w_hi, lo*w_hi,
+// hi*w_lo): 64 KB delivered per 12 MMAs instead of the 96 KB the generic K walk over [hi | lo | hi] x [w_hi | w_hi | w_lo]
+// needs.  The kernel is bound by exactly that delivery (above), and the bf16x3 operands (144 MB per head layer) no longer
+// fit the L2 beside the output, so fewer re-fetched bytes is what counts.  Same packed weights: w_hi = first, w_lo = third
+// block of a tap.
+template <int HALVES, bool X3 = false> struct Sk2Cfg {
+  static constexpr uint32_t STAGE = X3 ? 4 * SK2_A_BYTES : (HALVES + 1) * SK2_A_BYTES;   // per CTA: pixels (+ lo) + 128 filters (+ lo)
+  static constexpr int STAGES = X3 ? 3 : (HALVES == 1 ? 6 : 4);          // 192 KB of operands either way
 };
 
-template <int HALVES>
+template <int HALVES, bool X3 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SK_THREADS, 1)
 conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SkArgs a) {
-  constexpr int SK2_STAGES = Sk2Cfg<HALVES>::STAGES;
-  constexpr uint32_t SK2_STAGE = Sk2Cfg<HALVES>::STAGE;
+  static_assert(!X3 || HALVES == 1, "bf16x3 stages: 256-row pair tiles only");
+  constexpr int SK2_STAGES = Sk2Cfg<HALVES, X3>::STAGES;
+  constexpr uint32_t SK2_STAGE = Sk2Cfg<HALVES, X3>::STAGE;
   constexpr int NCHUNK = 4 * HALVES;                           // 32-column chunks per epilogue warp and segment
   constexpr uint32_t TILE_ROWS = 256u * HALVES;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -442,11 +449,22 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int kh = a.pad ? (tap * 11) >> 5 : 0, kw = tap - kh * 3;       // tap / 3 for tap < 9 (1x1: tap == 0)
           const uint32_t sA = smem_base + stage * SK2_STAGE;
           const uint32_t bar = smem_u32(&full_bar[stage]) & PEER_BIT_MASK;      // the leader's barrier
-#pragma unroll
-          for (int h = 0; h < HALVES; ++h)
-            tma_load_im2col_4d_2sm(sA + (uint32_t)h * SK2_A_BYTES, &tmA, bar, a_c0, w0[h] - a.pad, h0[h] - a.pad, n0[h], (uint16_t)kw,
+          if constexpr (X3) {
+            // stage = [pixels hi | pixels lo | filters hi | filters lo]; lo channels sit a_wrap/2 chunks further, w_lo two
+            // blocks (of cin_p / 3) further
+            const int lo_c = (a.a_wrap >> 1) * 64, lo_k = 2 * (a.cin_p / 3);
+            tma_load_im2col_4d_2sm(sA, &tmA, bar, a_c0, w0[0] - a.pad, h0[0] - a.pad, n0[0], (uint16_t)kw, (uint16_t)kh);
+            tma_load_im2col_4d_2sm(sA + SK2_A_BYTES, &tmA, bar, a_c0 + lo_c, w0[0] - a.pad, h0[0] - a.pad, n0[0], (uint16_t)kw,
                                    (uint16_t)kh);
-          tma_load_2d_2sm(sA + HALVES * SK2_A_BYTES, &tmB, bar, b_k, nrow0);
+            tma_load_2d_2sm(sA + 2 * SK2_A_BYTES, &tmB, bar, b_k, nrow0);
+            tma_load_2d_2sm(sA + 3 * SK2_A_BYTES, &tmB, bar, b_k + lo_k, nrow0);
+          } else {
+#pragma unroll
+            for (int h = 0; h < HALVES; ++h)
+              tma_load_im2col_4d_2sm(sA + (uint32_t)h * SK2_A_BYTES, &tmA, bar, a_c0, w0[h] - a.pad, h0[h] - a.pad, n0[h], (uint16_t)kw,
+                                     (uint16_t)kh);
+            tma_load_2d_2sm(sA + HALVES * SK2_A_BYTES, &tmB, bar, b_k, nrow0);
+          }
           if (++stage == SK2_STAGES) { stage = 0; phase ^= 1u; }
         }
         u += k1 - k0;
@@ -460,7 +478,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // D=f32, A=B=bf16, K-major both, N = 256, M = 256 (the pair)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint64_t adesc0 = make_smem_desc(smem_base, 16u, 8u * 128u, 2u);                    // SWIZZLE_128B, K-major
-      const uint64_t bdesc0 = make_smem_desc(smem_base + HALVES * SK2_A_BYTES, 16u, 8u * 128u, 2u);
+      const uint64_t bdesc0 = make_smem_desc(smem_base + (X3 ? 2 : HALVES) * SK2_A_BYTES, 16u, 8u * 128u, 2u);
       const uint32_t empty0 = smem_u32(&empty_bar[0]), tfull0 = smem_u32(&tmem_full[0]);
       int stage = 0;
       uint32_t phase = 0, seg = 0;
@@ -480,13 +498,25 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tc_fence_after();
           if (is_leader) {
             const uint32_t soff = (uint32_t)(stage * SK2_STAGE) >> 4;
+            if constexpr (X3) {
+              constexpr uint32_t LO = SK2_A_BYTES >> 4;            // the lo block follows the hi block of either operand
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ah = adesc0 + soff + (uint32_t)(ks * 2), bh = bdesc0 + soff + (uint32_t)(ks * 2);
+                umma_bf16_2sm(tmem_d, ah, bh, idesc, accum);        // hi * w_hi
+                umma_bf16_2sm(tmem_d, ah + LO, bh, idesc, 1u);      // lo * w_hi
+                umma_bf16_2sm(tmem_d, ah, bh + LO, idesc, 1u);      // hi * w_lo
+                accum = 1;
+              }
+            } else {
 #pragma unroll
-              for (int h = 0; h < HALVES; ++h)
-                umma_bf16_2sm(tmem_d + (uint32_t)(h * 256), adesc0 + soff + (uint32_t)(h * (SK2_A_BYTES >> 4)) + (uint32_t)(ks * 2),
-                              bdesc0 + soff + (uint32_t)(ks * 2), idesc, accum);
-              accum = 1;
+              for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int h = 0; h < HALVES; ++h)
+                  umma_bf16_2sm(tmem_d + (uint32_t)(h * 256), adesc0 + soff + (uint32_t)(h * (SK2_A_BYTES >> 4)) + (uint32_t)(ks * 2),
+                                bdesc0 + soff + (uint32_t)(ks * 2), idesc, accum);
+                accum = 1;
+              }
             }
             umma_commit_2sm_mc(empty0 + 8u * (uint32_t)stage, (uint16_t)3);
           }
@@ -649,10 +679,12 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   const bool split_in = (p->flags & Y2_CONV_IN_SPLIT) != 0;
   const bool split_out = (p->flags & Y2_CONV_OUT_SPLIT) != 0 && !out_f32;
   const int a_cin = split_in ? 2 * p->Cin : p->Cin, b_cin = split_in ? 3 * p->Cin : p->Cin;
-  const int taps = p->ksize * p->ksize, cchunks = b_cin / 64, ksteps = taps * cchunks;
+  const bool two_cta_pre = !env().conv_streamk_1cta && g_num_sms >= 2;
+  const bool x3 = split_in && two_cta_pre && !env().conv_streamk_512 && !env().conv_streamk_x3_generic;   // shared-operand stages
+  const int taps = p->ksize * p->ksize, cchunks = (x3 ? p->Cin : b_cin) / 64, ksteps = taps * cchunks;
   const int lo_off = split_out ? (p->lo_off > 0 ? p->lo_off : p->Cout) : 0;
   if (split_out && ((lo_off & 7) != 0 || ldy < lo_off + p->Cout)) return Y2_OK;
-  int min_ksteps = 18;                                          // short K: the epilogue starts to show
+  int min_ksteps = x3 ? 6 : 18;                                 // short K: the epilogue starts to show (bf16x3 steps are 3x heavier)
   if (env().conv_streamk_min_ksteps >= 0) min_ksteps = env().conv_streamk_min_ksteps;
   if (ksteps < min_ksteps || ksteps > SK_MAX_UNITS) return Y2_OK;
   int rc = load_driver_entry_points();
@@ -738,7 +770,11 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = fill_launch_attrs(attr, 2u);                 // (matches the kernels' __cluster_dims__)
-    if (halves == 2) {
+    if (x3) {
+      static_assert(Sk2Cfg<1, true>::STAGES * Sk2Cfg<1, true>::STAGE == Sk2Cfg<1>::STAGES * Sk2Cfg<1>::STAGE, "operand smem");
+      Y2_CUDA(cudaFuncSetAttribute((conv_streamk2_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      Y2_CUDA(cudaLaunchKernelEx(&cfg, (conv_streamk2_kernel<1, true>), tmA, tmB, a));
+    } else if (halves == 2) {
       Y2_CUDA(cudaFuncSetAttribute(conv_streamk2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_streamk2_kernel<2>, tmA, tmB, a));
     } else {

@@ -511,10 +511,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else if constexpr (A_MODE == 2) {
           if (a.kw_merge) {
-            // the three horizontally shifted (16+2)-row patches of the single channel chunk, one lane each
+            // the three horizontally shifted (16+2)-row patches of channel chunk `st`, one lane each
             if (lane < 3) {
-              if constexpr (cta2) tma_load_4d_2sm(sA + (uint32_t)lane * a.a_sub_bytes, &tmA, bar, 0, t.w0 + lane - 1, t.h0 - 1, t.n0);
-              else tma_load_4d(sA + (uint32_t)lane * a.a_sub_bytes, &tmA, bar, 0, t.w0 + lane - 1, t.h0 - 1, t.n0);
+              const int c0 = (int)s_units[st * 3].a_c0;
+              if constexpr (cta2) tma_load_4d_2sm(sA + (uint32_t)lane * a.a_sub_bytes, &tmA, bar, c0, t.w0 + lane - 1, t.h0 - 1, t.n0);
+              else tma_load_4d(sA + (uint32_t)lane * a.a_sub_bytes, &tmA, bar, c0, t.w0 + lane - 1, t.h0 - 1, t.n0);
             }
           } else {
             // one horizontally shifted (16+2)-row patch serves the three taps kh = 0..2 of this kw
@@ -524,7 +525,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               else tma_load_4d(sA, &tmA, bar, d.a_c0, t.w0 + d.kw - 1, t.h0 - 1, t.n0);
             } else if (lane < 4 && !a.b_stationary) {
               const int kh = lane - 1;
-              if (CS > 1)
+              if constexpr (cta2)      // pair, streamed filters: my half of the rows of tap (kh, kw), counted on the leader's barrier
+                tma_load_2d_2sm(sB + kh * a.b_sub_bytes, &tmB, bar, d.b_k + kh * 3 * a.cin_p, nrow0 + (int)crank * (BLOCK_N / 2));
+              else if (CS > 1)
                 tma_load_2d_mc(sB + kh * a.b_sub_bytes + crank * (a.b_sub_bytes / CS), &tmB, bar, d.b_k + kh * 3 * a.cin_p,
                                nrow0 + (int)crank * (BLOCK_N / CS), mc_mask);
               else
@@ -628,6 +631,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t b_cursor_inc = bstat ? (uint32_t)subs * b_sub16 : 0u;
     const uint32_t b_unit_mul = bstat ? b_sub16 : 0u;                                   // mode 2
     const uint32_t b_kh_mul = bstat ? (uint32_t)(3 * a.cchunks) * b_sub16 : b_sub16;    // mode 2
+    const uint32_t b_tap16 = (uint32_t)a.cchunks * b_sub16;                             // mode 2, kw-merged: one tap's chunks
     uint32_t stage = 0, phase = 0, soff = 0, bsoff = 0;
     uint32_t it = 0;
     for (int tile = sched_first; tile < (issuer ? total_tiles : 0); tile += sched_step, ++it) {
@@ -675,14 +679,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               accum = 1;
             };
             if (a.kw_merge) {
-              // all three horizontally shifted patches in one stage, stationary B indexed by tap = kh * 3 + kw
-              // (one channel chunk): 9 * KSTEPS MMAs behind a single barrier round trip, every offset a constant
+              // all three horizontally shifted patches of channel chunk `st` in one stage, stationary B indexed by
+              // (tap = kh * 3 + kw, chunk): 9 * KSTEPS MMAs behind a single barrier round trip
 #pragma unroll
               for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                   const uint64_t ad = ad_s + (uint32_t)kw * a_sub16 + (uint32_t)kh * khshift16;
-                  const uint64_t bd = bd_s + (uint32_t)(kh * 3 + kw) * b_sub16;     // (bd_s == bdesc0: stationary, bidx0 = 0)
+                  const uint64_t bd = bd_s + (uint32_t)(kh * 3 + kw) * b_tap16 + (uint32_t)st * b_sub16;     // (bd_s == bdesc0: stationary, bidx0 = 0)
 #pragma unroll
                   for (int ks = 0; ks < KSTEPS; ++ks) mma(ad + (uint32_t)ks * a_kstep, bd + (uint32_t)ks * b_kstep);
                 }
@@ -1146,11 +1150,19 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   // (4096 + 32 N) bytes of operands at ~64 B/clk -- 96 / 128 clk at N = 64 / 128 for 32 / 64 clk of arithmetic; in a
   // pair each SM fetches its own A rows and HALF of the filters (80 / 96 clk).  Each CTA keeps half of the resident bank.
   a.cta2 = 0;
+  bool cta2_streamed = false;
   if (a.a_mode == 2 && !a.first_layer && a.n_tiles == 1 && a.m_tiles >= 2 && block_n >= 64 && block_n <= 128 &&
       ((block_n / 2) * a.row_bytes) % 1024 == 0 && !env().conv_no_cta2) {
     const uint32_t half = (uint32_t)(block_n / 2) * a.row_bytes;
     if ((size_t)a.kblocks * half + 4 * (size_t)a.a_stage_bytes <= SMEM_BUDGET) {
       a.cta2 = 1;
+      a.b_sub_bytes = half;
+      a.b_stage_bytes = 3 * half;
+    } else if (!env().conv_no_bstat) {
+      // the bank does not fit (bf16x3: three times the K extent): still a pair, each CTA STREAMING its half of the three
+      // taps' filter rows next to its patch -- (4096 + 16 N) / 64 clk per MMA instead of the single CTA's (4096 + 32 N) / 64
+      a.cta2 = 1;
+      cta2_streamed = true;
       a.b_sub_bytes = half;
       a.b_stage_bytes = 3 * half;
     }
@@ -1166,22 +1178,22 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   // B-stationary: with a single N tile and a small filter bank, every tile of the CTA needs the same B
   a.b_total_bytes = a.first_layer ? a.b_sub_bytes : (uint32_t)a.kblocks * a.b_sub_bytes;
   a.b_stationary = (a.n_tiles == 1 && a.b_total_bytes + 4 * (size_t)a.a_stage_bytes <= SMEM_BUDGET &&
-                    !env().conv_no_bstat) ? 1 : 0;
+                    !env().conv_no_bstat && !cta2_streamed) ? 1 : 0;
   // halo-patch mode with a resident filter bank and a single channel chunk (layer 2: Cin = 32): the three
   // horizontally shifted patches share ONE stage, so the MMA warp issues all 9 taps behind one barrier round trip.
   // With one patch per stage that warp's ~800 clk of per-stage bookkeeping hid 192 clk of tensor work (ncu, r1c).
-  if (a.a_mode == 2 && !a.first_layer && a.b_stationary && a.cchunks == 1 &&
+  if (a.a_mode == 2 && !a.first_layer && a.b_stationary && (a.cchunks == 1 || split_in) &&
       a.b_total_bytes + 3 * (size_t)(3 * a.a_sub_bytes) <= SMEM_BUDGET && !env().conv_no_kwmerge) {
-    a.kw_merge = 1;
+    a.kw_merge = 1;                                      // (several chunks -- the bf16x3 K extent -- : one merged stage per chunk)
     a.a_stage_bytes = 3 * a.a_sub_bytes;
-    a.stages_per_tile = 1;
+    a.stages_per_tile = a.cchunks;
     a.tx_bytes = a.a_stage_bytes;
   }
   // CTA pairs with B multicast (opt-in, Y2_CONV_CLUSTER=1): each CTA fetches half of the B tile for both.
   // Measured on B200 it is ~15% SLOWER than independent CTAs: the kernel is bound by bytes delivered into
   // each SM (~49 B/clk/SM), which multicast does not reduce -- see DESIGN.md.
   a.cluster = a.cta2 ? 2 : 1;
-  if (a.cta2 && a.a_mode == 2 && !a.b_stationary) {
+  if (a.cta2 && a.a_mode == 2 && !a.b_stationary && !cta2_streamed) {
     set_error("y2_conv_fwd_bf16: internal: halo-patch CTA-pair mode without a resident filter bank");
     return Y2_ERR_UNSUPPORTED;
   }

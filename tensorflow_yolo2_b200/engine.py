@@ -293,12 +293,24 @@ class Yolo2Engine:
         self._slot = 0
         for e in self._free:
             e.record(torch.cuda.current_stream(dev))
+        # results leave through a second side stream: a small device-side snapshot of the outputs (two buffers), then the
+        # device->host copy runs while the NEXT batch computes (the outputs themselves are overwritten by it)
+        self._out_stream = torch.cuda.Stream(device=dev)
+        self._out_stage = [dict(), dict()]
+        self._out_ready = [torch.cuda.Event() for _ in range(2)]
+        self._out_free = [torch.cuda.Event() for _ in range(2)]
+        self._out_slot = 0
+        for e in self._out_free:
+            e.record(torch.cuda.current_stream(dev))
 
     def submit(self, host_images, out_host=None):
         """Enqueue one batch from (pinned) host memory: the host->device copy runs on a copy stream into one of two
         staging buffers, so it overlaps the previous batch's kernels; the step itself and the device->host copy of
         the detections (into `out_host`: dict of pinned tensors keyed keep_idx / keep_count / boxes / scores / net)
-        run on the current stream.  Returns immediately; synchronise the current stream before reading `out_host`."""
+        runs on the current stream; the results are snapshotted on the device and copied to the host on a second side
+        stream, behind the next batch's kernels.  Returns immediately; call wait_outputs() + synchronise the current stream
+        (or torch.cuda.synchronize()) before reading `out_host`.  Successive calls that pass the SAME host buffers
+        overwrite them in submission order."""
         if not hasattr(self, '_copy_stream'):
             self._pipeline_init()
         cur = torch.cuda.current_stream(self.device)
@@ -316,8 +328,28 @@ class Yolo2Engine:
             srcs = dict(net=self.acts[-1])
             if self.decode == 'region':
                 srcs.update(boxes=self.boxes, scores=self.scores, keep_idx=self.keep_idx, keep_count=self.keep_count)
-            for k, dst in out_host.items():
-                dst.copy_(srcs[k], non_blocking=True)
+            j = self._out_slot
+            self._out_slot ^= 1
+            stage = self._out_stage[j]
+            cur.wait_event(self._out_free[j])                   # the D2H that last read this snapshot has finished
+            for k in out_host:
+                if k not in stage:
+                    stage[k] = torch.empty_like(srcs[k])
+                stage[k].copy_(srcs[k], non_blocking=True)      # device-side snapshot (on the compute stream)
+            self._out_ready[j].record(cur)
+            with torch.cuda.stream(self._out_stream):
+                self._out_stream.wait_event(self._out_ready[j])
+                for k, dst in out_host.items():
+                    dst.copy_(stage[k], non_blocking=True)
+                self._out_free[j].record(self._out_stream)
+            self._last_out_event = self._out_free[j]
+
+    def wait_outputs(self):
+        """Make the current stream wait for the device->host copies of every submit() so far (then synchronise the stream,
+        or use torch.cuda.synchronize(), before reading the host buffers)."""
+        ev = getattr(self, '_last_out_event', None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     @property
     def net_out(self):

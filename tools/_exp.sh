@@ -1,7 +1,19 @@
-N=4; TAG=r2e
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-timeout 200 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_infer_${N}gpu.json 2> gpurun_out/${TAG}_infer_${N}gpu.err
-timeout 200 $TR bench.py --mode train --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_train_${N}gpu.json 2> gpurun_out/${TAG}_train_${N}gpu.err
-timeout 100 $TR tools/bench_detect.py --shard strong > gpurun_out/${TAG}_bench_detect_strong_${N}gpu.json 2> gpurun_out/${TAG}_detect_${N}gpu.err
-timeout 100 $TR tools/bench_detect.py --shard weak > gpurun_out/${TAG}_bench_detect_weak_${N}gpu.json 2> gpurun_out/${TAG}_detect_${N}gpu.err
-echo done
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_e2e_gpu.py -q -x -k "conv_split or small or pipelined" 2>&1 | tail -5
+for G in 0 1; do
+  if [ $G = 1 ]; then export Y2_CONV_STREAMK_X3_GENERIC=1; fi
+  timeout 300 python bench.py --steps 20 --warmup 5 --single-mode --precision bf16x3 --no-cpu-baseline --sustain-seconds 0 > gpurun_out/r2f_x3_g$G.json 2>gpurun_out/r2f_x3_g$G.err
+  python - <<PY
+import json
+d=json.loads([l for l in open('gpurun_out/r2f_x3_g$G.json') if l.startswith('{')][-1])
+m=d['precision_modes']['bf16x3']
+print('x3 generic_streamk=$G value %.0f ms %.4f e2e %.0f'%(d['value'], d['ms_per_step'], d['e2e']['value']), [round(x*1e3) for x in m['per_layer_ms']])
+PY
+done
+unset Y2_CONV_STREAMK_X3_GENERIC
+timeout 300 python bench.py --steps 20 --warmup 5 --single-mode --no-cpu-baseline --sustain-seconds 0 > gpurun_out/r2f_bf16.json 2>gpurun_out/r2f_bf16.err
+python - <<PY
+import json
+d=json.loads([l for l in open('gpurun_out/r2f_bf16.json') if l.startswith('{')][-1])
+print('bf16 value %.0f ms %.4f e2e %.0f'%(d['value'], d['ms_per_step'], d['e2e']['value']))
+PY
