@@ -49,6 +49,12 @@ int y2_reload_env(void);
  * on an already-resized BGR image.  out_dtype 0: float32 [N,H,W,3];  1: bf16 [N,H,W,8] with
  * channels 3..7 zero (the layout the first tensor-core conv consumes). */
 int y2_preprocess_u8(const uint8_t* img, void* out, int N, int H, int W, int out_dtype, y2_stream_t stream);
+/* cv2.resize(image, (dst_w, dst_h)) of pascal_detect_darknet.py:35 / img_dataset/pascal_voc.py:61 for an 8-bit 3-channel
+ * image (default INTER_LINEAR), BIT-EXACT: OpenCV's fixed-point algorithm (2048-scaled short coefficients, clamped columns
+ * with zeroed weights, clamped rows with kept weights, ((b * (R >> 4)) >> 16) vertical pass, + 2 >> 2; exact 2x down-scale ->
+ * 2x2 area mean).  src uint8 [src_h, src_w, 3] (device), dst uint8 [dst_h, dst_w, 3] -- typically one row of the engine's
+ * uint8 input batch, so the host never touches pixels after the JPEG decode. */
+int y2_resize_bilinear_u8(const uint8_t* src, int src_h, int src_w, uint8_t* dst, int dst_h, int dst_w, y2_stream_t stream);
 /* float32 [N,H,W,3] (already normalised, what the reference feeds sess.run) -> bf16 [N,H,W,8] */
 int y2_pad_cast_f32_to_bf16c8(const float* x, void* out, int N, int H, int W, y2_stream_t stream);
 
@@ -96,7 +102,13 @@ typedef struct y2_conv_params {
   float alpha;
   int ldy;      /* output row stride in elements; 0 -> Cout */
   int lo_off;   /* OUT_SPLIT: column of the lo half (0 -> Cout); must be 0 otherwise */
+  /* OUT_F32 only, optional: batch-norm statistics of the rows this call stores, without a second pass over them.  When
+   * y2_conv_stats_slab_rows(p) returns R > 0 (the layer runs on the stream-K kernel), a non-NULL stats_slabs receives
+   * [ceil(M / R)][3][Cout] float32 = per R-row slab and channel (k, sum(v - k), sum((v - k)^2)) of the stored values v
+   * (k = the slab's first row); y2_bn_stats_from_slabs folds them.  Must be NULL when the query returns 0. */
+  float* stats_slabs;
 } y2_conv_params;
+int y2_conv_stats_slab_rows(const y2_conv_params* p);
 int y2_conv_cin_padded(int Cin);
 size_t y2_conv_packed_weight_elems(int ksize, int Cin, int Cout);
 int y2_pack_weights_bf16(const float* w_hwio, void* w_packed, int ksize, int Cin, int Cout, y2_stream_t stream);
@@ -140,6 +152,10 @@ int y2_conv1_u8_pool_fwd_split(const uint8_t* img, const void* w_packed, const f
 size_t y2_bn_stats_workspace_bytes(int M, int C);
 int y2_bn_stats(const float* x, int M, int C, int ld, float* mean, float* var,
                 void* workspace, size_t workspace_bytes, y2_stream_t stream);
+/* Mean / biased variance (and, with gamma / beta / scale / shift non-NULL, the folded affine of y2_bn_stats_fold) from the
+ * slab partials a y2_conv_fwd_bf16 call wrote through y2_conv_params.stats_slabs: Chan's merge in float64, fixed order. */
+int y2_bn_stats_from_slabs(const float* slabs, int M, int C, int slab_rows, float* mean, float* var, const float* gamma,
+                           const float* beta, float eps, float* scale, float* shift, y2_stream_t stream);
 /* y2_bn_stats plus, in the same finalising kernel, the folded affine of the centred form
  * y = (x - mean) * scale + shift: scale = gamma * rsqrt(var + eps), shift = beta (what y2_bn_fold
  * gives for mean = 0, bias = NULL) -- the training=True branch of darknet.py:42-44 in two launches. */

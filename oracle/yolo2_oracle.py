@@ -656,6 +656,41 @@ def parse_voc_xml(path):
     return objs, im_h, im_w
 
 
+def resize_bilinear_u8(src, dst_w, dst_h):
+    """cv2.resize(src, (dst_w, dst_h)) for an 8-bit image, default INTER_LINEAR (pascal_detect_darknet.py:35,
+    pascal_voc.py:61).  The arithmetic lives in a third-party dependency that is not in /root/reference: OpenCV
+    (opencv-python 4.13.0 in this image; unpinned by the reference).  Restated from OpenCV's published fixed-point algorithm
+    (modules/imgproc/src/resize.cpp: 2048-scaled short coefficients; columns clamped with the weight zeroed, rows clamped
+    with the weights kept; vertical pass ((b*(R>>4))>>16), then (+2)>>2; exact 2x down-scale -> INTER_AREA) and pinned
+    against cv2.resize itself in tests/test_oracle.py."""
+    src = np.asarray(src)
+    sh, sw = src.shape[:2]
+    s = src.reshape(sh, sw, -1).astype(np.int64)
+    if sw == 2 * dst_w and sh == 2 * dst_h:
+        out = (s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2
+        return out.astype(np.uint8).reshape((dst_h, dst_w) + src.shape[2:])
+
+    def coef(dn, sn, clamp):
+        scale = 1.0 / (float(dn) / float(sn))
+        f = ((np.arange(dn, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s0 = np.floor(f).astype(np.int64)
+        f = (f - s0.astype(np.float32)).astype(np.float32)
+        if clamp:
+            lo, hi = s0 < 0, s0 >= sn - 1
+            f[lo | hi] = 0.0
+            s0 = np.where(lo, 0, np.where(hi, sn - 1, s0))
+        c0 = np.rint((np.float32(1.0) - f) * np.float32(2048.0)).astype(np.int64)
+        c1 = np.rint(f * np.float32(2048.0)).astype(np.int64)
+        return s0, c0, c1
+    xi, a0, a1 = coef(dst_w, sw, True)
+    yi, b0, b1 = coef(dst_h, sh, False)
+    x1 = np.minimum(xi + 1, sw - 1)
+    rows = s[:, xi, :] * a0[None, :, None] + s[:, x1, :] * a1[None, :, None]
+    y0, y1 = np.clip(yi, 0, sh - 1), np.clip(yi + 1, 0, sh - 1)
+    out = (((b0[:, None, None] * (rows[y0] >> 4)) >> 16) + ((b1[:, None, None] * (rows[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8).reshape((dst_h, dst_w) + src.shape[2:])
+
+
 def preprocess_u8(image_u8_bgr_resized):
     """pascal_voc.py:62-64 / pascal_detect_darknet.py:36-37 on an already-resized uint8 BGR
     image: float32, (x / 255.0) * 2.0 - 1.0."""

@@ -44,6 +44,8 @@ struct SkArgs {
   int cin_p, cchunks, ksteps;       // K steps per tile = taps * cchunks   (cin_p: K extent per tap of the B operand)
   int a_wrap;                       // channel chunks of the A tensor (bf16x3: 2/3 of cchunks -- the K loop walks [hi | lo | hi])
   int split_out, lo_off;            // bf16x3 output: hi at column c, lo at column lo_off + c
+  float* stats;                     // out_f32 only: per 32-row slab and column (k, sum(x - k), sum((x - k)^2)) of the stored rows,
+  int cout;                         //   laid out [slab][3][cout] -- batch-norm statistics without a second pass over the rows
   uint32_t fd_cc_mul, fd_cc_shr;    // division by cchunks
   int n_tiles, tiles;
   long long units;                  // tiles * ksteps
@@ -80,6 +82,30 @@ __device__ __forceinline__ void sk_store_rows_bf16(uint32_t stg, int lane, const
     if (grow0 + r < M) *reinterpret_cast<uint4*>(dst + (size_t)(grow0 + r) * ldy + j * 8) = o;
   }
   __syncwarp();
+}
+
+// Batch-norm statistics of one stored 32-row x 32-column chunk, from its swizzled float32 staging tile: lane = column, shifted
+// by the slab's first row (activations reach 1e9 with |mean| >> std under the reference's initialiser: plain sums would
+// cancel).  (k, sum d, sum d^2) per (slab, column); y2_bn_stats_from_slabs merges the slabs in float64.
+__device__ __forceinline__ void sk_slab_stats(const SkArgs& a, uint32_t stg, int lane, int col, long long grow0) {
+  if (grow0 >= a.M) return;
+  const int nvalid = (int)min((long long)32, a.M - grow0);
+  auto at = [&](int r) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stg + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2)));
+    return v;
+  };
+  const float k = at(0);
+  float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    const float d = at(r) - k;
+    if (r < nvalid) { s1 += d; s2 = fmaf(d, d, s2); }
+  }
+  float* o = a.stats + (size_t)(grow0 >> 5) * 3 * a.cout + col + lane;          // lane = column within the chunk
+  o[0] = k;
+  o[a.cout] = s1;
+  o[2 * a.cout] = s2;
 }
 
 // affine + leaky done: convert (and, bf16x3, split into hi / lo) and store one 32 x 32 chunk
@@ -316,6 +342,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                          : "r"(stg + r * 128 + ((j ^ (r & 7)) << 4)));
             if (grow0 + r < a.M) *reinterpret_cast<float4*>(dst + (size_t)(grow0 + r) * a.ldy + j * 4) = o;
           }
+          if (a.stats) sk_slab_stats(a, stg, lane, col0 + c, grow0);
         } else {
           sk_store_chunk_bf16(a, stg, lane, f, col0 + c, grow0);
         }
@@ -630,6 +657,7 @@ conv_streamk2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                          : "r"(stg + r * 128 + ((j ^ (r & 7)) << 4)));
             if (grow0 + r < a.M) *reinterpret_cast<float4*>(dst + (size_t)(grow0 + r) * a.ldy + j * 4) = o;
           }
+          if (a.stats) sk_slab_stats(a, stg, lane, col0 + c, grow0);
         } else {
           sk_store_chunk_bf16(a, stg, lane, f, col0 + c, grow0);
         }
@@ -665,7 +693,9 @@ constexpr size_t SK_FLAG_BYTES = 4096;
 static size_t sk_workspace_bytes(int sms) { return SK_FLAG_BYTES + (size_t)sms * 256 * 256 * sizeof(float); }
 
 // returns Y2_OK and sets *handled = 1 when the layer was issued on this path
-int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
+// dry != 0: only decide (*handled = 2 when the launch would be the CTA-pair kernel, whose float32 epilogue can emit the
+// batch-norm slab statistics; 1 for the single-CTA kernel) -- nothing is enqueued
+int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled, int dry) {
   *handled = 0;
   if (env().conv_no_streamk || g_sk_ws == nullptr) return Y2_OK;
   if ((p->flags & Y2_CONV_POOL2) != 0) return Y2_OK;
@@ -703,6 +733,8 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   a.a_wrap = a_cin / 64;
   a.split_out = split_out ? 1 : 0;
   a.lo_off = lo_off;
+  a.stats = out_f32 ? p->stats_slabs : nullptr;
+  a.cout = p->Cout;
   fastdiv_init((uint32_t)cchunks, &a.fd_cc_mul, &a.fd_cc_shr);
   a.n_tiles = p->Cout / 256;
   // CTA-pair kernel (cta_group::2) unless disabled; 512-row pair tiles (two halves per CTA) unless disabled or too few tiles
@@ -728,6 +760,14 @@ int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   fastdiv_init((uint32_t)p->H, &a.fd_h_mul, &a.fd_h_shr);
   fastdiv_init((uint32_t)ksteps, &a.fd_ks_mul, &a.fd_ks_shr);
 
+  if (dry) {
+    *handled = two_cta ? 2 : 1;
+    return Y2_OK;
+  }
+  if (a.stats && !two_cta) {
+    set_error("y2_conv_fwd_bf16: stats_slabs needs the CTA-pair stream-K kernel (query y2_conv_stats_slab_rows first)");
+    return Y2_ERR_UNSUPPORTED;
+  }
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)a_cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};

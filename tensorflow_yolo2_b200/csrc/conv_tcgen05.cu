@@ -998,11 +998,18 @@ static int launch_conv(int block_n, const CUtensorMap& tmA, const CUtensorMap& t
   }
 }
 
-int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled);   // conv_streamk_tcgen05.cu
+int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled, int dry);   // conv_streamk_tcgen05.cu
 
 }  // namespace y2
 
 using namespace y2;
+
+extern "C" int y2_conv_stats_slab_rows(const y2_conv_params* p) {
+  if (!p || !(p->flags & Y2_CONV_OUT_F32) || load_driver_entry_points() != Y2_OK) return 0;
+  int handled = 0;
+  if (conv_streamk_try(p, nullptr, &handled, 1) != Y2_OK) return 0;
+  return handled == 2 ? 32 : 0;
+}
 
 extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   Y2_ARG(p != nullptr);
@@ -1020,8 +1027,12 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   {
     // float32 pre-BN rows of a deep 3x3 layer on a small map: 256x256 stream-K tiles (conv_streamk_tcgen05.cu)
     int handled = 0;
-    rc = conv_streamk_try(p, (cudaStream_t)stream, &handled);
+    rc = conv_streamk_try(p, (cudaStream_t)stream, &handled, 0);
     if (rc != Y2_OK || handled) return rc;
+  }
+  if (p->stats_slabs) {
+    set_error("y2_conv_fwd_bf16: stats_slabs is only produced by the stream-K path (query y2_conv_stats_slab_rows first)");
+    return Y2_ERR_UNSUPPORTED;
   }
 
   ConvArgs a;

@@ -55,6 +55,58 @@ __global__ void pad_cast_f32_bf16c8_kernel(const float* __restrict__ x, uint4* _
 }
 
 // ---------------------------------------------------------------------------------------------
+// a10  cv2.resize(image, (IS, IS)) -- pascal_detect_darknet.py:35, img_dataset/pascal_voc.py:61 -- for 8-bit BGR images, default
+// interpolation (INTER_LINEAR).  OpenCV (opencv-python 4.13.0 in this image; the algorithm is unchanged since 2.x) computes it
+// in fixed point, which makes a bit-exact GPU restatement possible:
+//   * per output column: fx = (float)((dx + 0.5) * scale_x - 0.5) (double product), sx = floor(fx), fx -= sx; at the borders
+//     (sx < 0 or sx >= W - 1) sx is clamped and fx = 0; coefficients a0 = rint((1 - fx) * 2048), a1 = rint(fx * 2048) as shorts;
+//   * per output row: the same WITHOUT zeroing fy at the borders -- the two source ROWS are clamped instead;
+//   * horizontal pass in int32: R = S[sx] * a0 + S[sx + 1] * a1; vertical: ((b0 * (R0 >> 4)) >> 16) + ((b1 * (R1 >> 4)) >> 16),
+//     then (+ 2) >> 2;
+//   * an exact 2x down-scale in both directions is switched to INTER_AREA: (sum of the 2x2 block + 2) >> 2.
+// One thread per output pixel (3 channels).  scale_x / scale_y arrive as doubles computed like OpenCV does: 1.0 / (dst / src).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void resize_coef(int d, double scale, int sn, bool clamp, int& s0, int& c0, int& c1) {
+  float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);      // (no FMA contraction: two roundings, like the host code)
+  s0 = (int)floorf(f);
+  f -= (float)s0;
+  if (clamp) {
+    if (s0 < 0) { f = 0.0f; s0 = 0; }
+    if (s0 >= sn - 1) { f = 0.0f; s0 = sn - 1; }
+  }
+  c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.0f, f), 2048.0f));
+  c1 = __float2int_rn(__fmul_rn(f, 2048.0f));
+}
+
+__global__ void resize_bilinear_u8c3_kernel(const uint8_t* __restrict__ src, int sh, int sw, size_t src_pitch, uint8_t* __restrict__ dst,
+                                            int dh, int dw, double scale_x, double scale_y, int area2) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw || y >= dh) return;
+  uint8_t* o = dst + ((size_t)y * dw + x) * 3;
+  if (area2) {
+    const uint8_t* p0 = src + (size_t)(2 * y) * src_pitch + (size_t)(2 * x) * 3;
+    const uint8_t* p1 = p0 + src_pitch;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = (uint8_t)(((int)p0[c] + (int)p0[3 + c] + (int)p1[c] + (int)p1[3 + c] + 2) >> 2);
+    return;
+  }
+  int sx, a0, a1, sy, b0, b1;
+  resize_coef(x, scale_x, sw, true, sx, a0, a1);
+  resize_coef(y, scale_y, sh, false, sy, b0, b1);
+  const int x1 = min(sx + 1, sw - 1);
+  const int y0 = min(max(sy, 0), sh - 1), y1 = min(max(sy + 1, 0), sh - 1);
+  const uint8_t* r0 = src + (size_t)y0 * src_pitch;
+  const uint8_t* r1 = src + (size_t)y1 * src_pitch;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int R0 = (int)r0[sx * 3 + c] * a0 + (int)r0[x1 * 3 + c] * a1;
+    const int R1 = (int)r1[sx * 3 + c] * a0 + (int)r1[x1 * 3 + c] * a1;
+    const int v = (((b0 * (R0 >> 4)) >> 16) + ((b1 * (R1 >> 4)) >> 16) + 2) >> 2;
+    o[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // weight packing: TF HWIO [k,k,Cin,Cout] f32  ->  [Cout_p][Kp] bf16, K index = tap*Cin_p + c
 // (K-major rows, the B operand of the implicit GEMM).  Padding rows/columns are zero.
 // First layer (Cin 3 -> 8): [10 k-groups][Cout_p][8] instead: taps 0..7, a zero group, tap 8.
@@ -244,6 +296,52 @@ __global__ void bn_update_moving_kernel(float* __restrict__ mm, float* __restric
   if (c >= C) return;
   mm[c] = mm[c] * momentum + mean[c] * (1.0f - momentum);
   mv[c] = mv[c] * momentum + var[c] * (1.0f - momentum);
+}
+
+// Batch statistics from the per-slab partials the stream-K conv epilogue writes (conv_streamk_tcgen05.cu: sk_slab_stats):
+// slabs [nslab][3][C] = (k, sum(x - k), sum((x - k)^2)) over each 32-row slab.  Chan's pairwise merge in float64, slabs
+// folded in a fixed order (deterministic): block (32 columns, FIN_TY slab lanes), then one lane folds the FIN_TY partials.
+__global__ void __launch_bounds__(32 * 32) bn_stats_from_slabs_kernel(const float* __restrict__ slabs, int nslab, int slab_rows, int M,
+                                                                     int C, float* __restrict__ mean, float* __restrict__ var,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double s_n[32][33], s_mu[32][33], s_m2[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double n = 0.0, mu = 0.0, m2 = 0.0;
+  if (c < C)
+    for (int s = threadIdx.y; s < nslab; s += 32) {
+      const float* p = slabs + (size_t)s * 3 * C + c;
+      const double nb = (double)min(slab_rows, M - s * slab_rows);
+      const double k = (double)p[0], s1 = (double)p[C], s2 = (double)p[2 * C];
+      const double mub = k + s1 / nb, m2b = s2 - s1 * s1 / nb;
+      const double nt = n + nb, delta = mub - mu;
+      mu += delta * nb / nt;
+      m2 += m2b + delta * delta * n * nb / nt;
+      n = nt;
+    }
+  s_n[threadIdx.y][threadIdx.x] = n;
+  s_mu[threadIdx.y][threadIdx.x] = mu;
+  s_m2[threadIdx.y][threadIdx.x] = m2;
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= C) return;
+  for (int y = 1; y < 32; ++y) {
+    const double nb = s_n[y][threadIdx.x];
+    if (nb == 0.0) continue;
+    const double mub = s_mu[y][threadIdx.x], m2b = s_m2[y][threadIdx.x];
+    const double nt = n + nb, delta = mub - mu;
+    mu += delta * nb / nt;
+    m2 += m2b + delta * delta * n * nb / nt;
+    n = nt;
+  }
+  double v = m2 / (double)M;
+  if (v < 0.0) v = 0.0;
+  mean[c] = (float)mu;
+  const float vf = (float)v;
+  var[c] = vf;
+  if (scale) {
+    scale[c] = gamma[c] * rsqrtf(vf + eps);
+    shift[c] = beta[c];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -620,6 +718,18 @@ int y2_preprocess_u8(const uint8_t* img, void* out, int N, int H, int W, int out
   return Y2_OK;
 }
 
+int y2_resize_bilinear_u8(const uint8_t* src, int src_h, int src_w, uint8_t* dst, int dst_h, int dst_w, y2_stream_t stream) {
+  Y2_ARG(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0);
+  // OpenCV: inv_scale = dsize / ssize (double), scale = 1. / inv_scale
+  const double scale_x = 1.0 / ((double)dst_w / (double)src_w), scale_y = 1.0 / ((double)dst_h / (double)src_h);
+  const int area2 = (src_w == 2 * dst_w && src_h == 2 * dst_h) ? 1 : 0;
+  dim3 grid((unsigned)((dst_w + 127) / 128), (unsigned)dst_h);
+  resize_bilinear_u8c3_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, src_h, src_w, (size_t)src_w * 3, dst, dst_h, dst_w, scale_x,
+                                                                     scale_y, area2);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
 int y2_pad_cast_f32_to_bf16c8(const float* x, void* out, int N, int H, int W, y2_stream_t stream) {
   Y2_ARG(x && out && N > 0 && H > 0 && W > 0);
   size_t npix = (size_t)N * H * W;
@@ -714,6 +824,17 @@ int y2_bn_stats_fold(const float* x, int M, int C, int ld, float* mean, float* v
                      float eps, float* scale, float* shift, void* workspace, size_t workspace_bytes, y2_stream_t stream) {
   Y2_ARG(gamma && beta && scale && shift);
   return bn_stats_impl(x, M, C, ld, mean, var, gamma, beta, eps, scale, shift, workspace, workspace_bytes, stream);
+}
+
+int y2_bn_stats_from_slabs(const float* slabs, int M, int C, int slab_rows, float* mean, float* var, const float* gamma,
+                           const float* beta, float eps, float* scale, float* shift, y2_stream_t stream) {
+  Y2_ARG(slabs && mean && var && M > 0 && C > 0 && slab_rows > 0);
+  Y2_ARG((scale == nullptr) == (shift == nullptr) && (!scale || (gamma && beta)));
+  const int nslab = (M + slab_rows - 1) / slab_rows;
+  bn_stats_from_slabs_kernel<<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(slabs, nslab, slab_rows, M, C, mean, var, gamma,
+                                                                                      beta, eps, scale, shift);
+  Y2_LAUNCHED();
+  return Y2_OK;
 }
 
 int y2_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias,

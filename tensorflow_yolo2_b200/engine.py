@@ -100,6 +100,7 @@ class Yolo2Engine:
             self.in_f32 = torch.zeros((N, IS, IS, 3), **f32) if input_kind == 'f32' else None
             self.x0 = torch.empty((N, IS, IS, 8), dtype=torch.bfloat16, device=dev)
             self.acts, self.raw, self.stats = [], {}, {}
+            self.slab_rows, self.slabs = {}, {}           # batch-stat layers whose conv epilogue emits the BN partials
             H = IS
             max_ws = 1
             self.pt_src = None
@@ -231,10 +232,28 @@ class Yolo2Engine:
                 raw = self.raw[li]
                 mean, var, scale, shift, zeros = self.stats[li]
                 bn = L['bn']
-                ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], scale=None, shift=st[L['b']],
-                                  leaky=False, pool=False, out_f32=True, ldy=raw.shape[1], out=raw, split_in=x3)
-                ops.bn_stats_fold(raw, L['cout'], st[bn['gamma']], st[bn['beta']], ld=raw.shape[1], workspace=self.ws,
-                                  mean=mean, var=var, scale=scale, shift=shift)
+                kw = dict(scale=None, shift=st[L['b']], leaky=False, pool=False, out_f32=True, ldy=raw.shape[1], out=raw, split_in=x3)
+                if li not in self.slab_rows:
+                    # does this layer run on the stream-K kernel, whose epilogue can emit the batch-norm partials?  (decided
+                    # once, outside any graph capture: the first enqueue is the warm-up.)  OPT-IN (Y2_FUSED_BN_STATS=1):
+                    # measured slower on B200 -- 1.74-1.76 vs 1.69-1.70 ms per step in two same-run A/Bs: the column pass
+                    # lengthens the stream-K epilogue, which is only partly hidden behind the next segment's MMAs, by more
+                    # than the 17 us statistics pass it replaces
+                    R = 0 if not os.environ.get('Y2_FUSED_BN_STATS') else ops.conv_fwd_bf16(
+                        x, self.packed[li], L['k'], L['cin'], L['cout'], _query_slab_rows=True, **kw)
+                    self.slab_rows[li] = R
+                    if R:
+                        M = raw.shape[0]
+                        self.slabs[li] = torch.empty(((M + R - 1) // R, 3, L['cout']), dtype=torch.float32, device=self.device)
+                R = self.slab_rows[li]
+                if R:
+                    ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], stats_slabs=self.slabs[li], **kw)
+                    ops.bn_stats_from_slabs(self.slabs[li], raw.shape[0], L['cout'], R, st[bn['gamma']], st[bn['beta']],
+                                            mean=mean, var=var, scale=scale, shift=shift)
+                else:
+                    ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], **kw)
+                    ops.bn_stats_fold(raw, L['cout'], st[bn['gamma']], st[bn['beta']], ld=raw.shape[1], workspace=self.ws,
+                                      mean=mean, var=var, scale=scale, shift=shift)
                 ops.affine_leaky_pool(raw, self.N, Hl, Hl, L['cout'], ldx=raw.shape[1], sub=mean, scale=scale, shift=shift,
                                       leaky=True, pool=pool, out_bf16=not last, out=out, ldo=ldo, out_col=col,
                                       space_to_depth=s2d, split_out=x3)
@@ -350,6 +369,19 @@ class Yolo2Engine:
         ev = getattr(self, '_last_out_event', None)
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def load_images(self, images_bgr_u8):
+        """Fill the input batch from RAW decoded images of any size (list of uint8 [H,W,3] BGR arrays / tensors, host or
+        device): each is copied to the device as it is and resized there by y2_resize_bilinear_u8 -- bit-identical to the
+        cv2.resize((IS, IS)) of pascal_detect_darknet.py:35 -- straight into its row of the uint8 batch (the /255*2-1 is
+        fused into the first conv).  At tens of thousands of images per second the host-side cv2.resize is the bottleneck."""
+        assert self.input_kind == 'u8' and len(images_bgr_u8) <= self.N
+        for n, im in enumerate(images_bgr_u8):
+            t = torch.as_tensor(im)
+            assert t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3
+            t = t.to(self.device, non_blocking=True).contiguous()
+            ops.resize_bilinear_u8(t, self.IS, self.IS, out=self.in_u8[n])
+        return self.in_u8
 
     @property
     def net_out(self):

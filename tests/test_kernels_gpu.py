@@ -553,3 +553,67 @@ def test_loss_box_deltas_histogram_inputs(ops, golden_dir):
     want = np.stack([pb[..., 0] - (gt[..., 0] * S - off), pb[..., 1] - (gt[..., 1] * S - off.transpose(0, 2, 1, 3)),
                      pb[..., 2] - np.sqrt(gt[..., 2]), pb[..., 3] - np.sqrt(gt[..., 3])], axis=-1)
     np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------- a2: BN partials out of the conv epilogue
+@pytest.mark.parametrize('N,S,Cin,Cout,k,big_mean', [(32, 13, 512, 1024, 3, False), (70, 13, 512, 512, 3, True)])
+def test_conv_streamk_fused_bn_statistics(ops, N, S, Cin, Cout, k, big_mean):
+    """y2_conv_params.stats_slabs + y2_bn_stats_from_slabs == y2_bn_stats over the stored float32 rows (mean and biased
+    variance), also when |mean| >> std (bias 1e4: the shifted per-slab sums must not cancel) and with a ragged last slab
+    (70 * 169 = 11830 rows)."""
+    rs = np.random.RandomState(Cin + N)
+    x = rs.randn(N, S, S, Cin).astype(np.float32)
+    w = (rs.randn(k, k, Cin, Cout) * 0.05).astype(np.float32)
+    b = (rs.randn(Cout) + (1e4 if big_mean else 0.0)).astype(np.float32)
+    xb, wp, bt = cu(x, torch.bfloat16), ops.pack_weights_bf16(cu(w)), cu(b)
+    M = N * S * S
+    raw = torch.empty((M, Cout), dtype=torch.float32, device='cuda')
+    kw = dict(scale=None, shift=bt, leaky=False, pool=False, out_f32=True, ldy=Cout, out=raw)
+    R = ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, _query_slab_rows=True, **kw)
+    assert R == 32                                           # these shapes run on the CTA-pair stream-K kernel
+    slabs = torch.full(((M + R - 1) // R, 3, Cout), float('nan'), dtype=torch.float32, device='cuda')
+    ops.conv_fwd_bf16(xb, wp, k, Cin, Cout, stats_slabs=slabs, **kw)
+    gamma, beta = cu(rs.uniform(0.5, 1.5, Cout).astype(np.float32)), cu(rs.randn(Cout).astype(np.float32))
+    mean, var, scale, shift = ops.bn_stats_from_slabs(slabs, M, Cout, R, gamma, beta)
+    m2, v2, sc2, sh2 = ops.bn_stats_fold(raw, Cout, gamma, beta)
+    assert not torch.isnan(slabs).any()
+    np.testing.assert_allclose(mean.cpu().numpy(), m2.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(var.cpu().numpy(), v2.cpu().numpy(), rtol=2e-5)
+    np.testing.assert_allclose(scale.cpu().numpy(), sc2.cpu().numpy(), rtol=2e-5)
+    assert torch.equal(shift, sh2)
+    # and against float64 on the stored rows
+    r64 = raw.double()
+    np.testing.assert_allclose(var.cpu().numpy(), r64.var(dim=0, unbiased=False).cpu().numpy(), rtol=2e-5)
+    # a layer that does not run on stream-K reports 0 and refuses the buffer
+    xs, ws = cu(rs.randn(2, 8, 8, 64).astype(np.float32), torch.bfloat16), ops.pack_weights_bf16(cu(rs.randn(3, 3, 64, 256).astype(np.float32)))
+    assert ops.conv_fwd_bf16(xs, ws, 3, 64, 256, out_f32=True, _query_slab_rows=True) == 0
+    with pytest.raises(Exception):
+        ops.conv_fwd_bf16(xs, ws, 3, 64, 256, out_f32=True, stats_slabs=slabs)
+
+
+# ---------------------------------------------------------------------------------- a10 / f2: cv2.resize on the GPU
+def test_resize_bilinear_u8_bit_exact_vs_cv2(ops, golden_dir):
+    """y2_resize_bilinear_u8 == cv2.resize (the call of pascal_detect_darknet.py:35 / pascal_voc.py:61), bit for bit, on the
+    reference's fixtures at 224 / 416 / 608 and on random up- / down-scales incl. the exact-2x INTER_AREA switch; and the
+    engine's load_images() path == host cv2.resize + copy."""
+    import cv2
+    rs = np.random.RandomState(1)
+    cases = []
+    for f in ('testImg1.jpg', 'testImg2.jpg'):
+        im = cv2.imread(os.path.join(golden_dir, f))
+        cases += [(im, IS, IS) for IS in (224, 416, 608)]
+    cases += [(rs.randint(0, 256, (h, w, 3)).astype(np.uint8), dh, dw) for (h, w, dh, dw) in
+              [(240, 352, 416, 416), (375, 500, 608, 608), (832, 832, 416, 416), (100, 100, 416, 416), (1000, 750, 416, 416),
+               (123, 457, 224, 224), (37, 41, 96, 96), (416, 416, 416, 416), (333, 500, 200, 300)]]
+    for im, dh, dw in cases:
+        got = ops.resize_bilinear_u8(cu(im), dh, dw).cpu().numpy()
+        np.testing.assert_array_equal(got, cv2.resize(im, (dw, dh)))
+        np.testing.assert_array_equal(got, O.resize_bilinear_u8(im, dw, dh))
+    from tensorflow_yolo2_b200.engine import Yolo2Engine
+    from tests.helpers import make_store
+    st, _ = make_store(125, tame=True)
+    eng = Yolo2Engine(2, 96, 125, store=st, use_cuda_graph=False)
+    ims = [cv2.imread(os.path.join(golden_dir, f)) for f in ('testImg1.jpg', 'testImg2.jpg')]
+    eng.load_images(ims)
+    want = np.stack([cv2.resize(im, (96, 96)) for im in ims])
+    np.testing.assert_array_equal(eng.in_u8.cpu().numpy(), want)

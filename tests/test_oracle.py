@@ -191,3 +191,21 @@ def test_avg_pool_and_classifier_shapes():
     assert y.shape == (2, 2, 2, 3)
     np.testing.assert_allclose(y[0, 0, 0].numpy(), x[0, :2, :2].reshape(4, 3).mean(0).numpy())
     np.testing.assert_allclose(O.avg_pool_kxk(x, 4)[1, 0, 0].numpy(), x[1].reshape(16, 3).mean(0).numpy())
+
+
+def test_resize_restatement_pinned_to_cv2(golden_dir):
+    """oracle.resize_bilinear_u8 restates OpenCV's fixed-point INTER_LINEAR (a third-party dependency of the reference,
+    pascal_detect_darknet.py:35): bit-exact against cv2.resize on the fixtures and on random images -- up- and down-scales,
+    the exact-2x INTER_AREA switch, non-square sources."""
+    import cv2
+    rs = np.random.RandomState(0)
+    cases = [(rs.randint(0, 256, (h, w, 3)).astype(np.uint8), IS) for (h, w, IS) in
+             [(240, 352, 416), (500, 353, 224), (375, 500, 608), (832, 832, 416), (100, 100, 416), (416, 416, 416),
+              (1000, 750, 416), (123, 457, 224), (37, 41, 96), (448, 448, 224)]]
+    for f in ('testImg1.jpg', 'testImg2.jpg'):
+        im = cv2.imread(os.path.join(golden_dir, f))
+        cases += [(im, IS) for IS in (224, 416, 608)]
+    for im, IS in cases:
+        np.testing.assert_array_equal(O.resize_bilinear_u8(im, IS, IS), cv2.resize(im, (IS, IS)))
+    im = cases[0][0]
+    np.testing.assert_array_equal(O.resize_bilinear_u8(im, 300, 200), cv2.resize(im, (300, 200)))     # non-square target

@@ -124,3 +124,41 @@ def test_train_script_writes_scalar_and_histogram_summaries(fresh_env):
     h = acc.Histograms('iou')
     assert len(h) == 3 and h[0].histogram_value.num == 24 * 7 * 7 * 2          # every cell and predictor (unmasked)
     assert 0.0 <= h[0].histogram_value.min and h[0].histogram_value.max <= 1.0
+
+
+def test_imagenet_test_and_predict_scripts(fresh_env, golden_dir, capsys):
+    """Drop-ins for src/imagenet/imagenet_test_darknet.py and imagenet_predict_darknet.py on a synthetic database: same
+    loop, prints and return values; the logits of the predict script equal the oracle's classifier on the same weights
+    (raw 0..255 pixels, like the reference feeds them)."""
+    import cv2
+    from oracle import yolo2_oracle as O
+    from tensorflow_yolo2_b200 import variables
+    from tensorflow_yolo2_b200.imagenet import imagenet_predict_darknet as predict
+    from tensorflow_yolo2_b200.imagenet import imagenet_test_darknet as test
+    fresh_env.COMPUTE = 'fp32'                                   # exact path: raw 0..255 inputs through 19 layers
+    acc = test.main(['imagenet_test_darknet.py', '--synthetic', '100', '--batches', '2'])
+    out = capsys.readouterr().out
+    assert '######batch number: 2' in out and 'batch 2/2, acc:' in out and '###########validation accuracy:' in out
+    assert 0.0 <= acc <= 1.0
+    variables.reset_default_store(seed=0)
+    img = os.path.join(golden_dir, 'testImg1.jpg')
+    preds, probs = predict.main(['imagenet_predict_darknet.py', img, '--synthetic', '50'])
+    assert len(preds) == 5 and np.all(np.diff(probs) <= 0)
+    st = variables.default_store()
+    names = st.names()
+    core, cls = [], None
+    for li in range(19):
+        w, b = 'darknet19/Variable' + ('' if li == 0 else '_%d' % (2 * li)), 'darknet19/Variable_%d' % (2 * li + 1)
+        bn = 'darknet19/batch_normalization' + ('' if li == 0 else '_%d' % li) + '/'
+        g = lambda n: torch.tensor(np.asarray(st[n].cpu() if hasattr(st[n], 'cpu') else st[n]))
+        p = dict(W=g(w), b=g(b), gamma=g(bn + 'gamma'), beta=g(bn + 'beta'), mm=g(bn + 'moving_mean'), mv=g(bn + 'moving_variance'))
+        if li < 18:
+            core.append(p)
+        else:
+            cls = p
+    assert len(names) == 19 * 6
+    x = cv2.resize(cv2.imread(img), (224, 224)).astype(np.float32)[None]
+    want = O.darknet19_classifier_forward(torch.tensor(x), core, cls, training=False, dtype=torch.float64).numpy()[0]
+    order = np.argsort(-want, kind='stable')[:5]
+    np.testing.assert_allclose(probs, want[order], rtol=2e-3)
+    assert list(preds) == list(order)
