@@ -463,6 +463,138 @@ __global__ void __launch_bounds__(256) conv_wgrad_c3_kernel(const __nv_bfloat16*
   }
 }
 
+// The same weight gradient on the warp-level tensor-core instruction (mma.sync.m16n8k16, bf16 x bf16 -> f32): the FFMA
+// kernel above issues 27 FMAs + ~45 bookkeeping instructions per pixel and lane (1.0 ms of the 14.5 ms training step for
+// 19 GFLOP -- a quarter of the FP32 peak), while the GEMM  D[(tap, ci) = 27 -> 32, co = 32] += A[m][pixel] * B[pixel][co]
+// is 8 MMAs per 16 pixels and warp.  tcgen05 cannot tile it (M = 27, K = 11 M pixels, both operands pixel-major), the
+// synchronous warp MMA can, and at 0.9 GB of operands the kernel is then HBM-bound (~0.15 ms).
+//   smem   x halo tile as bf16 CHANNEL PLANES [ci][10 rows][40], once as is and once shifted by one pixel, so that the two
+//          consecutive pixels an A fragment register holds are one aligned 32-bit load for every horizontal tap;
+//          dh tile [8 rows][32 px][40 (32 co + pad)] read with ldmatrix.trans (B is pixel-major in memory).
+//   warp = tile row (32 pixels = two K blocks); 2 M tiles x 4 N tiles of accumulators per thread; CTA-level reduction
+//   through smem, then one atomicAdd per (tap, ci, co) and CTA, as above.
+__device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int W1_XP = 40;                         // plane pitch (bf16): 34 used, 32-bit loads at even offsets
+constexpr int W1_DP = 40;                         // dh row pitch (bf16): 32 co + 8 pad -> conflict-free ldmatrix rows
+
+__global__ void __launch_bounds__(256) conv_wgrad_c3_mma_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                const __nv_bfloat16* __restrict__ dh, int ld_dh, int N, int H,
+                                                                int W, int Cout, float* __restrict__ dw) {
+  // operands and the final cross-warp reduction share one buffer (static shared memory is capped at 48 KB)
+  constexpr int SX_ELEMS = 2 * 3 * (W1_TH + 2) * W1_XP, SDH_ELEMS = W1_TH * W1_TW * W1_DP;
+  constexpr size_t OPERAND_BYTES = (size_t)(SX_ELEMS + SDH_ELEMS) * 2, RED_BYTES = (size_t)8 * 32 * 33 * 4;
+  __shared__ __align__(16) unsigned char s_raw[OPERAND_BYTES > RED_BYTES ? OPERAND_BYTES : RED_BYTES];
+  typedef __nv_bfloat16 (*SxT)[3][W1_TH + 2][W1_XP];              // [copy: 0 as is, 1 shifted left by one][ci][row][col]
+  typedef __nv_bfloat16 (*SdhT)[W1_TW][W1_DP];
+  typedef float (*SredT)[32][33];
+  SxT s_x = reinterpret_cast<SxT>(s_raw);
+  SdhT s_dh = reinterpret_cast<SdhT>(s_raw + (size_t)SX_ELEMS * 2);
+  SredT s_red = reinterpret_cast<SredT>(s_raw);
+  static_assert(((size_t)SX_ELEMS * 2) % 16 == 0, "dh tile must stay 16-byte aligned");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int tiles_w = (W + W1_TW - 1) / W1_TW, tiles_h = (H + W1_TH - 1) / W1_TH;
+  const int total = N * tiles_h * tiles_w;
+  // per-thread A rows: m = mt * 16 + g + 8 * h  ->  (kh, kw, ci); element offset of the pixel pair (2t, 2t + 1) at p0 = 0
+  int a_off[2][2];
+  bool a_ok[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = mt * 16 + g + 8 * h;
+      a_ok[mt][h] = m < 27;
+      const int tap = m / 3, ci = m - tap * 3, kh = tap / 3, kw = tap - kh * 3;
+      const int copy = kw == 1 ? 1 : 0, sh = kw == 2 ? 2 : 0;
+      a_off[mt][h] = a_ok[mt][h] ? ((copy * 3 + ci) * (W1_TH + 2) + kh) * W1_XP + sh + 2 * t : 0;
+    }
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.0f;
+  const __nv_bfloat16* sx0 = &s_x[0][0][0][0];
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int h0 = th * W1_TH, w0 = tw * W1_TW;
+    __syncthreads();
+    for (int i = tid; i < (W1_TH + 2) * (W1_TW + 2); i += 256) {
+      const int r = i / (W1_TW + 2), cidx = i % (W1_TW + 2);
+      const int hh = h0 + r - 1, ww = w0 + cidx - 1;
+      uint2 v = make_uint2(0u, 0u);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+        v = *reinterpret_cast<const uint2*>(x + ((size_t)(n * H + hh) * W + ww) * 8);
+      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        s_x[0][ci][r][cidx] = e[ci];
+        if (cidx > 0) s_x[1][ci][r][cidx - 1] = e[ci];
+      }
+    }
+    for (int i = tid; i < W1_TH * W1_TW * 4; i += 256) {             // 4 x 16-byte chunks per pixel
+      const int p = i >> 2, q = i & 3;
+      const int r = p / W1_TW, cidx = p % W1_TW;
+      const int hh = h0 + r, ww = w0 + cidx;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (hh < H && ww < W && q * 8 < ld_dh)
+        v = *reinterpret_cast<const uint4*>(dh + ((size_t)(n * H + hh) * W + ww) * ld_dh + q * 8);
+      *reinterpret_cast<uint4*>(&s_dh[r][cidx][q * 8]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {                                  // two blocks of 16 pixels of this warp's row
+      const int p0 = kb * 16;
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const __nv_bfloat16* q = sx0 + a_off[mt][h] + warp * W1_XP + p0;
+          const uint32_t lo = *reinterpret_cast<const uint32_t*>(q), hi = *reinterpret_cast<const uint32_t*>(q + 8);
+          a[mt][h] = a_ok[mt][h] ? lo : 0u;                           // a0 / a1: pixels p0 + 2t, + 1
+          a[mt][2 + h] = a_ok[mt][h] ? hi : 0u;                       // a2 / a3: pixels p0 + 2t + 8, + 9
+        }
+      // B fragments: ldmatrix.x4.trans over [16 pixels][16 co]: matrices (k 0-7, n 0-7) (k 8-15, n 0-7) (k 0-7, n 8-15) (k 8-15, n 8-15)
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const int mi = lane >> 3, rr = lane & 7;
+        const __nv_bfloat16* rowp = &s_dh[warp][p0 + (mi & 1) * 8 + rr][nb * 16 + (mi >> 1) * 8];
+        uint32_t b[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"((uint32_t)__cvta_generic_to_shared(rowp)));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_bf16_16816(acc[mt][nb * 2 + 0], a[mt], b[0], b[1]);
+          mma_bf16_16816(acc[mt][nb * 2 + 1], a[mt], b[2], b[3]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // accumulator (mt, j, e): m = mt * 16 + g + 8 * (e >> 1), co = j * 8 + 2 t + (e & 1)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s_red[warp][mt * 16 + g + 8 * (e >> 1)][j * 8 + 2 * t + (e & 1)] = acc[mt][j][e];
+  __syncthreads();
+  for (int i = tid; i < 27 * 32; i += 256) {
+    const int k = i >> 5, co = i & 31;
+    float s = 0.0f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += s_red[w8][k][co];
+    if (co < Cout) atomicAdd(dw + (size_t)k * Cout + co, s);
+  }
+}
+
 // column sums of a bf16 matrix [M, ld] -> out[C] (+=): conv bias gradient
 __global__ void sum_rows_bf16_kernel(const __nv_bfloat16* __restrict__ a, int ld, size_t M, int C, size_t rows_per_block,
                                      float* __restrict__ out) {
@@ -584,8 +716,12 @@ int y2_conv_wgrad_c3(const void* x_bf16c8, const void* dh_bf16, int ld_dh, int N
   Y2_ARG(x_bf16c8 && dh_bf16 && dw && N > 0 && H > 0 && W > 0 && Cout > 0 && Cout <= 32 && ld_dh >= Cout && ld_dh % 8 == 0);
   const int tiles = N * ((H + W1_TH - 1) / W1_TH) * ((W + W1_TW - 1) / W1_TW);
   const int grid = tiles < 148 * 2 ? tiles : 148 * 2;
-  conv_wgrad_c3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16c8, (const __nv_bfloat16*)dh_bf16,
-                                                               ld_dh, N, H, W, Cout, dw);
+  if (env().bn_bwd_generic)      // (the switch that forces the generic backward kernels: the FFMA version)
+    conv_wgrad_c3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16c8, (const __nv_bfloat16*)dh_bf16,
+                                                                 ld_dh, N, H, W, Cout, dw);
+  else
+    conv_wgrad_c3_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16c8, (const __nv_bfloat16*)dh_bf16,
+                                                                     ld_dh, N, H, W, Cout, dw);
   Y2_LAUNCHED();
   return Y2_OK;
 }

@@ -617,3 +617,22 @@ def test_resize_bilinear_u8_bit_exact_vs_cv2(ops, golden_dir):
     eng.load_images(ims)
     want = np.stack([cv2.resize(im, (96, 96)) for im in ims])
     np.testing.assert_array_equal(eng.in_u8.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize('k,Cin,Cout', [(3, 32, 64), (3, 64, 125), (1, 1024, 125), (3, 512, 1024), (1, 96, 40)])
+def test_pack_weights_tiled_equals_generic(ops, monkeypatch, k, Cin, Cout):
+    """The transposing (coalesced) weight packer writes exactly what the element-wise one does, padding included."""
+    rs = np.random.RandomState(k + Cin + Cout)
+    w = cu(rs.randn(k, k, Cin, Cout).astype(np.float32))
+    n = int(ops._lib.load().y2_conv_packed_weight_elems(k, Cin, Cout))
+    a = torch.full((n,), 7.0, dtype=torch.bfloat16, device='cuda')
+    ops.pack_weights_bf16(w, out=a)
+    monkeypatch.setenv('Y2_AFFINE_GENERIC', '1')            # (the switch that forces every generic element-wise variant)
+    ops.reload_env()
+    b = torch.full((n,), 9.0, dtype=torch.bfloat16, device='cuda')
+    ops.pack_weights_bf16(w, out=b)
+    assert torch.equal(a, b)
+    cout_p = (Cout + 15) // 16 * 16
+    want = torch.zeros((cout_p, k * k, Cin), dtype=torch.float32, device='cuda')
+    want[:Cout] = w.permute(3, 0, 1, 2).reshape(Cout, k * k, Cin)
+    assert torch.equal(a.view(cout_p, k * k, Cin).float(), want.to(torch.bfloat16).float())

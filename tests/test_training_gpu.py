@@ -110,9 +110,15 @@ def test_wgrad_split_k_large_map(ops):
     assert rel_l2(dw.cpu().numpy(), wt.grad.numpy()) < 1e-4
 
 
-def test_wgrad_first_layer(ops):
+@pytest.mark.parametrize('ffma', [False, True])
+@pytest.mark.parametrize('N,H,W,cout', [(2, 40, 72, 32), (1, 13, 19, 32), (3, 64, 64, 24)])
+def test_wgrad_first_layer(ops, monkeypatch, ffma, N, H, W, cout):
+    """First-layer weight gradient: the mma.sync kernel (default) and the FFMA kernel (Y2_BN_BWD_GENERIC=1) against float64
+    autograd -- ragged tiles, fewer than 32 output channels."""
+    if ffma:
+        monkeypatch.setenv('Y2_BN_BWD_GENERIC', '1')
+        ops.reload_env()
     rs = np.random.RandomState(9)
-    N, H, W, cout = 2, 40, 72, 32
     x3 = bf16r(rs.uniform(-1, 1, (N, H, W, 3)))
     x8 = np.zeros((N, H, W, 8), dtype=np.float64)
     x8[..., :3] = x3

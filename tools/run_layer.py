@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Run single Darknet19 layers (batch 64, 416^2 geometry) through the tcgen05 conv, for ncu and for
-quick per-layer timing.   python tools/run_layer.py L3 L19 [--iters 5] [--batch 64]"""
+quick per-layer timing.   python tools/run_layer.py L3 L19 [--iters 5] [--batch 64] [--raw] [--x3]
+--raw: float32 conv + bias rows (the batch-statistics path); --x3: the bf16x3 precision mode (hi + lo operand pairs)."""
 import os
 import sys
 import torch
@@ -27,16 +28,19 @@ def main():
     specs = layer_specs()
     for name in args:
         k, cin, cout, pool, h, head = specs[name]
-        cin_p = ops.conv_cin_padded(cin)
+        x3 = '--x3' in sys.argv
+        cin_p = 2 * cin if x3 else ops.conv_cin_padded(cin)
         x = torch.randn((N, h, h, cin_p), device='cuda').to(torch.bfloat16)
         w = torch.randn((k, k, cin, cout), device='cuda') * 0.05
-        wp = ops.pack_weights_bf16(w)
+        wp = ops.pack_weights_bf16_split(w) if x3 else ops.pack_weights_bf16(w)
         scale = torch.ones(cout, device='cuda')
         shift = torch.zeros(cout, device='cuda')
         ld = (cout + 31) // 32 * 32
         kw = dict(scale=scale, shift=shift, leaky=not head, pool=pool, out_f32=head, ldy=ld if head else None)
         if '--raw' in sys.argv:        # float32 conv + bias rows (batch-statistics BN path)
             kw = dict(scale=None, shift=shift, leaky=False, pool=False, out_f32=True, ldy=ld)
+        if x3:
+            kw.update(split_in=True, split_out=not kw['out_f32'])
         y = ops.conv_fwd_bf16(x, wp, k, cin, cout, **kw)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
