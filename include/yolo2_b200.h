@@ -162,6 +162,11 @@ int y2_bn_stats_from_slabs(const float* slabs, int M, int C, int slab_rows, floa
 int y2_bn_stats_fold(const float* x, int M, int C, int ld, float* mean, float* var, const float* gamma,
                      const float* beta, float eps, float* scale, float* shift,
                      void* workspace, size_t workspace_bytes, y2_stream_t stream);
+/* ... and the UPDATE_OPS of the training step (pascal_train_darknet.py:49-50) in the same finalising kernel:
+ * moving = moving * momentum + batch * (1 - momentum) -- batch statistics of a training layer in two launches. */
+int y2_bn_stats_fold_train(const float* x, int M, int C, int ld, float* mean, float* var, const float* gamma, const float* beta,
+                           float eps, float* scale, float* shift, float* moving_mean, float* moving_var, float momentum,
+                           void* workspace, size_t workspace_bytes, y2_stream_t stream);
 /* scale = gamma * rsqrt(var + eps); shift = beta + (bias_or_0 - mean) * scale.
  * Pass conv_bias when the scale/shift is applied to a bias-free accumulator (fused epilogue),
  * NULL when it is applied to h = conv + b. */

@@ -50,6 +50,7 @@ _SIGNATURES = {
     'y2_bn_stats_workspace_bytes': (_sz, [_i, _i]),
     'y2_bn_stats': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'y2_bn_stats_fold': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
+    'y2_bn_stats_fold_train': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _f, _vp, _sz, _vp]),
     'y2_bn_fold': (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),
     'y2_bn_update_moving': (_i, [_vp, _vp, _vp, _vp, _f, _i, _vp]),
     'y2_affine_leaky_pool': (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),

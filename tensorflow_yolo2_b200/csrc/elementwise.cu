@@ -273,7 +273,8 @@ constexpr int FIN_TY = 32;
 __global__ void __launch_bounds__(32 * FIN_TY) bn_stats_final_kernel(const float* __restrict__ x, const double* __restrict__ part, int splits, int M,
                                       int C, float* __restrict__ mean, float* __restrict__ var,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                      float* __restrict__ scale, float* __restrict__ shift) {
+                                      float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mm,
+                                      float* __restrict__ mv, float momentum) {
   __shared__ double s1[FIN_TY][33], s2[FIN_TY][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double a1 = 0.0, a2 = 0.0;
@@ -297,6 +298,10 @@ __global__ void __launch_bounds__(32 * FIN_TY) bn_stats_final_kernel(const float
   if (scale) {
     scale[c] = gamma[c] * rsqrtf(vf + eps);                    // bit-identical to bn_fold_kernel on (mean = 0, bias = 0)
     shift[c] = beta[c];
+  }
+  if (mm) {                                                    // UPDATE_OPS (same expression as bn_update_moving_kernel)
+    mm[c] = mm[c] * momentum + mean[c] * (1.0f - momentum);
+    mv[c] = mv[c] * momentum + vf * (1.0f - momentum);
   }
 }
 
@@ -816,7 +821,8 @@ static int bn_splits(int M) {
 size_t y2_bn_stats_workspace_bytes(int M, int C) { return (size_t)bn_splits(M) * C * 2 * sizeof(double); }
 
 static int bn_stats_impl(const float* x, int M, int C, int ld, float* mean, float* var, const float* gamma, const float* beta,
-                         float eps, float* scale, float* shift, void* workspace, size_t workspace_bytes, y2_stream_t stream) {
+                         float eps, float* scale, float* shift, void* workspace, size_t workspace_bytes, y2_stream_t stream,
+                         float* mm = nullptr, float* mv = nullptr, float momentum = 0.0f) {
   Y2_ARG(x && mean && var && M > 0 && C > 0 && ld >= C);
   if (!workspace || workspace_bytes < y2_bn_stats_workspace_bytes(M, C)) {
     set_error("y2_bn_stats: workspace too small (%zu < %zu)", workspace_bytes, y2_bn_stats_workspace_bytes(M, C));
@@ -838,7 +844,7 @@ static int bn_stats_impl(const float* x, int M, int C, int ld, float* mean, floa
   }
   Y2_LAUNCHED();
   bn_stats_final_kernel<<<(C + 31) / 32, dim3(32, FIN_TY), 0, st>>>(x, (const double*)workspace, splits, M, C, mean, var, gamma, beta,
-                                                               eps, scale, shift);
+                                                               eps, scale, shift, mm, mv, momentum);
   Y2_LAUNCHED();
   return Y2_OK;
 }
@@ -863,6 +869,14 @@ int y2_bn_stats_from_slabs(const float* slabs, int M, int C, int slab_rows, floa
                                                                                       beta, eps, scale, shift);
   Y2_LAUNCHED();
   return Y2_OK;
+}
+
+int y2_bn_stats_fold_train(const float* x, int M, int C, int ld, float* mean, float* var, const float* gamma, const float* beta,
+                           float eps, float* scale, float* shift, float* moving_mean, float* moving_var, float momentum,
+                           void* workspace, size_t workspace_bytes, y2_stream_t stream) {
+  Y2_ARG(gamma && beta && scale && shift && moving_mean && moving_var);
+  return bn_stats_impl(x, M, C, ld, mean, var, gamma, beta, eps, scale, shift, workspace, workspace_bytes, stream, moving_mean,
+                       moving_var, momentum);
 }
 
 int y2_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias,

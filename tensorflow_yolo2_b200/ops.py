@@ -292,6 +292,21 @@ def bn_stats_fold(x2d, C_, gamma, beta, ld=None, workspace=None, mean=None, var=
     return mean, var, scale, shift
 
 
+def bn_stats_fold_train(x2d, C_, gamma, beta, moving_mean, moving_var, ld=None, workspace=None, mean=None, var=None, scale=None,
+                        shift=None, eps=BN_EPS, momentum=BN_MOMENTUM):
+    """bn_stats_fold + the moving-average update (UPDATE_OPS) in the same two launches."""
+    M = x2d.shape[0]
+    ld = ld or x2d.shape[1]
+    lib = _lib.load()
+    need = int(lib.y2_bn_stats_workspace_bytes(M, C_))
+    ws = workspace if workspace is not None else _workspace(need, x2d.device)
+    check(lib.y2_bn_stats_fold_train(_p(x2d, torch.float32), M, C_, ld, _p(mean), _p(var), _p(gamma, torch.float32),
+                                     _p(beta, torch.float32), eps, _p(scale), _p(shift), _p(moving_mean, torch.float32),
+                                     _p(moving_var, torch.float32), momentum, _p(ws), ws.numel(), _stream()),
+          'y2_bn_stats_fold_train')
+    return mean, var, scale, shift
+
+
 def bn_stats_from_slabs(slabs, M, C_, slab_rows, gamma=None, beta=None, mean=None, var=None, scale=None, shift=None, eps=BN_EPS):
     """Fold the slab partials of conv_fwd_bf16(stats_slabs=...) into (mean, biased var[, scale, shift])."""
     new = lambda: torch.empty((C_,), dtype=torch.float32, device=slabs.device)

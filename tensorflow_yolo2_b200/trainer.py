@@ -217,11 +217,16 @@ class Yolo2Trainer:
             raw = self.raw[li]
             ops.conv_fwd_bf16(x, self.packed[li], L['k'], L['cin'], L['cout'], scale=None, shift=P['b'], leaky=False,
                               pool=False, out_f32=True, ldy=g['ldh'], out=raw)
-            ops.bn_stats(raw, L['cout'], ld=g['ldh'], workspace=self.ws, mean=s['mean'], var=s['var'])
+            # batch statistics, the centred affine (scale = gamma * rsqrt(var + eps), shift = beta) and the UPDATE_OPS of the
+            # moving averages: two launches
             if self.update_moving:
                 bn = L['bn']
-                ops.bn_update_moving(self.store[bn['moving_mean']], self.store[bn['moving_variance']], s['mean'], s['var'])
-            ops.bn_fold(P['gamma'], P['beta'], s['zeros'], s['var'], None, scale=s['scale'], shift=s['shift'])
+                ops.bn_stats_fold_train(raw, L['cout'], P['gamma'], P['beta'], self.store[bn['moving_mean']],
+                                        self.store[bn['moving_variance']], ld=g['ldh'], workspace=self.ws, mean=s['mean'],
+                                        var=s['var'], scale=s['scale'], shift=s['shift'])
+            else:
+                ops.bn_stats_fold(raw, L['cout'], P['gamma'], P['beta'], ld=g['ldh'], workspace=self.ws, mean=s['mean'],
+                                  var=s['var'], scale=s['scale'], shift=s['shift'])
             ops.affine_leaky_pool(raw, self.N, H, H, L['cout'], ldx=g['ldh'], sub=s['mean'], scale=s['scale'],
                                   shift=s['shift'], leaky=True, pool=L['pool'], out_bf16=not last, out=self.acts[li])
             x = self.acts[li]
