@@ -66,7 +66,10 @@ def test_bn_leaky_pool_bwd_vs_autograd(ops, N, H, C, pool, dy_bf16):
 
 
 @pytest.mark.parametrize('N,H,cin,cout,k', [(2, 13, 64, 128, 3), (2, 10, 128, 64, 3), (1, 16, 256, 128, 1),
-                                             (2, 13, 1024, 125, 1), (2, 8, 32, 64, 3), (1, 13, 512, 1024, 3)])
+                                             (2, 13, 1024, 125, 1), (2, 8, 32, 64, 3), (1, 13, 512, 1024, 3),
+                                             (2, 40, 64, 128, 3),      # tile groups: two M tiles per unit (block_n 128), ragged last group
+                                             (3, 36, 32, 64, 3),       # three M tiles per unit (block_n 64)
+                                             (2, 34, 128, 64, 3)])
 def test_dgrad_and_wgrad_vs_autograd(ops, N, H, cin, cout, k):
     rs = np.random.RandomState(cin + cout + k)
     x = bf16r(rs.randn(N, H, H, cin))
