@@ -2,24 +2,31 @@
 """bench.py -- images/sec of Darknet19-YOLO2 416x416 inference (forward + region decode + per-class
 NMS), the metric BASELINE.json names, on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's CUDA path
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|bf16x3]   # this repo's CUDA path
     python bench.py --impl reference [--steps K] [--warmup W]        # CPU restatement of the reference
+    python bench.py --mode train [...]                               # one training step (BASELINE configs[4])
     torchrun ... bench.py --gpus N ...                               # N > 1: one rank per GPU
 
 One "step" = one pass of the hot path over one synthetic batch (64 images of 416x416x3 uint8 per
 GPU, random-init weights of the reference's initialiser, core BN in inference mode, head BN in
 batch-statistics mode -- the reference detect script's graph).  Prints ONE JSON line (rank 0).
 
-value      device-timed throughput with the batch already resident in HBM (CUDA events per step on
+precision  BOTH modes are timed in one invocation (--single-mode: only the selected one).  `--precision` (default bf16, the
+           dtype north_star names for the convs) picks the mode behind value / e2e / roofline and is printed as
+           config.precision; the other one is summarised under precision_modes.  bf16x3 is the mode that meets the 1e-3
+           detections bar (tests/test_parity_gpu.py, profiles/r2*_parity.json); plain bf16 measures 4e-2 on the net output.
+value      device-timed throughput of exactly K steps with the batch already resident in HBM (CUDA events per step on
            the launching stream, L2 flushed between steps, max over ranks).
-e2e        same metric through Yolo2Engine.submit(): pinned host uint8 batch -> H2D -> step -> D2H of
-           the detections, every copy inside the timed region (the H2D of batch i+1 runs on a copy
-           stream and overlaps the kernels of batch i, as a serving loop would).
-roofline   tensor-core bound: algorithmic conv FLOPs of one step / conv time per step vs MEASURED_PEAKS.json.
-           Conv time = min(sum of CUDA events around each of the 22 conv launches in an eager replay, the whole
-           device-timed graph step): eager launches leave idle gaps that the events count, and the convs cannot take
-           longer than the step that contains them (roofline.conv_ms_source names the bound used).  roofline.traffic =
-           DRAM bytes of those launches from the committed ncu launch list (profiles/*_traffic.json).
+e2e        same metric through Yolo2Engine.submit(): pinned host uint8 batch -> H2D -> step -> D2H of the
+           detections, every copy inside the timed region (H2D of batch i+1 on a copy stream, D2H of batch i-1 on a
+           second one, both behind the kernels of batch i, as a serving loop would).
+roofline   tensor-core bound, recomputable by hand: achieved = batch x algorithmic conv FLOPs / (conv_share_of_step x
+           ms_per_step); conv_share_of_step = time of the 22 conv launches / time of the step, both from CUDA-event NODES
+           inside a graph replay of the step (live, this run); peak = the burst figure of MEASURED_PEAKS.json when the K
+           timed steps took < 1 s of wall clock, the sustained one otherwise (regime + all three fractions printed).
+           roofline.traffic = DRAM bytes of the conv launches from the ncu launch list tools/profile_step.sh committed
+           (profiles/r2*_traffic_<mode>.json, with the git HEAD it was taken at).
+sustained  the same step back to back for >= --sustain-seconds (3 s): value of the last quarter of the run + its clocks.
 cpu_baseline  the oracle (CPU restatement of the reference, PyTorch-CPU fp32) on a bounded sample.
 
     --image-size 608 --batch 32    BASELINE.json configs[3] (19x19 grid) instead of the headline 416 / 64

@@ -1,15 +1,27 @@
 #!/bin/bash
-# usage: gpu_round.sh [diag cases...]   -- full validation + bench + per-layer timing
+# Round-closing validation on one B200 (gpurun -- "Y2_HEAD=<sha> bash tools/gpu_round.sh <tag>"): the whole GPU test suite, smoke(),
+# the driver's bench command, BASELINE configs[3], the reference arm, the training step (configs[4]), the decode+NMS
+# microbench (configs[2]) and the ncu launch lists behind roofline.traffic.  Everything lands in gpurun_out/<tag>_*.
+set -u
+TAG=${1:-r2}
 mkdir -p gpurun_out
-: > gpurun_out/diag_conv.log
-for c in "$@"; do
-  timeout 180 python tools/diag_conv.py $c >> gpurun_out/diag_conv.log 2>&1
-  echo "case $c rc=$?" >> gpurun_out/diag_conv.log
-done
-grep -E '"case"|rc=' gpurun_out/diag_conv.log | cut -c1-300
-timeout 900 python -m pytest tests -q -m gpu --timeout 600 -s > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-grep -E "^E  |passed|failed|rc=|rel_l2" gpurun_out/pytest_gpu.log | head -40
-timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?"; tail -3 gpurun_out/bench.log
-timeout 300 python tools/run_layer.py L1 L2 L3 L4 L5 L6 L7 L8 L9 L10 L13 L14 L15 L19 L22 > gpurun_out/layers.log 2>&1; cat gpurun_out/layers.log
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4 | tee gpurun_out/${TAG}_pytest_gpu.txt
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 | tee gpurun_out/${TAG}_smoke.txt
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 2> gpurun_out/${TAG}_bench.err | grep '^{' > gpurun_out/${TAG}_bench.json
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --precision bf16x3 --single-mode --no-cpu-baseline 2>> gpurun_out/${TAG}_bench.err | grep '^{' > gpurun_out/${TAG}_bench_bf16x3.json
+timeout 600 python bench.py --image-size 608 --batch 32 --steps 20 --warmup 5 --no-cpu-baseline 2>> gpurun_out/${TAG}_bench.err | grep '^{' > gpurun_out/${TAG}_bench_608.json
+timeout 600 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 2>> gpurun_out/${TAG}_bench.err | grep '^{' > gpurun_out/${TAG}_bench_reference_arm.json
+timeout 600 python bench.py --mode train --steps 10 --warmup 3 2>> gpurun_out/${TAG}_bench.err | grep '^{' > gpurun_out/${TAG}_bench_train_1gpu.json
+timeout 300 python tools/bench_detect.py 2>> gpurun_out/${TAG}_bench.err | grep '^{' > gpurun_out/${TAG}_bench_detect.json
+bash tools/profile_step.sh ${TAG} 2>&1 | tail -2
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_train_raw.csv python bench.py --mode train --steps 2 --warmup 3 --no-graph --no-cpu-baseline > /dev/null 2>&1
+python tools/ncu_train_breakdown.py gpurun_out/${TAG}_train_raw.csv > gpurun_out/${TAG}_train_breakdown.txt; rm -f gpurun_out/${TAG}_train_raw.csv
+tail -c 400 gpurun_out/${TAG}_bench.err
+python - <<PY
+import json
+for f in ('bench','bench_bf16x3','bench_608','bench_reference_arm','bench_train_1gpu'):
+    try:
+        d=json.loads(open('gpurun_out/${TAG}_%s.json'%f).read().splitlines()[-1])
+        print(f, round(d['value'],1), round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), (d.get('roofline') or {}).get('frac'))
+    except Exception as e: print(f, 'ERR', e)
+PY
