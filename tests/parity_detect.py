@@ -124,13 +124,18 @@ def compare(engine_out, oracle_out, num_class=20, edge=2e-3):
 
 
 def run_case(batch, image_size, tame, precision, score_thresh=0.3, iou_thresh=0.45, seed=0, img_seed=1234, per_layer=False,
-             oracle_cache=None, engine_kwargs=None):
+             oracle_cache=None, engine_kwargs=None, images=None):
     """One parity case.  Weights: the reference's initialiser with seed 0 (tame=False: what bench.py times) or the
     He-scaled variant (tame=True).  Returns the compare() dict (+ per-layer rel-L2 list)."""
     from tensorflow_yolo2_b200.engine import Yolo2Engine
     st, layers = make_store(125, seed=seed, tame=tame)
     core_p, head_p = oracle_params(st, layers)
-    img = np.random.RandomState(img_seed).randint(0, 256, (batch, image_size, image_size, 3)).astype(np.uint8)
+    if images is not None:               # given uint8 [batch, IS, IS, 3] images (e.g. the reference's fixture) instead of random ones
+        img = np.ascontiguousarray(images, dtype=np.uint8)
+        assert img.shape == (batch, image_size, image_size, 3)
+        img_seed = 'given:%d' % int(img.astype(np.int64).sum())
+    else:
+        img = np.random.RandomState(img_seed).randint(0, 256, (batch, image_size, image_size, 3)).astype(np.uint8)
     key = (batch, image_size, tame, seed, img_seed, score_thresh, iou_thresh, per_layer)
     t0 = time.time()
     if oracle_cache is not None and key in oracle_cache:

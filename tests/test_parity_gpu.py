@@ -248,3 +248,26 @@ def test_detections_tame_416_bf16x3():
     _dump_report()
     assert r3['matched'] > 0
     assert r3['score_rel_max'] < 1e-3 and r3['box_rel_max'] < 1e-3, r3
+
+
+@pytest.mark.parametrize('tame', [False, True])
+def test_detections_config0_testimg1_batch1(golden_dir, tame):
+    """BASELINE configs[0]: 416x416 detect on the reference's tests/testImg1.jpg, batch 1, random-init weights, 20 classes,
+    5 anchors -- the image read and resized on the GPU by the engine (load_images == cv2.resize, bit-exact), bf16x3 engine
+    against the float64 oracle end to end.  (Batch 1: the head's batch statistics run over 169 cells only.)"""
+    import cv2
+    from tensorflow_yolo2_b200.engine import Yolo2Engine
+    from tests.helpers import make_store
+    raw = cv2.imread(os.path.join(golden_dir, 'testImg1.jpg'))
+    st, _ = make_store(125, tame=tame)
+    eng = Yolo2Engine(1, 416, 125, store=st, use_cuda_graph=False, precision='bf16x3')
+    eng.load_images([raw])
+    img = eng.in_u8.cpu().numpy()
+    np.testing.assert_array_equal(img[0], cv2.resize(raw, (416, 416)))
+    del eng
+    r3 = _case(1, 416, tame, 'bf16x3', score_thresh=0.1, images=img)
+    r1 = _case(1, 416, tame, 'bf16', score_thresh=0.1, images=img)
+    _dump_report()
+    assert r3['net_rel_l2'] < 3e-4, r3
+    assert r3['score_rel_max'] < 1e-3 and r3['box_rel_max'] < 1e-3 and r3['unexplained_list_differences'] == 0, r3
+    assert r1['net_rel_l2'] < 8e-2, r1
