@@ -40,6 +40,8 @@ static void env_read() {
   e.conv_streamk_x3_generic = on("Y2_CONV_STREAMK_X3_GENERIC");
   e.wgrad_cta2 = on("Y2_WGRAD_CTA2");
   e.wgrad_no_group = on("Y2_WGRAD_NO_GROUP");
+  e.conv_no_is = on("Y2_CONV_NO_IS");
+  e.conv_force_is = on("Y2_CONV_FORCE_IS");
   e.conv_streamk_min_ksteps = num("Y2_CONV_STREAMK_MIN_KSTEPS", -1);
   e.conv_block_n = num("Y2_CONV_BLOCK_N", 0);
   e.conv1_debug = num("Y2_CONV1_DEBUG", 0);

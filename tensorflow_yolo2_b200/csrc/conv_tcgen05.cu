@@ -880,6 +880,211 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// Input-stationary 3x3 convolution for the 64-filter layers on large maps (Darknet19 layers 2 and 4), CTA pairs.
+//
+// Why.  At N = 64 a pair MMA fetches (4096 + 16 * 64) B of operands for 32 clk of arithmetic: 80 clk at the ~64 B/clk of
+// the smem operand path, i.e. the tensor pipe cannot exceed 40 % however the loop is written (section 4.1 of DESIGN.md;
+// measured 43 %).  The A slice (128 pixels x 16 channels) is what is expensive, and the tap loop re-reads it nine times.
+// Here the three HORIZONTAL taps become column blocks of ONE MMA: D[p, (kw, co)] = sum_{kh, c} A[p + kh rows, c] *
+// W[kh][kw][c][co] with N = 3 * 64 = 192, so an A slice is read once per filter ROW: (4096 + 16 * 192) / 64 = 112 clk for
+// 96 clk of arithmetic (86 %).  The horizontal shift moves to the accumulator: out[h, w] = D[(h, w - 1), kw = 0] +
+// D[(h, w), kw = 1] + D[(h, w + 1), kw = 2] -- two warp shuffles per output value in the epilogue, which is why the tile is
+// 8 rows x 16 pixels (a 16-lane half warp per row): lane L of a row produces output column L from D rows L, L + 1, L + 2,
+// columns 14 and 15 of every tile are halo (tiles advance by 14 pixels: 87.5 % of the MMA rows are outputs).
+//   smem   [resident filters: (kh, chunk) sub-blocks of 96 rows x KCHUNK -- this CTA's half of the 192 (kw, co) rows]
+//          [ring of (8 + 2) x 16 pixel patches, one per channel chunk]; the vertical taps are descriptor shifts by one patch
+//          row (two swizzle atoms), as in the halo-patch mode of conv_tc_kernel
+//   TMEM   two accumulators of 192 columns; roles, barriers and the epilogue math (scale/shift, leaky, pool, bf16 / bf16x3 /
+//          float32 stores) are those of conv_tc_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int IS_N = 192, IS_COUT = 64, IS_OUT_W = 14, IS_TW = 16, IS_TH = 8, IS_PROWS = IS_TH + 2;
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_is_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+  constexpr uint32_t ROW_BYTES = KIND == 1 ? 64u : 128u;
+  constexpr int KSTEPS = ROW_BYTES / 32;
+  constexpr int NBUF = 2;
+  constexpr uint32_t A_STAGE = IS_PROWS * IS_TW * ROW_BYTES;           // 160 patch pixels
+  constexpr uint32_t B_SUB = (IS_N / 2) * ROW_BYTES;                   // 96 (kw, co) rows of one (kh, chunk) sub-block
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar[NBUF], tmem_empty_bar[NBUF], bfull_bar;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(16) float s_scale[IS_COUT], s_shift[IS_COUT];
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_b = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_b + ((a.b_total_bytes + 1023u) & ~1023u);
+  const uint32_t crank = cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+  const int nsub = 3 * a.cchunks;                                      // (kh, chunk) sub-blocks
+
+  if (warp == WARP_PRODUCER && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 16); }   // 2 groups x 4 warps x 2 CTAs
+    mbar_init(&bfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();
+  if (threadIdx.x < IS_COUT) {
+    s_scale[threadIdx.x] = a.scale ? __ldg(a.scale + threadIdx.x) : 1.0f;
+    s_shift[threadIdx.x] = a.shift ? __ldg(a.shift + threadIdx.x) : 0.0f;
+  }
+  __syncthreads();
+  // pair p takes super tiles p, p + npairs, ...: two consecutive tiles (rank 0 / 1); tile -> (n, th, tw)
+  const int m_groups = (a.m_tiles + 1) / 2;
+  auto tile_of = [&](int sg, int& n, int& h0, int& w0) {
+    uint32_t mt = (uint32_t)sg * 2u + crank;
+    if ((int)mt >= a.m_tiles) mt = (uint32_t)a.m_tiles - 1u;            // odd tile count: the partner repeats the last tile (same values stored twice)
+    const uint32_t q = fdiv(mt, a.fd_w_mul, a.fd_w_shr);                // / tiles_w
+    const uint32_t twi = mt - q * (uint32_t)a.tiles_w;
+    const uint32_t ni = fdiv(q, a.fd_h_mul, a.fd_h_shr);                // / tiles_h
+    const uint32_t thi = q - ni * (uint32_t)a.tiles_h;
+    n = (int)ni; h0 = (int)thi * IS_TH; w0 = (int)twi * IS_OUT_W;
+  };
+
+  if (warp == WARP_PRODUCER) {
+    // ---- resident filters: this CTA's 96 of the 192 (kw, co) rows of every (kh, chunk) sub-block, three 32-row pieces each ----
+    if (lane == 0 && crank == 0) mbar_expect_tx(&bfull_bar, 2u * a.b_total_bytes);
+    __syncwarp();
+    const uint32_t bbar = smem_u32(&bfull_bar) & PEER_BIT_MASK;
+    for (int i = lane; i < nsub * 3; i += 32) {
+      const int sub = i / 3, piece = i - sub * 3;
+      const int kh = sub / a.cchunks, cc = sub - kh * a.cchunks;
+      const int nrow = (int)crank * (IS_N / 2) + piece * 32;           // row of the (kw, co) stack
+      const int kw = nrow >> 6, co0 = nrow & 63;
+      tma_load_2d_2sm(smem_b + (uint32_t)sub * B_SUB + (uint32_t)piece * 32u * ROW_BYTES, &tmB, bbar,
+                      (kh * 3 + kw) * a.cin_p + cc * a.kchunk, co0);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int sg = pair; sg < m_groups; sg += npairs) {
+        int n, h0, w0;
+        tile_of(sg, n, h0, w0);
+        for (int cc = 0; cc < a.cchunks; ++cc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (crank == 0) mbar_expect_tx(&full_bar[stage], 2u * A_STAGE);
+          const int ca = cc < a.a_wrap ? cc : cc - a.a_wrap;              // bf16x3: the third K block re-reads the hi channels
+          tma_load_4d_2sm(smem_a + stage * A_STAGE, &tmA, smem_u32(&full_bar[stage]) & PEER_BIT_MASK, ca * a.kchunk, w0 - 1, h0 - 1, n);
+          if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    if (crank == 0) {
+      uint32_t is_leader;
+      asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(is_leader));
+      // D = f32, A = B = bf16, K-major both, N = 192, M = 256 (the pair)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(IS_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      constexpr uint32_t layout = KIND == 1 ? 4u : 2u;
+      const uint64_t adesc0 = make_smem_desc(smem_a, 16u, 8u * ROW_BYTES, layout);
+      const uint64_t bdesc0 = make_smem_desc(smem_b, 16u, 8u * ROW_BYTES, layout);
+      constexpr uint32_t KH16 = (IS_TW * ROW_BYTES) >> 4;              // one patch row = two swizzle atoms
+      mbar_wait(&bfull_bar, 0);
+      tc_fence_after();
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int sg = pair; sg < m_groups; sg += npairs, ++it) {
+        const uint32_t buf = it & 1u;
+        mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * (uint32_t)IS_N;
+        uint32_t accum = 0;
+        for (int cc = 0; cc < a.cchunks; ++cc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (is_leader) {
+            const uint64_t ad = adesc0 + (uint32_t)((stage * A_STAGE) >> 4);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint64_t bd = bdesc0 + (uint32_t)(((uint32_t)(kh * a.cchunks + cc) * B_SUB) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < KSTEPS; ++ks) {
+                umma_bf16_2sm(tmem_d, ad + (uint32_t)kh * KH16 + (uint32_t)(ks * 2), bd + (uint32_t)(ks * 2), idesc, accum);
+                accum = 1;
+              }
+            }
+            umma_commit_2sm_mc(smem_u32(&empty_bar[stage]), (uint16_t)3);
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (is_leader) umma_commit_2sm_mc(smem_u32(&tmem_full_bar[buf]), (uint16_t)3);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- epilogue: group gi -> tiles of parity tp, output channels [cp * 32, cp * 32 + 32) ----
+    const int q = warp & 3, gi = warp >> 2;
+    const int tp = gi & 1, cp = gi >> 1;
+    const int r = q * 32 + lane;
+    const int r_tw = r & (IS_TW - 1), r_th = r >> 4;
+    const bool pool = (a.flags & Y2_CONV_POOL2) != 0;
+    const bool leaky_on = (a.flags & Y2_CONV_LEAKY) != 0;
+    const bool out_f32 = (a.flags & Y2_CONV_OUT_F32) != 0;
+    const int Ho = pool ? a.H >> 1 : a.H, Wo = pool ? a.W >> 1 : a.W;
+    const int cc0 = cp * 32;
+    int it = tp;
+    for (int sg = pair + tp * npairs; sg < m_groups; sg += 2 * npairs, it += 2) {
+      int n, h0, w0;
+      tile_of(sg, n, h0, w0);
+      const int h = h0 + r_th, w = w0 + r_tw;
+      const bool valid_px = r_tw < IS_OUT_W && h < a.H && w < a.W;
+      const bool valid = valid_px && (!pool || (((r_tw | r_th) & 1) == 0));
+      const long long orow = (long long)((n * Ho + (pool ? h >> 1 : h)) * Wo + (pool ? w >> 1 : w));
+      const uint32_t buf = (uint32_t)tp;
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)IS_N + (uint32_t)cc0;
+      uint32_t sum[32];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v0[16], v1[16], v2[16];
+        tmem_ld_cols<16>(taddr + (uint32_t)(hf * 16), v0);
+        tmem_ld_cols<16>(taddr + (uint32_t)(IS_COUT + hf * 16), v1);
+        tmem_ld_cols<16>(taddr + (uint32_t)(2 * IS_COUT + hf * 16), v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float c1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), 1);
+          const float c2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2);
+          sum[hf * 16 + i] = __float_as_uint((__uint_as_float(v0[i]) + c1) + c2);      // taps kw = 0, 1, 2 in order
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[buf]) & PEER_BIT_MASK);
+      if (pool && !out_f32 && (a.ldy & 7) == 0 && (a.lo_off & 7) == 0)
+        epilogue_chunk_pooled_bf16(a, sum, s_scale, s_shift, cc0, cc0, valid_px, orow, leaky_on, lane);
+      else
+        epilogue_chunk<32>(a, sum, s_scale, s_shift, cc0, cc0, valid, orow, pool, leaky_on, out_f32);
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == WARP_MMA) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side: tensor maps (driver entry points fetched at run time -> no libcuda link dependency)
 // ------------------------------------------------------------------------------------------
 PFN_encodeTiled g_encodeTiled = nullptr;
@@ -1000,6 +1205,96 @@ static int launch_conv(int block_n, const CUtensorMap& tmA, const CUtensorMap& t
 
 int conv_streamk_try(const y2_conv_params* p, cudaStream_t st, int* handled, int dry);   // conv_streamk_tcgen05.cu
 
+// The input-stationary kernel (conv_is_kernel): 3x3, Cout == 64, maps >= 64 x 64, filters resident.  *handled = 1 when issued.
+static int conv_is_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
+  *handled = 0;
+  if (env().conv_no_is || p->ksize != 3 || p->Cout != IS_COUT || p->H < 64 || p->W < 64 || p->Cin % 32 != 0 || g_num_sms < 2) return Y2_OK;
+  const bool split_in = (p->flags & Y2_CONV_IN_SPLIT) != 0;
+  const bool out_f32 = (p->flags & Y2_CONV_OUT_F32) != 0;
+  const bool split_out = (p->flags & Y2_CONV_OUT_SPLIT) != 0 && !out_f32;
+  const bool pool = (p->flags & Y2_CONV_POOL2) != 0;
+  // Short K (layer 2: 32 channels) is epilogue-bound, and this kernel's epilogue is the heavier one (three accumulator
+  // blocks + two shuffles per value): measured 149 vs 115 us there, against 88 vs 114 us on layer 4 (128 channels).
+  if ((split_in ? 3 : 1) * p->Cin < 96 && !env().conv_force_is) return Y2_OK;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.scale = p->scale; a.shift = p->shift; a.y = p->y;
+  a.N = p->N; a.H = p->H; a.W = p->W; a.Cout = p->Cout;
+  a.M = (long long)p->N * p->H * p->W;
+  a.split_out = split_out ? 1 : 0;
+  a.lo_off = split_out ? (p->lo_off > 0 ? p->lo_off : p->Cout) : 0;
+  a.ldy = p->ldy > 0 ? p->ldy : (split_out ? 2 * p->Cout : p->Cout);
+  if (a.ldy < p->Cout || (split_out && (a.lo_off < p->Cout || a.ldy < a.lo_off + p->Cout))) return Y2_OK;   // (the generic path reports it)
+  a.flags = p->flags; a.alpha = p->alpha; a.ksize = 3; a.pad = 1;
+  a.cin_p = split_in ? 3 * p->Cin : p->Cin;
+  const int a_cin = split_in ? 2 * p->Cin : p->Cin;
+  a.kchunk = (p->Cin % 64 == 0) ? 64 : 32;
+  a.row_bytes = a.kchunk * 2;
+  a.cchunks = a.cin_p / a.kchunk;
+  a.a_wrap = a_cin / a.kchunk;
+  a.kblocks = 9 * a.cchunks;
+  a.tw_log2 = 4; a.th_log2 = 3; a.nb_log2 = 0;
+  a.tiles_w = (p->W + IS_OUT_W - 1) / IS_OUT_W; a.tiles_h = (p->H + IS_TH - 1) / IS_TH; a.tiles_nb = p->N;
+  const long long tiles = (long long)a.tiles_w * a.tiles_h * p->N;
+  if (tiles < 2 || tiles >= (1ll << 30) || a.M >= (1ll << 31)) return Y2_OK;
+  a.m_tiles = (int)tiles; a.n_tiles = 1;
+  a.a_stage_bytes = (uint32_t)(IS_PROWS * IS_TW * a.row_bytes);
+  a.b_sub_bytes = (uint32_t)((IS_N / 2) * a.row_bytes);
+  a.b_total_bytes = (uint32_t)(3 * a.cchunks) * a.b_sub_bytes;
+  const size_t SMEM_BUDGET = 218 * 1024;
+  const size_t b_region = ((size_t)a.b_total_bytes + 1023) & ~(size_t)1023;
+  if (b_region + 3 * (size_t)a.a_stage_bytes > SMEM_BUDGET) return Y2_OK;      // filters not resident: the halo-patch kernel
+  int stages = (int)((SMEM_BUDGET - b_region) / a.a_stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  a.stages = stages;
+  fastdiv_init((uint32_t)a.tiles_w, &a.fd_w_mul, &a.fd_w_shr);
+  fastdiv_init((uint32_t)a.tiles_h, &a.fd_h_mul, &a.fd_h_shr);
+  const size_t smem = b_region + (size_t)stages * a.a_stage_bytes + 1024;
+  int rc = load_driver_entry_points();
+  if (rc != Y2_OK) return rc;
+  CUtensorMap tmA, tmB;
+  const CUtensorMapSwizzle sw = swizzle_for(a.row_bytes);
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a_cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t strides[3] = {(cuuint64_t)a_cin * 2, (cuuint64_t)p->W * a_cin * 2, (cuuint64_t)p->H * p->W * a_cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)a.kchunk, (cuuint32_t)IS_TW, (cuuint32_t)IS_PROWS, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encodeTiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("y2_conv_fwd_bf16 (input-stationary): tensor map A encode failed (CUresult %d)", (int)r); return Y2_ERR_DRIVER; }
+    const int Kp = 9 * a.cin_p;
+    cuuint64_t bdims[2] = {(cuuint64_t)Kp, (cuuint64_t)IS_COUT};
+    cuuint64_t bstrides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t bbox[2] = {(cuuint32_t)a.kchunk, 32};
+    cuuint32_t bestr[2] = {1, 1};
+    r = g_encodeTiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->w_packed), bdims, bstrides, bbox, bestr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("y2_conv_fwd_bf16 (input-stationary): tensor map B encode failed (CUresult %d)", (int)r); return Y2_ERR_DRIVER; }
+  }
+  (void)pool;
+  const int groups = (a.m_tiles + 1) / 2;
+  const int npairs = groups < g_num_sms / 2 ? groups : g_num_sms / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(2 * npairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr;
+  cfg.numAttrs = fill_launch_attrs(attr, 2u);
+  if (a.row_bytes == 64) {
+    Y2_CUDA(cudaFuncSetAttribute(conv_is_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_is_kernel<1>, tmA, tmB, a));
+  } else {
+    Y2_CUDA(cudaFuncSetAttribute(conv_is_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_is_kernel<2>, tmA, tmB, a));
+  }
+  Y2_LAUNCHED();
+  *handled = 1;
+  return Y2_OK;
+}
+
 }  // namespace y2
 
 using namespace y2;
@@ -1033,6 +1328,11 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   if (p->stats_slabs) {
     set_error("y2_conv_fwd_bf16: stats_slabs is only produced by the stream-K path (query y2_conv_stats_slab_rows first)");
     return Y2_ERR_UNSUPPORTED;
+  }
+  {
+    int handled = 0;
+    rc = conv_is_try(p, (cudaStream_t)stream, &handled);
+    if (rc != Y2_OK || handled) return rc;
   }
 
   ConvArgs a;

@@ -93,6 +93,8 @@ def test_conv_halo_pair_vs_single_cta_and_oracle(ops, monkeypatch, N, H, W, Cin,
     xb = cu(x, torch.bfloat16)
     wp = ops.pack_weights_bf16(cu(w))
     kw = dict(scale=cu(sc), shift=cu(b), leaky=True, pool=pool)
+    monkeypatch.setenv('Y2_CONV_NO_IS', '1')         # (the 64-filter shapes would otherwise take the input-stationary kernel)
+    ops.reload_env()
     got = ops.conv_fwd_bf16(xb, wp, 3, Cin, Cout, **kw)
     monkeypatch.setenv('Y2_CONV_NO_CTA2', '1')
     ops.reload_env()                     # the launchers cache the Y2_* switches
@@ -108,6 +110,66 @@ def test_conv_halo_pair_vs_single_cta_and_oracle(ops, monkeypatch, N, H, W, Cin,
     g = got.float().cpu().numpy()
     np.testing.assert_allclose(g, want, rtol=1e-2, atol=1e-2 * np.abs(want).max())
     assert np.linalg.norm(g - want) / np.linalg.norm(want) < 4e-3
+
+
+@pytest.mark.parametrize('N,H,W,Cin,pool,out_f32,x3', [(3, 72, 72, 32, True, False, False),     # layer 2 shape: 64-byte rows, pooled epilogue
+                                                         (1, 104, 104, 128, False, False, False),  # layer 4 shape: two chunks, odd tile count
+                                                         (2, 70, 66, 64, False, False, False),     # ragged: W % 14 != 0, H % 8 != 0
+                                                         (2, 64, 64, 64, True, True, False),       # float32 rows + pool (generic epilogue)
+                                                         (2, 80, 72, 128, False, True, False),     # training forward / float32 rows
+                                                         (2, 72, 72, 32, True, False, True),       # bf16x3: three K blocks, split output
+                                                         (1, 64, 98, 64, False, False, False)])    # exactly 7 tiles wide
+def test_conv_input_stationary_vs_halo_kernel_and_oracle(ops, monkeypatch, N, H, W, Cin, pool, out_f32, x3):
+    """conv_is_kernel (3x3, 64 filters, maps >= 64x64: the three horizontal taps as column blocks of one N = 192 MMA, the
+    horizontal shift applied to the accumulators with warp shuffles) against the halo-patch kernel it replaces
+    (Y2_CONV_NO_IS=1: same products, different fp32 summation order) and the float64 oracle on the same operands."""
+    Cout = 64
+    rs = np.random.RandomState(H + W + Cin)
+    x = rs.randn(N, H, W, Cin).astype(np.float32)
+    w = (rs.randn(3, 3, Cin, Cout) * 0.05).astype(np.float32)
+    b = rs.randn(Cout).astype(np.float32)
+    sc = (rs.uniform(0.5, 1.5, Cout) * np.where(rs.rand(Cout) < 0.3, -1, 1)).astype(np.float32)
+    if x3:
+        t = torch.tensor(x)
+        hi = t.to(torch.bfloat16)
+        xb = torch.cat([hi, (t - hi.float()).to(torch.bfloat16)], dim=-1).contiguous().cuda()
+        wp = ops.pack_weights_bf16_split(cu(w))
+        xo = (hi.float() + (t - hi.float()).to(torch.bfloat16).float()).double()
+        wt = torch.tensor(w)
+        wh = wt.to(torch.bfloat16).float()
+        wo = (wh + (wt - wh).to(torch.bfloat16).float()).double()
+    else:
+        xb, wp = cu(x, torch.bfloat16), ops.pack_weights_bf16(cu(w))
+        xo, wo = O.bf16_round(torch.tensor(x)).double(), O.bf16_round(torch.tensor(w)).double()
+    kw = dict(scale=cu(sc), shift=cu(b), leaky=True, pool=pool, out_f32=out_f32, split_in=x3, split_out=x3 and not out_f32)
+    monkeypatch.setenv('Y2_CONV_FORCE_IS', '1')        # (by default the kernel is only chosen for K >= 96 channels per tap)
+    ops.reload_env()
+    got = ops.conv_fwd_bf16(xb, wp, 3, Cin, Cout, **kw)
+    monkeypatch.delenv('Y2_CONV_FORCE_IS')
+    monkeypatch.setenv('Y2_CONV_NO_IS', '1')
+    ops.reload_env()
+    ref = ops.conv_fwd_bf16(xb, wp, 3, Cin, Cout, **kw)
+    torch.cuda.synchronize()
+    want = O.conv2d_same(xo, wo, torch.float64) * torch.tensor(sc).double() + torch.tensor(b).double()
+    want = torch.maximum(O.ALPHA * want, want)
+    if pool:
+        want = O.max_pool_2x2(want)
+    want = want.numpy()
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+
+    def f32(t):
+        if out_f32:
+            return t.view(N, Ho, Wo, Cout).cpu().numpy()
+        if x3:
+            return (t[..., :Cout].float() + t[..., Cout:].float()).cpu().numpy()
+        return t.float().cpu().numpy()
+    g, r = f32(got), f32(ref)
+    tol = 3e-5 if (x3 or out_f32) else 4e-3
+    e_g, e_r = np.linalg.norm(g - want) / np.linalg.norm(want), np.linalg.norm(r - want) / np.linalg.norm(want)
+    print('input-stationary rel_l2 %.3g (halo kernel %.3g)' % (e_g, e_r))
+    assert e_g < tol and e_r < tol
+    # same products, only the fp32 summation order differs: the two kernels agree far inside the output rounding
+    np.testing.assert_allclose(g, r, rtol=2e-2 if not (x3 or out_f32) else 1e-4, atol=(1e-2 if not (x3 or out_f32) else 1e-4) * np.abs(want).max())
 
 
 @pytest.mark.parametrize('N,S,Cin,Cout,k,pool,out_f32', [(5, 26, 256, 512, 3, True, False),     # tiled boxes + fused pool, 256-wide, streamed B
