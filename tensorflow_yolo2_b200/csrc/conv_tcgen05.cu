@@ -914,8 +914,12 @@ conv_is_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // resident filters (b_stationary): [all (kh, chunk) sub-blocks][ring of patches]; streamed (bf16x3 at 128 channels: the bank
+  // does not fit): every ring stage is [patch | the chunk's three kh sub-blocks]
+  const bool bstat = a.b_stationary != 0;
   const uint32_t smem_b = (smem_u32(smem) + 1023u) & ~1023u;
-  const uint32_t smem_a = smem_b + ((a.b_total_bytes + 1023u) & ~1023u);
+  const uint32_t smem_a = smem_b + (bstat ? ((a.b_total_bytes + 1023u) & ~1023u) : 0u);
+  const uint32_t stage_bytes = A_STAGE + (bstat ? 0u : 3u * B_SUB);
   const uint32_t crank = cluster_ctarank();
   const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
   const int nsub = 3 * a.cchunks;                                      // (kh, chunk) sub-blocks
@@ -957,10 +961,10 @@ conv_is_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == WARP_PRODUCER) {
     // ---- resident filters: this CTA's 96 of the 192 (kw, co) rows of every (kh, chunk) sub-block, three 32-row pieces each ----
-    if (lane == 0 && crank == 0) mbar_expect_tx(&bfull_bar, 2u * a.b_total_bytes);
+    if (bstat && lane == 0 && crank == 0) mbar_expect_tx(&bfull_bar, 2u * a.b_total_bytes);
     __syncwarp();
     const uint32_t bbar = smem_u32(&bfull_bar) & PEER_BIT_MASK;
-    for (int i = lane; i < nsub * 3; i += 32) {
+    for (int i = lane; i < (bstat ? nsub * 3 : 0); i += 32) {
       const int sub = i / 3, piece = i - sub * 3;
       const int kh = sub / a.cchunks, cc = sub - kh * a.cchunks;
       const int nrow = (int)crank * (IS_N / 2) + piece * 32;           // row of the (kw, co) stack
@@ -969,16 +973,31 @@ conv_is_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                       (kh * 3 + kw) * a.cin_p + cc * a.kchunk, co0);
     }
     __syncwarp();
-    if (lane == 0) {
+    {
+      // lane 0: the patch (and the barrier handshake); streamed filters: lanes 1..9 fetch the chunk's 3 kh x 3 row pieces
       uint32_t stage = 0, phase = 0;
       for (int sg = pair; sg < m_groups; sg += npairs) {
         int n, h0, w0;
         tile_of(sg, n, h0, w0);
         for (int cc = 0; cc < a.cchunks; ++cc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (crank == 0) mbar_expect_tx(&full_bar[stage], 2u * A_STAGE);
-          const int ca = cc < a.a_wrap ? cc : cc - a.a_wrap;              // bf16x3: the third K block re-reads the hi channels
-          tma_load_4d_2sm(smem_a + stage * A_STAGE, &tmA, smem_u32(&full_bar[stage]) & PEER_BIT_MASK, ca * a.kchunk, w0 - 1, h0 - 1, n);
+          if (lane == 0) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+          }
+          __syncwarp();
+          const uint32_t fbar = smem_u32(&full_bar[stage]) & PEER_BIT_MASK;
+          const uint32_t sA = smem_a + stage * stage_bytes;
+          if (lane == 0) {
+            const int ca = cc < a.a_wrap ? cc : cc - a.a_wrap;            // bf16x3: the third K block re-reads the hi channels
+            tma_load_4d_2sm(sA, &tmA, fbar, ca * a.kchunk, w0 - 1, h0 - 1, n);
+          } else if (!bstat && lane < 10) {
+            const int kh = (lane - 1) / 3, piece = (lane - 1) - kh * 3;
+            const int nrow = (int)crank * (IS_N / 2) + piece * 32;
+            const int kw = nrow >> 6, co0 = nrow & 63;
+            tma_load_2d_2sm(sA + A_STAGE + (uint32_t)kh * B_SUB + (uint32_t)piece * 32u * ROW_BYTES, &tmB, fbar,
+                            (kh * 3 + kw) * a.cin_p + cc * a.kchunk, co0);
+          }
+          __syncwarp();
           if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -991,10 +1010,12 @@ conv_is_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(IS_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       constexpr uint32_t layout = KIND == 1 ? 4u : 2u;
       const uint64_t adesc0 = make_smem_desc(smem_a, 16u, 8u * ROW_BYTES, layout);
-      const uint64_t bdesc0 = make_smem_desc(smem_b, 16u, 8u * ROW_BYTES, layout);
+      const uint64_t bdesc0 = make_smem_desc(bstat ? smem_b : smem_a + A_STAGE, 16u, 8u * ROW_BYTES, layout);
       constexpr uint32_t KH16 = (IS_TW * ROW_BYTES) >> 4;              // one patch row = two swizzle atoms
-      mbar_wait(&bfull_bar, 0);
-      tc_fence_after();
+      if (bstat) {
+        mbar_wait(&bfull_bar, 0);
+        tc_fence_after();
+      }
       uint32_t stage = 0, phase = 0, it = 0;
       for (int sg = pair; sg < m_groups; sg += npairs, ++it) {
         const uint32_t buf = it & 1u;
@@ -1006,10 +1027,11 @@ conv_is_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (is_leader) {
-            const uint64_t ad = adesc0 + (uint32_t)((stage * A_STAGE) >> 4);
+            const uint64_t ad = adesc0 + (uint32_t)((stage * stage_bytes) >> 4);
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
-              const uint64_t bd = bdesc0 + (uint32_t)(((uint32_t)(kh * a.cchunks + cc) * B_SUB) >> 4);
+              const uint64_t bd = bdesc0 + (bstat ? (uint32_t)(((uint32_t)(kh * a.cchunks + cc) * B_SUB) >> 4)
+                                                  : (uint32_t)((stage * stage_bytes + (uint32_t)kh * B_SUB) >> 4));
 #pragma unroll
               for (int ks = 0; ks < KSTEPS; ++ks) {
                 umma_bf16_2sm(tmem_d, ad + (uint32_t)kh * KH16 + (uint32_t)(ks * 2), bd + (uint32_t)(ks * 2), idesc, accum);
@@ -1242,14 +1264,20 @@ static int conv_is_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   a.b_sub_bytes = (uint32_t)((IS_N / 2) * a.row_bytes);
   a.b_total_bytes = (uint32_t)(3 * a.cchunks) * a.b_sub_bytes;
   const size_t SMEM_BUDGET = 218 * 1024;
-  const size_t b_region = ((size_t)a.b_total_bytes + 1023) & ~(size_t)1023;
-  if (b_region + 3 * (size_t)a.a_stage_bytes > SMEM_BUDGET) return Y2_OK;      // filters not resident: the halo-patch kernel
-  int stages = (int)((SMEM_BUDGET - b_region) / a.a_stage_bytes);
+  size_t b_region = ((size_t)a.b_total_bytes + 1023) & ~(size_t)1023;
+  a.b_stationary = b_region + 3 * (size_t)a.a_stage_bytes <= SMEM_BUDGET ? 1 : 0;
+  size_t stage_bytes = a.a_stage_bytes;
+  if (!a.b_stationary) {                                 // the bank does not fit (bf16x3, 128 channels): stream the chunk's three kh sub-blocks
+    b_region = 0;
+    stage_bytes += 3 * (size_t)a.b_sub_bytes;
+  }
+  int stages = (int)((SMEM_BUDGET - b_region) / stage_bytes);
+  if (stages < 3) return Y2_OK;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   a.stages = stages;
   fastdiv_init((uint32_t)a.tiles_w, &a.fd_w_mul, &a.fd_w_shr);
   fastdiv_init((uint32_t)a.tiles_h, &a.fd_h_mul, &a.fd_h_shr);
-  const size_t smem = b_region + (size_t)stages * a.a_stage_bytes + 1024;
+  const size_t smem = b_region + (size_t)stages * stage_bytes + 1024;
   int rc = load_driver_entry_points();
   if (rc != Y2_OK) return rc;
   CUtensorMap tmA, tmB;

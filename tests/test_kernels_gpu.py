@@ -118,6 +118,7 @@ def test_conv_halo_pair_vs_single_cta_and_oracle(ops, monkeypatch, N, H, W, Cin,
                                                          (2, 64, 64, 64, True, True, False),       # float32 rows + pool (generic epilogue)
                                                          (2, 80, 72, 128, False, True, False),     # training forward / float32 rows
                                                          (2, 72, 72, 32, True, False, True),       # bf16x3: three K blocks, split output
+                                                         (1, 72, 80, 128, False, False, True),     # bf16x3 at 128 channels: streamed filters
                                                          (1, 64, 98, 64, False, False, False)])    # exactly 7 tiles wide
 def test_conv_input_stationary_vs_halo_kernel_and_oracle(ops, monkeypatch, N, H, W, Cin, pool, out_f32, x3):
     """conv_is_kernel (3x3, 64 filters, maps >= 64x64: the three horizontal taps as column blocks of one N = 192 MMA, the
