@@ -178,6 +178,7 @@ class Yolo2Engine:
             pack_c1 = ops.pack_weights_conv1_u8_split if self.x3 else ops.pack_weights_conv1_u8
             self.packed_c1 = pack_c1(st[self.layers[0]['W']], self.fold[0][0])
         self.graph = None
+        self._pipe_graphs = {}
         self._version = st.version
 
     # ------------------------------------------------------------------------------------------
@@ -340,21 +341,47 @@ class Yolo2Engine:
             self._staging[i].copy_(torch.as_tensor(host_images), non_blocking=True)
             self._ready[i].record(self._copy_stream)
         cur.wait_event(self._ready[i])
-        (self.in_u8 if self.input_kind == 'u8' else self.in_f32).copy_(self._staging[i], non_blocking=True)
-        self._free[i].record(cur)
-        self.run()
+        srcs = dict(net=self.acts[-1])
+        if self.decode == 'region':
+            srcs.update(boxes=self.boxes, scores=self.scores, keep_idx=self.keep_idx, keep_count=self.keep_count)
+        j = stage = None
         if out_host is not None:
-            srcs = dict(net=self.acts[-1])
-            if self.decode == 'region':
-                srcs.update(boxes=self.boxes, scores=self.scores, keep_idx=self.keep_idx, keep_count=self.keep_count)
             j = self._out_slot
             self._out_slot ^= 1
             stage = self._out_stage[j]
-            cur.wait_event(self._out_free[j])                   # the D2H that last read this snapshot has finished
             for k in out_host:
                 if k not in stage:
                     stage[k] = torch.empty_like(srcs[k])
+            cur.wait_event(self._out_free[j])                   # the D2H that last read this snapshot has finished
+        if self.use_cuda_graph and self.input_kind == 'u8':
+            # one CUDA graph per staging slot: the first conv reads the staging buffer DIRECTLY (no device-side copy of the
+            # 33 MB batch) and the snapshot of the results is part of the graph -- one launch per batch on the compute stream
+            if self._version != self.store.version:
+                self.refresh_weights()
+            key = (i, j, tuple(sorted(out_host)) if out_host is not None else ())
+            g = self._pipe_graphs.get(key)
+            if g is None:
+                if self.graph is None:
+                    self.run()                                  # warm-up + the plain graph (sets launches_per_step)
+                saved, self.in_u8 = self.in_u8, self._staging[i]
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._enqueue()
+                        for k in (out_host or ()):
+                            stage[k].copy_(srcs[k], non_blocking=True)
+                finally:
+                    self.in_u8 = saved
+                self._pipe_graphs[key] = g
+            g.replay()
+            self._free[i].record(cur)
+        else:
+            (self.in_u8 if self.input_kind == 'u8' else self.in_f32).copy_(self._staging[i], non_blocking=True)
+            self._free[i].record(cur)
+            self.run()
+            for k in (out_host or ()):
                 stage[k].copy_(srcs[k], non_blocking=True)      # device-side snapshot (on the compute stream)
+        if out_host is not None:
             self._out_ready[j].record(cur)
             with torch.cuda.stream(self._out_stream):
                 self._out_stream.wait_event(self._out_ready[j])
