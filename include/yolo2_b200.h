@@ -314,6 +314,19 @@ int y2_adam_step(float* p, const float* g, float* m, float* v, size_t n, float l
 int y2_adam_step_ex(float* p, float* g, float* m, float* v, size_t n, float lr_t, const float* lr_t_dev, float beta1,
                     float beta2, float eps, float grad_scale, int zero_grad, y2_stream_t stream);
 
+
+/* ---- f4: the ImageNet classifier's training graph (src/imagenet/imagenet_train_darknet.py:46-61) ----------------------
+ * logits = average over the HW positions of net[N,HW,C] (darknet.py:116-117; HW = 1 for ready-made logits),
+ * losses[n] = tf.nn.sparse_softmax_cross_entropy_with_logits (:50-51), correct[n] = (argmax == label) (:60),
+ * terms[0] = reduce_mean(losses) (:52), terms[1] = accuracy (:61); dnet (optional, [N,HW,C]) = d terms[0] / d net;
+ * logits (optional, [N,C]).  Two launches. */
+int y2_softmax_xent_fwd_bwd(const float* net, const int* labels, int N, int HW, int C, float* logits, float* losses,
+                            float* correct, float* terms, float* dnet, y2_stream_t stream);
+/* tf.train.MomentumOptimizer(lr, momentum) (:58): accum = momentum * accum + g * grad_scale; p -= lr * accum; same
+ * conventions as y2_adam_step_ex (n % 4 == 0, 16-byte aligned, zero_grad clears g behind the read). */
+int y2_momentum_step(float* p, float* g, float* accum, size_t n, float lr, float momentum, float grad_scale, int zero_grad,
+                     y2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,8 @@ _SIGNATURES = {
     'y2_sum_rows_bf16': (_i, [_vp, _i, _sz, _i, _vp, _vp]),
     'y2_adam_step': (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _vp]),
     'y2_adam_step_ex': (_i, [_vp, _vp, _vp, _vp, _sz, _f, _vp, _f, _f, _f, _f, _i, _vp]),
+    'y2_softmax_xent_fwd_bwd': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'y2_momentum_step': (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _i, _vp]),
 }
 
 _lib = None

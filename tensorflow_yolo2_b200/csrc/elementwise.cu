@@ -681,6 +681,22 @@ __global__ void __launch_bounds__(256) adam_ex_kernel(float4* __restrict__ p, fl
   }
 }
 
+// tf.train.MomentumOptimizer (imagenet_train_darknet.py:58; TF's ApplyMomentum without Nesterov): accum = momentum * accum + g,
+// p -= lr * accum.  Same conventions as adam_ex_kernel: gradient scaled on the fly, arena cleared behind the read.
+__global__ void __launch_bounds__(256) momentum_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ acc,
+                                                       size_t n4, float lr, float mom, float gscale, int zero_grad) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 gi = g[i], ai = acc[i], pi = p[i];
+    ai.x = mom * ai.x + gi.x * gscale; ai.y = mom * ai.y + gi.y * gscale;
+    ai.z = mom * ai.z + gi.z * gscale; ai.w = mom * ai.w + gi.w * gscale;
+    pi.x -= lr * ai.x; pi.y -= lr * ai.y; pi.z -= lr * ai.z; pi.w -= lr * ai.w;
+    acc[i] = ai; p[i] = pi;
+    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // dtype plumbing of the drop-in builders (float32 <-> bf16, 8 elements per thread where aligned) and the chain-rule scale of
 // get_loss's backward (dnet * upstream scalar, the scalar read from device memory: no host sync)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
@@ -1025,6 +1041,16 @@ int y2_adam_step_ex(float* p, float* g, float* m, float* v, size_t n, float lr_t
   Y2_ARG(((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0);
   adam_ex_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n / 4, lr_t,
                                                                          lr_t_dev, beta1, beta2, eps, grad_scale, zero_grad);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_momentum_step(float* p, float* g, float* accum, size_t n, float lr, float momentum, float grad_scale, int zero_grad,
+                     void* stream) {
+  Y2_ARG(p && g && accum && n > 0 && n % 4 == 0);
+  Y2_ARG(((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)accum)) & 15) == 0);
+  momentum_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((float4*)p, (float4*)g, (float4*)accum, n / 4, lr, momentum,
+                                                                          grad_scale, zero_grad);
   Y2_LAUNCHED();
   return Y2_OK;
 }

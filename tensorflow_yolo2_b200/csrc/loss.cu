@@ -214,6 +214,81 @@ __global__ void loss_v1_box_deltas_kernel(const float* __restrict__ net, const f
 
 using namespace y2;
 
+// ----------------------------------------------------------------------------------------------------------------------
+// ImageNet classifier loss (imagenet_train_darknet.py:50-54,60-61): logits = 7x7 average pool of the last layer
+// (darknet.py:116-117), tf.nn.sparse_softmax_cross_entropy_with_logits, reduce_mean, accuracy = mean(argmax == label), and the
+// gradient of the mean loss w.r.t. the PRE-pool map (softmax - onehot) / (N * HW) broadcast over the window -- one CTA per image.
+// ----------------------------------------------------------------------------------------------------------------------
+constexpr int XENT_THREADS = 256;
+
+__device__ __forceinline__ float xent_block_reduce(float v, float* red, bool is_max) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();                                   // red[] may still be read by the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < XENT_THREADS / 32; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(XENT_THREADS) softmax_xent_kernel(const float* __restrict__ net, const int* __restrict__ labels,
+                                                                    int N, int HW, int C, float* __restrict__ logits_out,
+                                                                    float* __restrict__ losses, float* __restrict__ correct,
+                                                                    float* __restrict__ dnet) {
+  extern __shared__ float xs[];                      // C logits
+  __shared__ float red[XENT_THREADS / 32];
+  __shared__ int amax_s;
+  const int n = blockIdx.x;
+  const float* src = net + (size_t)n * HW * C;
+  const float inv_hw = 1.0f / (float)HW;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += XENT_THREADS) {
+    float acc = 0.0f;
+    for (int p = 0; p < HW; ++p) acc += src[(size_t)p * C + c];
+    acc *= inv_hw;
+    xs[c] = acc;
+    if (logits_out) logits_out[(size_t)n * C + c] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = xent_block_reduce(mx, red, true);
+  if (threadIdx.x == 0) amax_s = C;
+  __syncthreads();
+  float se = 0.0f;
+  for (int c = threadIdx.x; c < C; c += XENT_THREADS) {
+    se += expf(xs[c] - mx);
+    if (xs[c] == mx) atomicMin(&amax_s, c);          // tf.argmax: the first maximum
+  }
+  se = xent_block_reduce(se, red, false);
+  const int lab = labels[n];
+  const bool lab_ok = lab >= 0 && lab < C;           // TF raises on an out-of-range label; here it contributes NaN like TF-GPU
+  if (threadIdx.x == 0) {
+    losses[n] = lab_ok ? (logf(se) + mx - xs[lab]) : NAN;
+    correct[n] = (amax_s == lab) ? 1.0f : 0.0f;
+  }
+  if (dnet) {
+    const float gs = inv_hw / (float)N, inv_se = 1.0f / se;
+    float* dst = dnet + (size_t)n * HW * C;
+    for (int c = threadIdx.x; c < C; c += XENT_THREADS) {
+      const float g = (expf(xs[c] - mx) * inv_se - (c == lab ? 1.0f : 0.0f)) * gs;
+      for (int p = 0; p < HW; ++p) dst[(size_t)p * C + c] = g;
+    }
+  }
+}
+
+__global__ void softmax_xent_finalize_kernel(const float* __restrict__ losses, const float* __restrict__ correct, int N,
+                                             float* __restrict__ terms) {
+  double l = 0.0, a = 0.0;
+  for (int i = threadIdx.x; i < N; i += 32) { l += losses[i]; a += correct[i]; }
+  for (int o = 16; o > 0; o >>= 1) {
+    l += __shfl_xor_sync(0xffffffffu, l, o);
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+  }
+  if (threadIdx.x == 0) { terms[0] = (float)(l / N); terms[1] = (float)(a / N); }
+}
+
 extern "C" {
 
 int y2_iou(const float* boxes1, const float* boxes2, float* iou, size_t n, y2_stream_t stream) {
@@ -263,6 +338,22 @@ int y2_loss_v1_box_deltas(const float* net, const float* labels, int N, int S, i
   Y2_ARG(total < (1ll << 31));
   loss_v1_box_deltas_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(net, labels, (int)total, S, B, C,
                                                                                               image_size, deltas);
+  Y2_LAUNCHED();
+  return Y2_OK;
+}
+
+int y2_softmax_xent_fwd_bwd(const float* net, const int* labels, int N, int HW, int C, float* logits, float* losses, float* correct,
+                            float* terms, float* dnet, y2_stream_t stream) {
+  Y2_ARG(net && labels && losses && correct && terms && N > 0 && HW > 0 && C > 0);
+  const size_t smem = (size_t)C * sizeof(float);
+  if (smem > 48 * 1024) {
+    set_error("y2_softmax_xent_fwd_bwd: C=%d needs %zu B smem", C, smem);
+    return Y2_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  softmax_xent_kernel<<<N, XENT_THREADS, smem, st>>>(net, labels, N, HW, C, logits, losses, correct, dnet);
+  Y2_LAUNCHED();
+  softmax_xent_finalize_kernel<<<1, 32, 0, st>>>(losses, correct, N, terms);
   Y2_LAUNCHED();
   return Y2_OK;
 }

@@ -54,6 +54,21 @@ def create_variables(store, output_filter, passthrough=False):
     return layers
 
 
+def create_classifier_variables(store, num_classes=1000):
+    """The variables of the `darknet19` ImageNet classifier (darknet.py:61-123) in creation order: the 18 core layers and the
+    19th conv_bn_layer (1x1, 1024 -> num_classes) in the SAME scope, so its names continue the core's numbering
+    (darknet19/Variable_36, Variable_37, batch_normalization_18)."""
+    store.reset_name_counters()
+    layers = []
+    with store.scope('darknet19'):
+        for (k, cin, cout, pool) in list(CORE_PLAN) + [(1, 1024, int(num_classes), False)]:
+            wn, _ = store.weight_variable([k, k, cin, cout])
+            bn_, _ = store.bias_variable([cout])
+            layers.append(dict(k=k, cin=cin, cout=cout, pool=pool, W=wn, b=bn_, bn=store.batch_norm_variables(cout),
+                               head=len(layers) == len(CORE_PLAN), role='logits' if len(layers) == len(CORE_PLAN) else None))
+    return layers
+
+
 class Yolo2Engine:
     def __init__(self, batch, image_size=416, output_filter=125, store=None, core_training=False, head_training=True,
                  anchors=VOC_ANCHORS, num_class=20, score_thresh=0.3, iou_thresh=0.45, max_keep=None,

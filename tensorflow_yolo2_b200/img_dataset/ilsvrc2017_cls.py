@@ -2,7 +2,8 @@
 (src/img_dataset/ilsvrc2017_cls_multithread.py: class `ilsvrc_cls` -- .name, .classes, .num_class, .image_num,
 .total_batch, .epoch, .get(), .image_read()).
 
-Scope: the evaluation path (imagenet_test_darknet.py / imagenet_predict_darknet.py): single process, no augmentation --
+Scope: what imagenet_test_darknet.py / imagenet_predict_darknet.py / imagenet_train_darknet.py feed the network with: single
+process, no augmentation --
 `image_read` is cv2.imread -> (optional BGR->RGB) -> cv2.resize((IS, IS)) -> float32 -> x/255*2-1
 (ilsvrc2017_cls_multithread.py:320-323,408-415).  The training-time augmentation (random rotation / crop / colour,
 :328-407) and the 10-process prefetcher (:119-205, :221-318) are host-side data plumbing outside the hot path (SURVEY

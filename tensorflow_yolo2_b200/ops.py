@@ -680,3 +680,30 @@ def adam_step_ex(p, g, m, v, lr_t=0.0, lr_t_dev=None, b1=0.9, b2=0.999, eps=1e-8
     check(_lib.load().y2_adam_step_ex(_p(p, torch.float32), _p(g, torch.float32), _p(m, torch.float32), _p(v, torch.float32),
                                       p.numel(), float(lr_t), _p(lr_t_dev, torch.float32), b1, b2, eps, float(grad_scale),
                                       1 if zero_grad else 0, _stream()), 'y2_adam_step_ex')
+
+
+def momentum_step(p, g, accum, lr, momentum, grad_scale=1.0, zero_grad=False):
+    """y2_momentum_step: tf.train.MomentumOptimizer's update (imagenet_train_darknet.py:58) over a flat fp32 arena."""
+    check(_lib.load().y2_momentum_step(_p(p, torch.float32), _p(g, torch.float32), _p(accum, torch.float32), p.numel(), float(lr),
+                                       float(momentum), float(grad_scale), 1 if zero_grad else 0, _stream()), 'y2_momentum_step')
+
+
+def softmax_xent(net, labels, want_grad=False, terms=None, logits=None, losses=None, correct=None, dnet=None):
+    """y2_softmax_xent_fwd_bwd.  net: fp32 [N,H,W,C] (average-pooled over H*W first, darknet.py:116-117) or [N,C] logits;
+    labels: int32 [N].  Returns dict(terms=[mean loss, accuracy], logits [N,C], losses [N], correct [N], dnet or None)."""
+    assert net.dtype == torch.float32 and net.dim() in (2, 4)
+    N, C = net.shape[0], net.shape[-1]
+    HW = 1 if net.dim() == 2 else net.shape[1] * net.shape[2]
+    f32 = dict(dtype=torch.float32, device=net.device)
+    terms = torch.empty((2,), **f32) if terms is None else terms
+    logits = torch.empty((N, C), **f32) if logits is None else logits
+    losses = torch.empty((N,), **f32) if losses is None else losses
+    correct = torch.empty((N,), **f32) if correct is None else correct
+    if want_grad and dnet is None:
+        dnet = torch.empty_like(net)
+    assert labels.dtype == torch.int32 and labels.numel() == N
+    check(_lib.load().y2_softmax_xent_fwd_bwd(_p(net, torch.float32), _p(labels, torch.int32), N, HW, C, _p(logits, torch.float32),
+                                              _p(losses, torch.float32), _p(correct, torch.float32), _p(terms, torch.float32),
+                                              _p(dnet, torch.float32) if dnet is not None else None, _stream()),
+          'y2_softmax_xent_fwd_bwd')
+    return dict(terms=terms, logits=logits, losses=losses, correct=correct, dnet=dnet)

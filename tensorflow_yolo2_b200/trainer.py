@@ -29,7 +29,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .engine import create_variables
+from .engine import create_classifier_variables, create_variables
 from .parallel import BucketedAllReduce, make_buckets
 from .variables import VariableStore
 from .yolo2_nets.net_utils import VOC_ANCHORS
@@ -43,7 +43,11 @@ class Yolo2Trainer:
     def __init__(self, batch, image_size=416, output_filter=None, store=None, loss='v1', num_class=20, B=5,
                  anchors=VOC_ANCHORS, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, lambda_coord=None, lambda_noobj=None,
                  max_gt=32, device=None, seed=0, process_group=None, bucket_bytes=48 << 20, update_moving=True,
-                 use_cuda_graph=False):
+                 use_cuda_graph=False, optimizer='adam', momentum=0.9):
+        """loss: 'v1' (the reference's get_loss), 'region' (YOLOv2 region loss) or 'softmax' -- the ImageNet classifier of
+        imagenet_train_darknet.py:46-58: the 18 core layers + the 1x1 conv to `num_class` logits maps + 7x7 average pool,
+        sparse softmax cross-entropy (image_size 224, num_class 1000 there).  optimizer: 'adam' (pascal_train_darknet.py:51)
+        or 'momentum' (tf.train.MomentumOptimizer(lr, momentum), imagenet_train_darknet.py:58)."""
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.N, self.IS = int(batch), int(image_size)
         assert self.IS % 32 == 0
@@ -62,8 +66,13 @@ class Yolo2Trainer:
             self.lambda_coord = 1.0 if lambda_coord is None else lambda_coord
             self.lambda_noobj = 1.0 if lambda_noobj is None else lambda_noobj
             self.max_gt = int(max_gt)
+        elif loss == 'softmax':
+            of = self.C
         else:
-            raise ValueError('loss must be "v1" or "region"')
+            raise ValueError('loss must be "v1", "region" or "softmax"')
+        if optimizer not in ('adam', 'momentum'):
+            raise ValueError('optimizer must be "adam" or "momentum"')
+        self.optimizer, self.momentum = optimizer, float(momentum)
         self.OF = int(output_filter) if output_filter is not None else of
         assert self.OF == of, 'output_filter %d does not match the %s loss layout (%d)' % (self.OF, loss, of)
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
@@ -73,7 +82,8 @@ class Yolo2Trainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.update_moving = update_moving
         self.store = store if store is not None else VariableStore(seed=seed)
-        self.layers = create_variables(self.store, self.OF)
+        self.layers = (create_classifier_variables(self.store, self.OF) if loss == 'softmax'
+                       else create_variables(self.store, self.OF))
         self.iteration = 0
         # the whole step (forward, loss, backward, Adam: ~290 launches) replayed as ONE CUDA graph; single-process only --
         # with world > 1 the NCCL buckets are issued eagerly on NCCL's stream so that they overlap the backward kernels
@@ -112,8 +122,8 @@ class Yolo2Trainer:
         f32 = dict(dtype=torch.float32, device=dev)
         self.params = torch.zeros((off,), **f32)
         self.grads = torch.zeros((off,), **f32)
-        self.adam_m = torch.zeros((off,), **f32)
-        self.adam_v = torch.zeros((off,), **f32)
+        self.adam_m = torch.zeros((off,), **f32)           # (momentum optimizer: the accumulator slot)
+        self.adam_v = torch.zeros((off if self.optimizer == 'adam' else 4,), **f32)
         self.P, self.G = [], []
         for li, L in enumerate(self.layers):
             sl = self.slots[li]
@@ -169,7 +179,7 @@ class Yolo2Trainer:
         self.dh = torch.empty((max_dh,), **bf16)
         self.dx = [torch.empty((max_dx,), **bf16), torch.empty((max_dx,), **bf16)]
         S = self.S
-        self.terms = torch.zeros((5,), **f32)
+        self.terms = torch.zeros((2 if self.loss_kind == 'softmax' else 5,), **f32)
         self.lr_dev = torch.zeros((1,), **f32)              # Adam step size of the current iteration (read by the update kernel)
         self._lr_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
         self.dnet = torch.empty((N, S, S, self.OF), **f32)
@@ -177,6 +187,11 @@ class Yolo2Trainer:
             self.labels = torch.zeros((N, S, S, 5 + self.C), **f32)
             self.ious = torch.empty((N, S, S, self.B), **f32)
             self.object_mask = torch.empty((N, S, S, self.B), **f32)
+        elif self.loss_kind == 'softmax':
+            self.class_labels = torch.zeros((N,), dtype=torch.int32, device=dev)
+            self.logits = torch.empty((N, self.OF), **f32)
+            self.losses = torch.empty((N,), **f32)
+            self.correct = torch.empty((N,), **f32)
         else:
             self.anchors = torch.as_tensor(self.anchors_np).to(dev).contiguous()
             self.gt_boxes = torch.zeros((N, self.max_gt, 4), **f32)
@@ -195,6 +210,11 @@ class Yolo2Trainer:
         pascal_voc.py:43-46; cast to float32 at the feed like the TF placeholder does)."""
         assert self.loss_kind == 'v1'
         self.labels.copy_(torch.as_tensor(np.asarray(labels), dtype=torch.float32), non_blocking=True)
+
+    def set_class_labels(self, labels):
+        """softmax loss: int class index per image (the int32 `label_data` placeholder, imagenet_train_darknet.py:47)."""
+        assert self.loss_kind == 'softmax'
+        self.class_labels.copy_(torch.as_tensor(np.asarray(labels).astype(np.int32)), non_blocking=True)
 
     def set_ground_truth(self, gt_boxes, gt_classes, gt_counts):
         assert self.loss_kind == 'region'
@@ -237,6 +257,9 @@ class Yolo2Trainer:
         if self.loss_kind == 'v1':
             ops.loss_v1(net, self.labels, self.S, self.B, self.C, float(self.IS), self.lambda_coord, self.lambda_noobj,
                         want_grad=True, terms=self.terms, ious=self.ious, object_mask=self.object_mask, dnet=self.dnet)
+        elif self.loss_kind == 'softmax':
+            ops.softmax_xent(net, self.class_labels, terms=self.terms, logits=self.logits, losses=self.losses,
+                             correct=self.correct, dnet=self.dnet)
         else:
             ops.region_loss(net, self.anchors, self.gt_boxes, self.gt_classes, self.gt_counts, self.C,
                             lambda_coord=self.lambda_coord, lambda_noobj=self.lambda_noobj, terms=self.terms,
@@ -284,8 +307,12 @@ class Yolo2Trainer:
         if not _lr_set:
             self.iteration += 1
             self._set_lr()
-        ops.adam_step_ex(self.params, self.grads, self.adam_m, self.adam_v, lr_t_dev=self.lr_dev, b1=self.beta1, b2=self.beta2,
-                         eps=self.eps, grad_scale=1.0 / self.world, zero_grad=zero_grad)
+        if self.optimizer == 'momentum':
+            ops.momentum_step(self.params, self.grads, self.adam_m, self.lr, self.momentum, grad_scale=1.0 / self.world,
+                              zero_grad=zero_grad)
+        else:
+            ops.adam_step_ex(self.params, self.grads, self.adam_m, self.adam_v, lr_t_dev=self.lr_dev, b1=self.beta1,
+                             b2=self.beta2, eps=self.eps, grad_scale=1.0 / self.world, zero_grad=zero_grad)
         self._grads_clean = bool(zero_grad)
         self.store.version += 1
 
@@ -403,10 +430,14 @@ class Yolo2Trainer:
             sl = self.slots[li]
             for key, nm in zip(('W', 'b', 'gamma', 'beta'), (L['W'], L['b'], L['bn']['gamma'], L['bn']['beta'])):
                 o, n, shp = sl[key]
+                if self.optimizer == 'momentum':            # MomentumOptimizer's one slot: `<var>/Momentum`
+                    out[nm + '/Momentum'] = self.adam_m[o:o + n].view(shp).detach().cpu().numpy()
+                    continue
                 out[nm + '/Adam'] = self.adam_m[o:o + n].view(shp).detach().cpu().numpy()
                 out[nm + '/Adam_1'] = self.adam_v[o:o + n].view(shp).detach().cpu().numpy()
-        out['beta1_power'] = np.float32(self.beta1 ** (self.iteration + 1))      # TF holds beta^(t+1) after t updates
-        out['beta2_power'] = np.float32(self.beta2 ** (self.iteration + 1))
+        if self.optimizer == 'adam':
+            out['beta1_power'] = np.float32(self.beta1 ** (self.iteration + 1))      # TF holds beta^(t+1) after t updates
+            out['beta2_power'] = np.float32(self.beta2 ** (self.iteration + 1))
         out['y2_iteration'] = np.int64(self.iteration)
         return out
 
@@ -419,7 +450,9 @@ class Yolo2Trainer:
             sl = self.slots[li]
             for key, nm in zip(('W', 'b', 'gamma', 'beta'), (L['W'], L['b'], L['bn']['gamma'], L['bn']['beta'])):
                 o, n, shp = sl[key]
-                for suffix, arena in (('/Adam', self.adam_m), ('/Adam_1', self.adam_v)):
+                slots_ = ((('/Momentum', self.adam_m),) if self.optimizer == 'momentum'
+                          else (('/Adam', self.adam_m), ('/Adam_1', self.adam_v)))
+                for suffix, arena in slots_:
                     if nm + suffix in data.files:
                         arena[o:o + n].view(shp).copy_(torch.as_tensor(data[nm + suffix], dtype=torch.float32))
                         found.append(nm + suffix)

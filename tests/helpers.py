@@ -2,15 +2,16 @@
 import numpy as np
 import torch
 
-from tensorflow_yolo2_b200.engine import create_variables
+from tensorflow_yolo2_b200.engine import create_classifier_variables, create_variables
 from tensorflow_yolo2_b200.variables import VariableStore, _to_numpy
 
 
-def make_store(output_filter, seed=0, tame=False, passthrough=False):
+def make_store(output_filter, seed=0, tame=False, passthrough=False, classifier=False):
     """Variables in the reference's order/naming.  tame=True rescales W to He-init magnitude
     (sqrt(2/fan_in)) so activations stay O(1) instead of exploding to 1e9+."""
     st = VariableStore(seed=seed)
-    layers = create_variables(st, output_filter, passthrough=passthrough)
+    layers = (create_classifier_variables(st, output_filter) if classifier      # darknet19 classifier: 18 core layers + logits conv
+              else create_variables(st, output_filter, passthrough=passthrough))
     if tame:
         rs = np.random.RandomState(seed + 1)
         for L in layers:

@@ -162,3 +162,34 @@ def test_imagenet_test_and_predict_scripts(fresh_env, golden_dir, capsys):
     order = np.argsort(-want, kind='stable')[:5]
     np.testing.assert_allclose(probs, want[order], rtol=2e-3)
     assert list(preds) == list(order)
+
+
+def test_imagenet_train_script_synthetic(fresh_env, capsys):
+    """Drop-in for src/imagenet/imagenet_train_darknet.py on a synthetic database: the reference's log lines, a validation
+    pass (is_training = 0) every --val-every iterations, the epoch snapshot with the Momentum slots, and a resumed run that
+    picks the snapshot up and continues at the next epoch (:80-98)."""
+    from tensorflow_yolo2_b200 import variables
+    from tensorflow_yolo2_b200.imagenet import imagenet_train_darknet as script
+    argv = ['imagenet_train_darknet.py', '--synthetic', '64', '--batch', '16', '--iters', '6', '--val-every', '3']
+    tr, hist = script.main(argv)
+    torch.cuda.synchronize()
+    out = capsys.readouterr().out
+    assert 'epoch 1, iter 1/4, training loss:' in out and out.count('###validation loss:') == 2
+    assert 'No darknet19 snapshot' in out and 'Model saved in file:' in out
+    assert len(hist) == 6 and all(np.isfinite(l) and 0.0 <= a <= 1.0 for l, a in hist)
+    assert abs(hist[0][0] - np.log(1000.0)) < 3.0                # random init: cross-entropy around ln(1000)
+    ck = os.path.join(fresh_env.get_ckpts_dir('darknet19', 'ilsvrc_2017_cls'), 'train_epoch_0.ckpt.npz')
+    data = np.load(ck)
+    assert 'darknet19/Variable_36' in data.files and 'darknet19/Variable_36/Momentum' in data.files
+    w_saved = np.array(data['darknet19/Variable_36'])            # (the resumed run rewrites the file)
+    data.close()
+    assert tr.graph is not None and tr.optimizer == 'momentum' and tr.iteration == 6
+    # resume: the snapshot is found, the epoch continues from the file name
+    variables.reset_default_store(seed=0)
+    tr2, hist2 = script.main(argv[:5] + ['--iters', '1'])
+    out = capsys.readouterr().out
+    assert 'Restorining model snapshots from' in out and 'Restored.' in out and 'epoch 1, iter 1/4' in out
+    assert tr2.iteration == 2 and np.isfinite(hist2[0][0])       # y2_iteration = 1 came back with the snapshot
+    # the restored weights are the snapshot's (taken after iteration 0's update) moved by one more momentum step
+    assert np.abs(tr2.P[18]['W'].cpu().numpy() - w_saved).max() < 0.05
+

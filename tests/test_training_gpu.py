@@ -344,3 +344,111 @@ def test_bn_bwd_apply_rows_equals_generic(ops, monkeypatch, pool, dy_bf16, C, ld
     assert float(outs[0][2].float().abs().sum()) > 0
     if outs[0][3] is not None:
         assert torch.equal(outs[0][3], outs[1][3])
+
+
+# ---- the ImageNet classifier's training graph (imagenet_train_darknet.py:46-61) ---------------------------------------------
+@pytest.mark.parametrize('N,H,C', [(5, 7, 1000), (3, 1, 37), (2, 3, 40)])
+def test_softmax_xent_vs_torch(ops, N, H, C):
+    """y2_softmax_xent_fwd_bwd = average pool + sparse softmax cross-entropy + reduce_mean + accuracy + d loss / d (pre-pool
+    map), against torch float64 autograd."""
+    rs = np.random.RandomState(N * 100 + C)
+    net = (rs.randn(N, H, H, C) * 3).astype(np.float32)
+    labels = rs.randint(0, C, N).astype(np.int32)
+    net[0, :, :, labels[0]] += 50.0                             # image 0 is classified correctly for sure
+    x = torch.tensor(net, dtype=torch.float64, requires_grad=True)
+    logits = x.mean(dim=(1, 2))
+    losses = torch.nn.functional.cross_entropy(logits, torch.tensor(labels, dtype=torch.long), reduction='none')
+    losses.mean().backward()
+    arg = cu(net) if H > 1 else cu(net.reshape(N, C))
+    r = ops.softmax_xent(arg, cu(labels), want_grad=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(r['logits'].cpu().numpy(), logits.detach().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(r['losses'].cpu().numpy(), losses.detach().numpy(), rtol=1e-5, atol=1e-5)
+    want_acc = float((logits.argmax(dim=1).numpy() == labels).mean())
+    assert abs(float(r['terms'][0]) - float(losses.mean())) < 1e-5 * max(1.0, float(losses.mean()))
+    assert abs(float(r['terms'][1]) - want_acc) < 1e-6 and float(r['correct'][0]) == 1.0
+    assert rel_l2(r['dnet'].cpu().numpy().reshape(N, H, H, C), x.grad.numpy()) < 1e-5
+
+
+def test_momentum_step_matches_tf_formula(ops):
+    rs = np.random.RandomState(0)
+    n = 4096 + 64
+    p, g, a = (rs.randn(n).astype(np.float32) for _ in range(3))
+    P, G, A = cu(p), cu(g), cu(a)
+    ops.momentum_step(P, G, A, 0.001, 0.9, grad_scale=0.5, zero_grad=True)
+    a2 = 0.9 * a.astype(np.float64) + 0.5 * g
+    np.testing.assert_allclose(A.cpu().numpy(), a2, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(P.cpu().numpy(), p - 0.001 * a2, rtol=1e-6, atol=1e-7)
+    assert float(G.abs().max()) == 0.0
+
+
+def test_classifier_training_step_vs_oracle(ops):
+    """Yolo2Trainer(loss='softmax', optimizer='momentum') -- one iteration of imagenet_train_darknet.py:110-113 -- at 96x96
+    (3x3 final map), batch 4, 40 classes: loss / accuracy / logits gradient against torch on the product's own net, the whole
+    chain against the oracle's autograd (direction), the logits layer's backward layer-locally, and the momentum update."""
+    from tensorflow_yolo2_b200.trainer import Yolo2Trainer
+    N, IS, C = 4, 96, 40
+    st, layers = make_store(C, tame=True, classifier=True)
+    assert len(layers) == 19 and layers[-1]['W'] == 'darknet19/Variable_36' \
+        and layers[-1]['bn']['gamma'] == 'darknet19/batch_normalization_18/gamma'           # darknet.py:114 continues the core's numbering
+    core_p, head_p = oracle_params(st, layers)
+    rs = np.random.RandomState(1)
+    img = rs.uniform(-1, 1, (N, IS, IS, 3)).astype(np.float32)          # ilsvrc_cls.get(): already x/255*2-1
+    labels = rs.randint(0, C, N)
+    tr = Yolo2Trainer(N, IS, store=st, loss='softmax', num_class=C, optimizer='momentum', lr=0.001, momentum=0.9, device='cuda:0')
+    p_before = [{k: v.clone() for k, v in tr.P[li].items()} for li in range(len(layers))]
+    tr.set_class_labels(labels)
+    cap = {}
+    terms = tr.step(torch.tensor(img), capture=cap)
+    torch.cuda.synchronize()
+    lab_t = torch.tensor(labels, dtype=torch.long)
+    loss_fn = lambda net: torch.nn.functional.cross_entropy(net.mean(dim=(1, 2)), lab_t)
+    want_loss, grads, stats, net = O.train_step_reference(img, core_p, head_p, loss_fn, bf16_operands=True)
+    got_net = tr.acts[-1].cpu().numpy()
+    print('net rel_l2 %.3g  loss %.6g vs %.6g' % (rel_l2(got_net, net), float(terms[0]), want_loss))
+    assert rel_l2(got_net, net) < 8e-2 and abs(float(terms[0]) - want_loss) / abs(want_loss) < 5e-2
+    for li in (18, 12, 0):
+        a, b = tr.G[li]['W'].cpu().numpy().ravel().astype(np.float64), grads[li]['W'].ravel()
+        cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+        print('layer %2d dW cosine vs whole-chain oracle %.3f' % (li + 1, cos))
+        assert cos > 0.8
+    # loss, accuracy and d loss / d net on the product's own net output
+    x = torch.tensor(got_net, dtype=torch.float64, requires_grad=True)
+    l = loss_fn(x)
+    l.backward()
+    assert abs(float(terms[0]) - float(l)) < 1e-5 * float(l)
+    assert abs(float(terms[1]) - float((x.detach().mean(dim=(1, 2)).argmax(dim=1) == lab_t).double().mean())) < 1e-6
+    assert rel_l2(cap[18].cpu().numpy(), x.grad.numpy()) < 1e-5
+    # the logits layer (1x1, 1024 -> C, BN, leaky), layer-locally
+    li = 18
+    xin = tr.acts[li - 1].double().cpu().requires_grad_(True)
+    q = {k: p_before[li][k].double().cpu().requires_grad_(True) for k in ('W', 'b', 'gamma', 'beta')}
+    q['mm'], q['mv'] = torch.zeros(C, dtype=torch.float64), torch.ones(C, dtype=torch.float64)
+    y, _, _ = O.conv_bn_layer(xin, q, True, torch.float64, bf16_operands=True)
+    (y * cap[li].double().cpu()).sum().backward()
+    for key in ('W', 'gamma', 'beta'):
+        assert rel_l2(tr.G[li][key].cpu().numpy(), q[key].grad.numpy()) < 1e-2, key
+    assert rel_l2(cap[li - 1].float().cpu().numpy(), xin.grad.numpy()) < 1e-2
+    # MomentumOptimizer, first step: accum = g, p -= lr * g
+    for li in (0, 9, 18):
+        for key in ('W', 'gamma', 'beta'):
+            g = tr.G[li][key].cpu().numpy().astype(np.float64)
+            assert rel_l2(tr.P[li][key].cpu().numpy(), p_before[li][key].cpu().numpy() - 0.001 * g) < 1e-6
+    st_names = tr.optimizer_state()
+    assert 'darknet19/Variable_36/Momentum' in st_names and 'beta1_power' not in st_names
+
+
+def test_classifier_training_loss_decreases_graph(ops):
+    """A few momentum iterations on one fixed batch, CUDA-graphed, reduce the cross-entropy."""
+    from tensorflow_yolo2_b200.trainer import Yolo2Trainer
+    N, IS, C = 8, 64, 16
+    st, _ = make_store(C, tame=True, classifier=True)
+    rs = np.random.RandomState(2)
+    img = torch.tensor(rs.uniform(-1, 1, (N, IS, IS, 3)).astype(np.float32))
+    tr = Yolo2Trainer(N, IS, store=st, loss='softmax', num_class=C, optimizer='momentum', lr=0.01, device='cuda:0',
+                      use_cuda_graph=True)
+    tr.set_class_labels(rs.randint(0, C, N))
+    losses = [float(tr.step(img)[0]) for _ in range(15)]
+    print(losses)
+    assert tr.graph is not None and losses[-1] < 0.8 * losses[0]
+
