@@ -820,40 +820,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int c0 = nbase + cc;
         if constexpr (tma_store) {
-          const uint32_t stg = stg_group + (nstore & 1u) * 8192u;
-          if (r == 0) bulk_wait_group_read<1>();              // the store that last used this buffer has read it
-          asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
-          // row r = h * 8 + w of the box, 64 B per row; 16-byte unit j (8 channels) at j ^ ((r >> 1) & 3)  (SWIZZLE_64B);
-          // one unit at a time: affine + leaky + pack + store, so that only the 32 accumulators stay live
+          // bf16x3 output: the chunk leaves as TWO boxes, the hi halves at channel c0 and the lo halves at lo_off + c0 (the affine
+          // is evaluated again for the second box -- cheaper than keeping 32 more packed registers live)
+          const int nparts = a.split_out ? 2 : 1;
+#pragma unroll 1
+          for (int part = 0; part < nparts; ++part) {
+            const uint32_t stg = stg_group + (nstore & 1u) * 8192u;
+            if (r == 0) bulk_wait_group_read<1>();              // the store that last used this buffer has read it
+            asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
+            // row r = h * 8 + w of the box, 64 B per row; 16-byte unit j (8 channels) at j ^ ((r >> 1) & 3)  (SWIZZLE_64B);
+            // one unit at a time: affine + leaky + pack + store, so that only the 32 accumulators stay live
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t pk[4];
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int i = 8 * j + 4 * h;
-              const float4 sc = *reinterpret_cast<const float4*>(&my_scale[cc + i]);
-              const float4 sh = *reinterpret_cast<const float4*>(&my_shift[cc + i]);
-              float f0 = fmaf(__uint_as_float(v[i + 0]), sc.x, sh.x), f1 = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
-              float f2 = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z), f3 = fmaf(__uint_as_float(v[i + 3]), sc.w, sh.w);
-              if (leaky_on) {
-                f0 = fmaxf(f0, a.alpha * f0); f1 = fmaxf(f1, a.alpha * f1);
-                f2 = fmaxf(f2, a.alpha * f2); f3 = fmaxf(f3, a.alpha * f3);
+              for (int h = 0; h < 2; ++h) {
+                const int i = 8 * j + 4 * h;
+                const float4 sc = *reinterpret_cast<const float4*>(&my_scale[cc + i]);
+                const float4 sh = *reinterpret_cast<const float4*>(&my_shift[cc + i]);
+                float f0 = fmaf(__uint_as_float(v[i + 0]), sc.x, sh.x), f1 = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
+                float f2 = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z), f3 = fmaf(__uint_as_float(v[i + 3]), sc.w, sh.w);
+                if (leaky_on) {
+                  f0 = fmaxf(f0, a.alpha * f0); f1 = fmaxf(f1, a.alpha * f1);
+                  f2 = fmaxf(f2, a.alpha * f2); f3 = fmaxf(f3, a.alpha * f3);
+                }
+                f[4 * h] = f0; f[4 * h + 1] = f1; f[4 * h + 2] = f2; f[4 * h + 3] = f3;
               }
-              const __nv_bfloat162 h0 = __floats2bfloat162_rn(f0, f1), h1 = __floats2bfloat162_rn(f2, f3);
-              pk[2 * h] = *reinterpret_cast<const uint32_t*>(&h0);
-              pk[2 * h + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+              uint4 pk;
+              if (a.split_out) {
+                uint4 hi, lo;
+                split8_bf16(f, hi, lo);
+                pk = part ? lo : hi;
+              } else {
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+                pk = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4)),
+                           "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w)
+                           : "memory");
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4)),
-                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                         : "memory");
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
+            if (r == 0) {
+              tma_store_4d(&tmY, stg, c0 + part * a.lo_off, t.w0, t.h0, t.n0);   // rows / pixels outside the tensor are clipped by the TMA unit
+              bulk_commit_group();
+            }
+            ++nstore;
           }
-          fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
-          if (r == 0) {
-            tma_store_4d(&tmY, stg, c0, t.w0, t.h0, t.n0);     // rows / pixels outside the tensor are clipped by the TMA unit
-            bulk_commit_group();
-          }
-          ++nstore;
         } else if (A_MODE != 0 && pool && !out_f32 && c0 + 32 <= a.Cout && (a.ldy & 7) == 0 && (a.lo_off & 7) == 0) {
           epilogue_chunk_pooled_bf16(a, v, my_scale, my_shift, cc, c0, valid_px, orow, leaky_on, lane);
         } else if (c0 < (a.split_out ? a.Cout : a.ldy)) {
@@ -1546,9 +1561,12 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   // TMA-store epilogue for the un-pooled 128-channel bf16 output of the halo-patch pair kernel (layer 3): 4 groups x 2 x 8 KB
   // of staging.  (Measured: layer 3 108 -> 93 us; the 64-channel layer 4 got slower -- two chunks per tile do not amortise
   // the per-chunk group barriers and the ring loses four stages -- so it keeps the direct stores.)
+  // (bf16x3: the hi / lo halves as two boxes per chunk -- implemented, opt-in Y2_CONV_TMA_STORE_SPLIT=1: the 64 KB of staging
+  // leaves 3 instead of 5 operand stages next to the streamed filters and layer 3 got SLOWER, 308 -> 325 us.)
   const size_t STG_BYTES = 4 * 2 * 8192;
   a.tma_store = 0;
-  if (a.a_mode == 2 && !a.first_layer && !pool && !out_f32 && !split_out && p->Cout % 32 == 0 && a.ldy % 8 == 0 &&
+  if (a.a_mode == 2 && !a.first_layer && !pool && !out_f32 && (!split_out || (a.lo_off % 8 == 0 && env().conv_tma_store_split)) &&
+      p->Cout % 32 == 0 && a.ldy % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(p->y) & 15) == 0 && EPI_GROUPS == 4 && block_n == 128 && a.row_bytes == 128 && a.cta2 &&
       b_region + 3 * (size_t)stage_bytes + STG_BYTES <= SMEM_BUDGET && !env().conv_no_tma_store)
     a.tma_store = 1;
@@ -1643,7 +1661,7 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   memset(&tmY, 0, sizeof(tmY));
   if (a.tma_store) {
     // output [N, H, W, Cout] with row stride ldy: boxes of 32 channels x the 8 x 16 pixel tile, 64-byte swizzled rows
-    cuuint64_t dims[4] = {(cuuint64_t)p->Cout, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t dims[4] = {(cuuint64_t)(split_out ? a.lo_off + p->Cout : p->Cout), (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
     cuuint64_t strides[3] = {(cuuint64_t)a.ldy * 2, (cuuint64_t)p->W * a.ldy * 2, (cuuint64_t)p->H * p->W * a.ldy * 2};
     cuuint32_t box[4] = {32, 8, 16, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};

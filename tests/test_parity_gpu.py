@@ -50,6 +50,7 @@ def join_pair(y):
 @pytest.mark.parametrize('N,H,W,Cin,Cout,k,pool,out_f32', [
     (2, 72, 72, 32, 64, 3, True, False),        # halo-patch pair, 64-byte rows (layer 2 shape), pooled bf16 epilogue
     (2, 80, 64, 64, 128, 3, False, False),      # halo-patch, 128-wide, un-pooled (layer 3 shape): generic split epilogue
+    (2, 70, 68, 64, 128, 3, False, False),      # ... with tiles clipped at the right / bottom edge
     (1, 64, 64, 128, 64, 3, False, False),      # layer 4 shape
     (3, 26, 26, 256, 512, 3, True, False),      # tiled boxes + pool, streamed B, pair
     (4, 26, 26, 512, 256, 1, False, False),     # 1x1, im2col mode
@@ -58,7 +59,7 @@ def join_pair(y):
     (5, 13, 13, 1024, 125, 1, False, True),     # output layer
     (2, 7, 7, 64, 48, 3, False, False),         # Cout not a multiple of 32: scalar split stores
 ])
-def test_conv_split_vs_oracle(ops, N, H, W, Cin, Cout, k, pool, out_f32):
+def test_conv_split_vs_oracle(ops, monkeypatch, N, H, W, Cin, Cout, k, pool, out_f32):
     """y2_conv_fwd_bf16 with IN_SPLIT (+ OUT_SPLIT) against a float64 convolution of the SAME (hi + lo) operands:
     the three-MMA scheme drops only a_lo*w_lo (2^-18) -> 2e-5 relative."""
     rs = np.random.RandomState(Cin + Cout + H)
@@ -91,6 +92,14 @@ def test_conv_split_vs_oracle(ops, N, H, W, Cin, Cout, k, pool, out_f32):
     print('split conv %s: rel_l2=%.3g' % ((N, H, W, Cin, Cout, k, pool, out_f32), e))
     assert e < 4e-5           # (measured 2.4e-5 at K = 3 * 9216: fp32 accumulation over 27 648 products)
     np.testing.assert_allclose(g, want, rtol=2e-4, atol=2e-4 * np.abs(want).max())
+    if (Cin, Cout, k, pool) == (64, 128, 3, False) and H >= 64:
+        # opt-in variant of the layer-3 epilogue: the hi / lo halves leave as two TMA box stores per chunk -- same bits
+        monkeypatch.setenv('Y2_CONV_TMA_STORE_SPLIT', '1')
+        ops.reload_env()
+        got2 = ops.conv_fwd_bf16(xs, wp, k, Cin, Cout, scale=cu(scale), shift=cu(shift), leaky=True, pool=pool, out_f32=out_f32,
+                                 ldy=ld, split_in=True, split_out=True)
+        torch.cuda.synchronize()
+        assert torch.equal(got2, got)
 
 
 @pytest.mark.parametrize('N,H,W', [(2, 32, 16), (3, 96, 96), (2, 416, 416)])
