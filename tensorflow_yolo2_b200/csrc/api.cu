@@ -36,6 +36,9 @@ static void env_read() {
   e.conv_no_kwmerge = on("Y2_CONV_NO_KWMERGE");
   e.conv_no_tma_store = on("Y2_CONV_NO_TMA_STORE");
   e.conv_tma_store_split = on("Y2_CONV_TMA_STORE_SPLIT");
+  e.bn_stats_unr4 = on("Y2_BN_STATS_UNR4");
+  e.bn_stats_variant = num("Y2_BN_STATS_VARIANT", 0);
+  e.bn_bwd_minb = num("Y2_BN_BWD_MINB", 4);
   e.affine_generic = on("Y2_AFFINE_GENERIC");
   e.no_pdl = on("Y2_NO_PDL");
   e.conv_streamk_x3_generic = on("Y2_CONV_STREAMK_X3_GENERIC");

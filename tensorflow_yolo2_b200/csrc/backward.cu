@@ -17,6 +17,7 @@
 #include "common.cuh"
 
 namespace y2 {
+int num_sms();                    // conv_tcgen05.cu: SM count of the current device
 
 // ---------------------------------------------------------------------------------------------
 // pooled unit -> rows.  unit u indexes output pixels (n, ho, wo); rows are input pixels.
@@ -86,8 +87,8 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ h, int ldh, const
 
 // Vectorised pass 1 (C % 4 == 0): a thread owns 4 channels (16-byte loads of h, 8-byte loads of bf16 dy) and keeps
 // UNR units in flight; block = TX channel groups x (256/TX) unit lanes.
-template <bool POOL, int TX>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_v4_kernel(
+template <bool POOL, int TX, int MINB>
+__global__ void __launch_bounds__(256, MINB) bn_bwd_reduce_v4_kernel(
     const float* __restrict__ h, int ldh, const void* __restrict__ dy, int dy_f32, const float* __restrict__ mean,
     const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float alpha,
     int leaky_on, int H, int W, int C, size_t units, size_t units_per_split, double* __restrict__ part) {
@@ -97,7 +98,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v4_kernel(
   __shared__ double sm[TY][TX][8];
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int c0 = (blockIdx.x * TX + tx) * 4;
-  const size_t u0 = (size_t)blockIdx.y * units_per_split, u1 = min(units, u0 + units_per_split);
+  // unit tiles of UNR*TY units dealt to the splits round-robin (see bn_stats_partial_v4_kernel: DRAM page locality)
+  (void)units_per_split;
+  const size_t u1 = units;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c0 < C) {
     const float4 mu = *reinterpret_cast<const float4*>(mean + c0), vr = *reinterpret_cast<const float4*>(var + c0);
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v4_kernel(
     const float pg[4] = {g.x, g.y, g.z, g.w}, pb[4] = {b.x, b.y, b.z, b.w};
     float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int cnt = 0;
-    for (size_t ub = u0 + ty; ub < u1; ub += (size_t)UNR * TY) {
+    for (size_t ub = (size_t)blockIdx.y * UNR * TY + ty; ub < u1; ub += (size_t)gridDim.y * UNR * TY) {
       float4 hv[UNR][NR];
       float dv[UNR][4];
 #pragma unroll
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v4_kernel(
         if (u < u1) {
           const UnitRows ur = unit_rows(u, H, W, POOL);
 #pragma unroll
-          for (int k = 0; k < NR; ++k) hv[j][k] = __ldg(reinterpret_cast<const float4*>(h + ur.r[k] * ldh + c0));
+          for (int k = 0; k < NR; ++k) hv[j][k] = __ldg(reinterpret_cast<const float4*>(h + ur.r[k] * ldh + c0));   // (re-read by the apply pass)
           if (dy_f32) {
             const float4 q = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + u * C + c0));
             dv[j][0] = q.x; dv[j][1] = q.y; dv[j][2] = q.z; dv[j][3] = q.w;
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(
   }
   const unsigned Wo = POOL ? (unsigned)W >> 1 : (unsigned)W, Ho = POOL ? (unsigned)H >> 1 : (unsigned)H;
   const unsigned ustep = gridDim.x * blockDim.y;
+  // (un-pooled layers with four rows in flight per thread: measured no faster -- layer 3 304 -> 328 us -- not kept)
   for (unsigned u = blockIdx.x * blockDim.y + threadIdx.y; u < units; u += ustep) {
     size_t rows[POOL ? 4 : 1];
     if (POOL) {
@@ -676,12 +680,25 @@ int y2_bn_leaky_pool_bwd(const float* h_raw, int ldh, const void* dy, int dy_dty
   splits = (int)((units + ups - 1) / ups);
   if (C % 4 == 0 && ldh % 4 == 0 && (((uintptr_t)h_raw) & 15) == 0 && (((uintptr_t)dy) & 15) == 0) {
     const int cg = C / 4;
-#define Y2_LAUNCH_RED(POOL_, TX_)                                                                                     \
-  bn_bwd_reduce_v4_kernel<POOL_, TX_><<<dim3((cg + TX_ - 1) / TX_, splits), 256, 0, st>>>(                            \
+    const int minb = env().bn_bwd_minb;
+    {   // one wave of blocks (see bn_stats_impl); tiles are dealt round-robin, so any number of splits is balanced
+      const int tx = cg <= 8 ? 8 : (cg <= 16 ? 16 : 32);
+      const int wave = num_sms() * (minb == 1 ? 2 : minb) / ((cg + tx - 1) / tx);
+      if (splits > wave) splits = wave > 1 ? wave : 1;
+    }
+#define Y2_LAUNCH_RED1(POOL_, TX_, MB_)                                                                               \
+  bn_bwd_reduce_v4_kernel<POOL_, TX_, MB_><<<dim3((cg + TX_ - 1) / TX_, splits), 256, 0, st>>>(                       \
       h_raw, ldh, dy, dy_dtype == 0, mean, var, gamma, beta, eps, alpha, leaky_on, H, W, C, units, ups, (double*)workspace)
+#define Y2_LAUNCH_RED(POOL_, TX_)                                                                                     \
+  do {                                                                                                                \
+    if (minb == 1) Y2_LAUNCH_RED1(POOL_, TX_, 1);                                                                     \
+    else if (minb == 4) Y2_LAUNCH_RED1(POOL_, TX_, 4);                                                                \
+    else Y2_LAUNCH_RED1(POOL_, TX_, 3);                                                                               \
+  } while (0)
     if (pool) { if (cg <= 8) Y2_LAUNCH_RED(true, 8); else if (cg <= 16) Y2_LAUNCH_RED(true, 16); else Y2_LAUNCH_RED(true, 32); }
     else      { if (cg <= 8) Y2_LAUNCH_RED(false, 8); else if (cg <= 16) Y2_LAUNCH_RED(false, 16); else Y2_LAUNCH_RED(false, 32); }
 #undef Y2_LAUNCH_RED
+#undef Y2_LAUNCH_RED1
   } else {
     dim3 grid((C + 31) / 32, splits), block(32, 8);
     bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(h_raw, ldh, dy, dy_dtype == 0, mean, var, gamma, beta, eps, alpha, leaky_on,

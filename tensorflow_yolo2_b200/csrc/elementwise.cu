@@ -216,34 +216,41 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ x, int M, int 
 
 // Vectorised variant (C % 4 == 0): a thread owns 4 consecutive channels (16-byte loads) and keeps four rows in
 // flight; block = TX channel groups x (256/TX) row lanes, so narrow layers (C = 32) still fill 256 threads.
-template <int TX>
+template <int TX, int UNR>
 __global__ void __launch_bounds__(256) bn_stats_partial_v4_kernel(const float* __restrict__ x, int M, int C, int ld,
-                                                                  int rows_per_split, double* __restrict__ part) {
+                                                                  int rows_per_split, double* __restrict__ part, int stream_loads) {
   constexpr int TY = 256 / TX;
   __shared__ double sm[TY][TX][8];
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int c0 = (blockIdx.x * TX + tx) * 4;
-  const int r0 = blockIdx.y * rows_per_split, r1 = min(M, r0 + rows_per_split);
+  // Row tiles of 4*TY rows are dealt to the splits ROUND-ROBIN (split y takes tiles y, y + splits, ...), not as one contiguous
+  // range per split: all resident blocks then stream through the same few hundred KB at any moment (DRAM pages stay open)
+  // instead of 1024 far-apart streams -- the contiguous version reached 3.9 TB/s of 6.5 (ncu r2n).  Still a fixed assignment:
+  // the result does not depend on scheduling.
+  (void)rows_per_split;
+  const int r1 = M;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c0 < C) {
     const float4 k = *reinterpret_cast<const float4*>(x + c0);
     float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int cnt = 0;
     // (eight rows in flight instead of four was tried: 17 -> 20 us per head layer under ncu, no gain live)
-    for (int rb = r0 + ty; rb < r1; rb += 4 * TY) {
-      float4 v[4];
+    for (int rb = blockIdx.y * UNR * TY + ty; rb < r1; rb += gridDim.y * UNR * TY) {
+      float4 v[UNR];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < UNR; ++j) {
         const int r = rb + j * TY;
-        v[j] = r < r1 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ld + c0)) : k;   // (default caching: the affine pass re-reads it)
+        // default caching when the rows fit in L2 (the affine pass re-reads them), streaming (evict-first) loads otherwise
+        const float4* px = reinterpret_cast<const float4*>(x + (size_t)r * ld + c0);
+        v[j] = r < r1 ? (stream_loads ? __ldcs(px) : __ldg(px)) : k;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < UNR; ++j) {
         const float d0 = v[j].x - k.x, d1 = v[j].y - k.y, d2 = v[j].z - k.z, d3 = v[j].w - k.w;
         f[0] += d0; f[1] += d1; f[2] += d2; f[3] += d3;
         f[4] = fmaf(d0, d0, f[4]); f[5] = fmaf(d1, d1, f[5]); f[6] = fmaf(d2, d2, f[6]); f[7] = fmaf(d3, d3, f[7]);
       }
-      if (++cnt == 8) {
+      if (++cnt == 32 / UNR) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { acc[i] += (double)f[i]; f[i] = 0.0f; }
         cnt = 0;
@@ -851,9 +858,27 @@ static int bn_stats_impl(const float* x, int M, int C, int ld, float* mean, floa
   splits = (M + rows - 1) / rows;
   if (C % 4 == 0 && ld % 4 == 0 && (((uintptr_t)x) & 15) == 0) {
     const int cg = C / 4;
-    if (cg <= 8) bn_stats_partial_v4_kernel<8><<<dim3((cg + 7) / 8, splits), 256, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
-    else if (cg <= 16) bn_stats_partial_v4_kernel<16><<<dim3(1, splits), 256, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
-    else bn_stats_partial_v4_kernel<32><<<dim3((cg + 31) / 32, splits), 256, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
+    // ONE wave of blocks: registers allow 5 blocks of 256 threads per SM, and the 1024 splits of a large map used to run as
+    // 740 + 284 -- the second wave at 38 % occupancy (ncu r2n: 46 % of the warp slots active, 3.9 TB/s).  The round-robin
+    // tile assignment balances any number of splits.  Layer 1 at batch 64 (1.4 GB): 382 -> 237 us = 6.0 TB/s.
+    {
+      const int tx = cg <= 8 ? 8 : (cg <= 16 ? 16 : 32);
+      const int wave = g_sms_elementwise() * ((env().bn_stats_variant & 2) ? 4 : 5) / ((cg + tx - 1) / tx);
+      if (!env().bn_stats_unr4 && splits > wave) splits = wave > 1 ? wave : 1;
+    }
+    // large maps: eight rows (128 B per thread) in flight -- with four the kernel sat at 3.9 TB/s (ncu r2n: 47 % of DRAM peak, the
+    // affine pass with 128 B per thread in flight reaches 5.7); the deep 13x13 layers keep four (measured: no gain there)
+    const bool deep = M >= 32768 && !env().bn_stats_unr4;
+    const int cs = ((size_t)M * ld * 4 > (96u << 20)) && !(env().bn_stats_variant & 1) ? 1 : 0;
+#define Y2_LAUNCH_STATS(TX_)                                                                                                  \
+  do {                                                                                                                        \
+    if (deep) bn_stats_partial_v4_kernel<TX_, 8><<<dim3((cg + TX_ - 1) / TX_, splits), 256, 0, st>>>(x, M, C, ld, rows, (double*)workspace, cs); \
+    else bn_stats_partial_v4_kernel<TX_, 4><<<dim3((cg + TX_ - 1) / TX_, splits), 256, 0, st>>>(x, M, C, ld, rows, (double*)workspace, cs);      \
+  } while (0)
+    if (cg <= 8) Y2_LAUNCH_STATS(8);
+    else if (cg <= 16) Y2_LAUNCH_STATS(16);
+    else Y2_LAUNCH_STATS(32);
+#undef Y2_LAUNCH_STATS
   } else {
     dim3 grid((C + 31) / 32, splits), block(32, 8);
     bn_stats_partial_kernel<<<grid, block, 0, st>>>(x, M, C, ld, rows, (double*)workspace);
