@@ -178,12 +178,24 @@ __global__ void __launch_bounds__(32 * BWD_FIN_TY) bn_bwd_final_kernel(const dou
   __shared__ double s1[BWD_FIN_TY][33], s2[BWD_FIN_TY][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double a1 = 0.0, a2 = 0.0;
-  if (c < C)
-    for (int s = threadIdx.y; s < splits; s += BWD_FIN_TY) {
+  if (c < C) {
+    double b1 = 0.0, b2 = 0.0, c1 = 0.0, c2 = 0.0, d1 = 0.0, d2 = 0.0;      // four independent loads in flight, fixed order
+    int s = threadIdx.y;
+    for (; s + 3 * BWD_FIN_TY < splits; s += 4 * BWD_FIN_TY) {
+      const double2 p0 = *reinterpret_cast<const double2*>(part + ((size_t)s * C + c) * 2);
+      const double2 p1 = *reinterpret_cast<const double2*>(part + ((size_t)(s + BWD_FIN_TY) * C + c) * 2);
+      const double2 p2 = *reinterpret_cast<const double2*>(part + ((size_t)(s + 2 * BWD_FIN_TY) * C + c) * 2);
+      const double2 p3 = *reinterpret_cast<const double2*>(part + ((size_t)(s + 3 * BWD_FIN_TY) * C + c) * 2);
+      a1 += p0.x; a2 += p0.y; b1 += p1.x; b2 += p1.y; c1 += p2.x; c2 += p2.y; d1 += p3.x; d2 += p3.y;
+    }
+    for (; s < splits; s += BWD_FIN_TY) {
       const double2 p = *reinterpret_cast<const double2*>(part + ((size_t)s * C + c) * 2);
       a1 += p.x;
       a2 += p.y;
     }
+    a1 = (a1 + b1) + (c1 + d1);
+    a2 = (a2 + b2) + (c2 + d2);
+  }
   s1[threadIdx.y][threadIdx.x] = a1;
   s2[threadIdx.y][threadIdx.x] = a2;
   __syncthreads();
@@ -198,7 +210,7 @@ __global__ void __launch_bounds__(32 * BWD_FIN_TY) bn_bwd_final_kernel(const dou
 // The generic kernel below spent 3.5 ms of a 17.4 ms training step (ncu launch list) on 64-bit div/mod per element,
 // scalar bf16 dy loads and six constant loads + two rsqrt per channel per element.
 template <bool POOL>
-__global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_rows_kernel(
     const float* __restrict__ h, int ldh, const void* __restrict__ dy, int dy_f32, const float* __restrict__ mean,
     const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ dgamma, const float* __restrict__ dbeta, float eps, float alpha, int leaky_on, int H, int W, int C,
