@@ -64,13 +64,16 @@ static_assert(C1_MMA_WARPS == C1_NBUF && C1_EPI_GROUPS == C1_NBUF, "MMA warp m /
 static_assert(C1_A_STAGES % C1_MMA_WARPS == 0 && C1_RAW_STAGES % C1_CVT_WARPS == 0 && C1_RAW_STAGES % C1_PROD_WARPS == 0,
               "stage -> warp ownership must be static");
 constexpr int C1_TASKS = C1_PROWS * (C1_PCOLS / 2);     // 16-byte (two-pixel) units per patch
-constexpr size_t C1_SMEM = 1024 + C1_B_BYTES + C1_A_STAGES * C1_A_STAGE + C1_RAW_STAGES * C1_RAW_STAGE;
+// Output staging for the TMA-store epilogue: one buffer per epilogue group, 128 pooled pixels x 64 B (bf16) / 128 B ([hi | lo]);
+// a group owns every fourth tile, so its previous box store has long been read out of smem when it writes the next one.
+constexpr int C1_STG = 128 * 64;
+constexpr size_t C1_SMEM = 1024 + C1_B_BYTES + C1_A_STAGES * C1_A_STAGE + C1_RAW_STAGES * C1_RAW_STAGE + C1_EPI_GROUPS * C1_STG + 1024;
 // bf16x3 variant (SPLIT): the patch holds the raw bytes as EXACT bf16 integers (v0, v1, v2) plus a "ones" channel that is
 // 1 inside the image and 0 in the SAME-padding halo; the preprocessing x = v*2/255 - 1 is folded into the weights
 // (w*2/255 on the colour channels, -sum_c w on the ones channel), which are kept as a hi + lo bf16 pair.  So A is exact,
 // B carries 16 mantissa bits, and a tile costs 8 MMAs (4 footprint rows x {hi, lo}) into the same accumulator.  The output
 // row is [hi(32) | lo(32)] (Y2_CONV_OUT_SPLIT layout).
-constexpr size_t C1_SMEM_SPLIT = C1_SMEM + C1_B_BYTES;
+constexpr size_t C1_SMEM_SPLIT = C1_SMEM + C1_B_BYTES + C1_EPI_GROUPS * C1_STG;
 
 struct Conv1Args {
   const uint4* w_packed;
@@ -80,6 +83,7 @@ struct Conv1Args {
   int tiles_w, tiles_per_img, total_tiles;
   uint32_t fd_img_mul, fd_img_shr, fd_w_mul, fd_w_shr;   // magic-number division by tiles_per_img / tiles_w
   float alpha;
+  int tma_store;         // the pooled tile leaves as one TMA box store from swizzled smem (0: 16-byte global stores per lane)
   int debug;             // ablation knobs (env Y2_CONV1_DEBUG): 1 no raw loads, 2 no conversion, 4 no TMEM drain/stores, 8 no MMA
 };
 
@@ -118,7 +122,7 @@ __device__ __forceinline__ C1Tile c1_tile(const Conv1Args& a, int tile) {
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(C1_THREADS, 1)
-conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args a) {
+conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_constant__ CUtensorMap tmY, const Conv1Args a) {
   constexpr int B_BYTES = SPLIT ? 2 * C1_B_BYTES : C1_B_BYTES;
   pdl_launch_dependents();   // persistent grid: layer 2 (launched with programmatic serialization) may take SMs as my CTAs retire
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -133,6 +137,8 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args 
   const uint32_t sB = sm0;
   const uint32_t sA = sB + B_BYTES;
   const uint32_t sRaw = sA + C1_A_STAGES * C1_A_STAGE;
+  constexpr uint32_t STG_BYTES = SPLIT ? 2 * C1_STG : C1_STG, STG_ROW = SPLIT ? 128 : 64;
+  const uint32_t sStg = (sRaw + C1_RAW_STAGES * C1_RAW_STAGE + 1023u) & ~1023u;      // swizzle atoms: 1024-byte aligned
   uint8_t* const gen0 = smem + (sm0 - smem_u32(smem));              // generic pointer to the aligned base
 
   // ---- one-time setup ----
@@ -266,6 +272,11 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args 
     const int r = q * 32 + lane, g = r >> 3, i = r & 7;
     const int Ho = a.H >> 1, Wo = a.W >> 1;
     const float alpha = a.alpha;
+    const bool tma_st = a.tma_store != 0;
+    const bool st_leader = q == 0 && lane == 0;
+    // my row of the staging box (row r = g * 8 + i, STG_ROW bytes); 16-byte unit u sits at u ^ swz (SWIZZLE_64B / _128B)
+    const uint32_t stg_row = sStg + (uint32_t)eg * STG_BYTES + (uint32_t)r * STG_ROW;
+    const uint32_t swz = SPLIT ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
     for (int it = eg;; it += C1_EPI_GROUPS) {
       const int tile = first + it * step;
       if (tile >= a.total_tiles) break;
@@ -280,6 +291,10 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args 
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         continue;
+      }
+      if (tma_st) {
+        if (st_leader) bulk_wait_group_read<0>();        // my group's previous box store has read the staging buffer
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
       }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {                  // 8 output channels at a time
@@ -311,7 +326,12 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args 
           __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
           o[e] = *reinterpret_cast<uint32_t*>(&h);
         }
-        dst[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+        if (tma_st)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + (((uint32_t)ch ^ swz) << 4)), "r"(o[0]), "r"(o[1]),
+                       "r"(o[2]), "r"(o[3])
+                       : "memory");
+        else
+          dst[ch] = make_uint4(o[0], o[1], o[2], o[3]);
         if constexpr (SPLIT) {
           uint32_t l[4];
 #pragma unroll
@@ -320,11 +340,25 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const Conv1Args 
             __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
             l[e] = *reinterpret_cast<uint32_t*>(&h);
           }
-          dst[4 + ch] = make_uint4(l[0], l[1], l[2], l[3]);     // lo half: channels 32..63 of the row
+          if (tma_st)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + (((uint32_t)(4 + ch) ^ swz) << 4)), "r"(l[0]),
+                         "r"(l[1]), "r"(l[2]), "r"(l[3])
+                         : "memory");
+          else
+            dst[4 + ch] = make_uint4(l[0], l[1], l[2], l[3]);     // lo half: channels 32..63 of the row
+        }
+      }
+      if (tma_st) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+        if (st_leader) {
+          tma_store_4d(&tmY, sStg + (uint32_t)eg * STG_BYTES, 0, t.pw0, t.ph0, t.n);
+          bulk_commit_group();
         }
       }
       __syncwarp();
     }
+    if (tma_st && st_leader) bulk_wait_group_read<0>();   // smem must outlive the last box store's read
   }
 
   tc_fence_before();
@@ -423,7 +457,23 @@ static int conv1_u8_pool_launch(const uint8_t* img, const void* w_packed, const 
   a.total_tiles = (int)total;
   a.alpha = alpha;
   a.debug = env().conv1_debug;
-  CUtensorMap tmImg;
+  a.tma_store = env().conv1_no_tma_store ? 0 : 1;
+  CUtensorMap tmImg, tmY;
+  {
+    // pooled output [N, H/2, W/2, 32 | 64] bf16: boxes of one tile (8 x 16 pooled pixels, the whole row), swizzled rows
+    const cuuint64_t cw = split ? 2 * C1_COUT : C1_COUT, Ho = H / 2, Wo = W / 2;
+    cuuint64_t dims[4] = {cw, Wo, Ho, (cuuint64_t)N};
+    cuuint64_t strides[3] = {cw * 2, Wo * cw * 2, Ho * Wo * cw * 2};
+    cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)C1_TW, (cuuint32_t)C1_TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encodeTiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               split ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("y2_conv1_u8_pool_fwd: output tensor map encode failed (CUresult %d)", (int)r);
+      return Y2_ERR_DRIVER;
+    }
+  }
   {
     cuuint64_t dims[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[2] = {(cuuint64_t)W * 3, (cuuint64_t)H * W * 3};
@@ -440,10 +490,10 @@ static int conv1_u8_pool_launch(const uint8_t* img, const void* w_packed, const 
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
   if (split) {
     Y2_CUDA(cudaFuncSetAttribute(conv1_u8_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1_SMEM_SPLIT));
-    conv1_u8_pool_kernel<true><<<grid, C1_THREADS, C1_SMEM_SPLIT, (cudaStream_t)stream>>>(tmImg, a);
+    conv1_u8_pool_kernel<true><<<grid, C1_THREADS, C1_SMEM_SPLIT, (cudaStream_t)stream>>>(tmImg, tmY, a);
   } else {
     Y2_CUDA(cudaFuncSetAttribute(conv1_u8_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1_SMEM));
-    conv1_u8_pool_kernel<false><<<grid, C1_THREADS, C1_SMEM, (cudaStream_t)stream>>>(tmImg, a);
+    conv1_u8_pool_kernel<false><<<grid, C1_THREADS, C1_SMEM, (cudaStream_t)stream>>>(tmImg, tmY, a);
   }
   Y2_LAUNCHED();
   return Y2_OK;

@@ -15,7 +15,7 @@ timeout 600 python bench.py --mode train --steps 10 --warmup 3 2>> gpurun_out/${
 timeout 300 python tools/bench_detect.py 2>> gpurun_out/${TAG}_bench.err | grep '^{' > gpurun_out/${TAG}_bench_detect.json
 bash tools/profile_step.sh ${TAG} 2>&1 | tail -2
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_train_raw.csv python bench.py --mode train --steps 2 --warmup 3 --no-graph --no-cpu-baseline > /dev/null 2>&1
-python tools/ncu_train_breakdown.py gpurun_out/${TAG}_train_raw.csv > gpurun_out/${TAG}_train_breakdown.txt; rm -f gpurun_out/${TAG}_train_raw.csv
+python tools/ncu_train_breakdown.py gpurun_out/${TAG}_train_raw.csv --detail > gpurun_out/${TAG}_train_breakdown.txt; rm -f gpurun_out/${TAG}_train_raw.csv
 tail -c 400 gpurun_out/${TAG}_bench.err
 python - <<PY
 import json

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list of `bench.py --mode train --no-graph` by kernel for
 ONE training step (the launches between the last two L2-flush memsets that enclose the most common launch count).
-    python tools/ncu_train_breakdown.py gpurun_out/train_launches.csv > profiles/r2_train_breakdown.txt"""
+    python tools/ncu_train_breakdown.py gpurun_out/train_launches.csv [--detail] > profiles/r2_train_breakdown.txt
+--detail appends the launches of the contraction kernels (forward conv, data gradient, weight gradient) in launch order."""
 import csv
 import re
 import sys
@@ -40,6 +41,11 @@ def main():
     print('one training step under ncu (cold-cache, serialised launches): %d launches, %.1f us' % (len(step), total))
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print('  %-44s x%-3d %9.1f us  %5.1f %%' % (k, c, t, 100 * t / total))
+    if '--detail' in sys.argv:
+        print('contraction kernels in launch order (forward layers 1..22, then backward 22..1: wgrad, dgrad):')
+        for i, (n, v) in enumerate(step):
+            if n.startswith('conv'):
+                print('  #%-3d %-60s %8.1f us' % (i, n[:60], v))
 
 
 if __name__ == '__main__':
