@@ -63,7 +63,6 @@ static_assert(C1_MMA_WARPS == C1_NBUF && C1_EPI_GROUPS == C1_NBUF, "MMA warp m /
 // buffers dead-locked exactly this way at 146 tiles per CTA while passing every small test).
 static_assert(C1_A_STAGES % C1_MMA_WARPS == 0 && C1_RAW_STAGES % C1_CVT_WARPS == 0 && C1_RAW_STAGES % C1_PROD_WARPS == 0,
               "stage -> warp ownership must be static");
-constexpr int C1_TASKS = C1_PROWS * (C1_PCOLS / 2);     // 16-byte (two-pixel) units per patch
 // Output staging for the TMA-store epilogue: one buffer per epilogue group, 128 pooled pixels x 64 B (bf16) / 128 B ([hi | lo]);
 // a group owns every fourth tile, so its previous box store has long been read out of smem when it writes the next one.
 constexpr int C1_STG = 128 * 64;
@@ -92,19 +91,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr)
                : "memory");
-}
-
-// two bytes -> two bf16 holding the byte values exactly, packed (first byte in the low half)
-__device__ __forceinline__ uint32_t c1_cvt2_int(uint32_t b0, uint32_t b1) {
-  __nv_bfloat162 h = __floats2bfloat162_rn((float)b0, (float)b1);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// two bytes -> two bf16 of (v/255)*2-1, packed (first byte in the low half)
-__device__ __forceinline__ uint32_t c1_cvt2(uint32_t b0, uint32_t b1) {
-  const float k = 2.0f / 255.0f;
-  __nv_bfloat162 h = __floats2bfloat162_rn(fmaf((float)b0, k, -1.0f), fmaf((float)b1, k, -1.0f));
-  return *reinterpret_cast<uint32_t*>(&h);
 }
 
 struct C1Tile {
@@ -190,40 +176,77 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
       const C1Tile t = c1_tile(a, tile);
       if (!(a.debug & 1)) mbar_wait(&raw_full[rs], (uint32_t)(it / C1_RAW_STAGES) & 1u);
       mbar_wait(&a_empty[cw], ((uint32_t)(it / C1_A_STAGES) & 1u) ^ 1u);
-      const uint8_t* raw = gen0 + (sRaw - sm0) + rs * C1_RAW_STAGE + C1_RAW_LEAD;
+      const uint8_t* raw = gen0 + (sRaw - sm0) + rs * C1_RAW_STAGE;
       const int row0 = 2 * t.ph0 - 1, col0 = 2 * t.pw0 - 1;
-#pragma unroll 2
-      for (int task = (a.debug & 2) ? C1_TASKS : lane; task < C1_TASKS; task += 32) {
-        const int pr = task / (C1_PCOLS / 2), j = task - pr * (C1_PCOLS / 2);
-        const bool rok = (unsigned)(row0 + pr) < (unsigned)a.H;
-        const int ca = col0 + 2 * j;
-        const bool va = rok && ca >= 0, vb = rok && ca + 1 < a.W;
-        const uint8_t* p = raw + pr * C1_RAW_ROW + 6 * j;
-        // bf16_rn(fma(v, 2/255, -1)) == bf16_rn((v/255)*2 - 1) for all 256 byte values (tests/test_abi_cpu.py checks
-        // the identity), so no LUT: the smem crossbar is the contended resource of this kernel
-        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-        if constexpr (SPLIT) {
-          if (va) {
-            w0 = c1_cvt2_int(p[0], p[1]);
-            w1 = (c1_cvt2_int(p[2], 0) & 0xffffu) | 0x3f800000u;   // channel 3 = 1.0 inside the image
-          }
-          if (vb) {
-            w2 = c1_cvt2_int(p[3], p[4]);
-            w3 = (c1_cvt2_int(p[5], 0) & 0xffffu) | 0x3f800000u;
+      // One patch ROW per lane: the 80 raw bytes arrive in five conflict-free 16-byte loads (rows are 80 B apart), the 54
+      // image bytes sit at COMPILE-TIME positions (lead of 13 bytes), so every byte is one PRMT into the mantissa of 2^23,
+      // one FADD (exact) and -- bf16 mode -- one FFMA: all independent, no byte loads, no I2F.  The per-task version (two
+      // pixels per lane and iteration: 6 byte loads -> I2F -> FFMA -> pack -> store, a serial chain) took ~5 500 clk per
+      // tile and warp; with four converter warps the kernel was conversion-bound at 120 us (r2n ablation).
+      // rows 0..31: one per lane (static byte positions); rows 32..33: their 18 two-pixel units go to lanes 0..17 with
+      // byte loads (a second full row pass would issue 235 instructions for two active lanes)
+      static_assert(C1_PROWS == 34 && C1_PCOLS == 18, "converter passes are laid out for a 34 x 18 patch");
+#pragma unroll 1
+      for (int pass = (a.debug & 2) ? 2 : 0; pass < 2; ++pass) {
+        if (pass == 1 && lane >= 2 * (C1_PCOLS / 2)) break;
+        const int pr = pass == 0 ? lane : 32 + lane / (C1_PCOLS / 2);
+        const int jt = pass == 0 ? 0 : lane % (C1_PCOLS / 2);
+        uint32_t w[20];
+        if (pass == 0) {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const uint4 q = *reinterpret_cast<const uint4*>(raw + pr * C1_RAW_ROW + 16 * i);
+            w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
           }
         } else {
-          if (va) {
-            w0 = c1_cvt2(p[0], p[1]);
-            w1 = c1_cvt2(p[2], 0) & 0xffffu;         // channel 3 is zero padding
-          }
-          if (vb) {
-            w2 = c1_cvt2(p[3], p[4]);
-            w3 = c1_cvt2(p[5], 0) & 0xffffu;
-          }
+          const uint8_t* pb = raw + pr * C1_RAW_ROW + C1_RAW_LEAD + 6 * jt;    // place the unit's 6 bytes where unit 0 is read from
+          w[3] = (uint32_t)pb[0] << 8 | (uint32_t)pb[1] << 16 | (uint32_t)pb[2] << 24;
+          w[4] = (uint32_t)pb[3] | (uint32_t)pb[4] << 8 | (uint32_t)pb[5] << 16;
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dstA + pr * C1_PITCH + j * 16), "r"(w0), "r"(w1),
-                     "r"(w2), "r"(w3)
-                     : "memory");
+        const bool rok = (unsigned)(row0 + pr) < (unsigned)a.H;
+#pragma unroll
+        for (int j = 0; j < C1_PCOLS / 2; ++j) {
+          if (pass == 1 && j > 0) break;
+          const int jj = pass == 0 ? j : jt;                           // which unit of the row this is
+          const int ca = col0 + 2 * jj;
+          const bool va = rok && ca >= 0, vb = rok && ca + 1 < a.W;
+          float f[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const int bi = C1_RAW_LEAD + 6 * j + k;                  // compile-time after unrolling
+            f[k] = __uint_as_float(__byte_perm(w[bi >> 2], 0x4B000000u, 0x7650u | (uint32_t)(bi & 3))) - 8388608.0f;
+          }
+          uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+          if constexpr (SPLIT) {
+            // exact integers (8 significant bits fit bf16); channel 3 = 1.0 inside the image
+            if (va) {
+              w0 = __byte_perm(__float_as_uint(f[0]), __float_as_uint(f[1]), 0x7632);
+              w1 = (__float_as_uint(f[2]) >> 16) | 0x3f800000u;
+            }
+            if (vb) {
+              w2 = __byte_perm(__float_as_uint(f[3]), __float_as_uint(f[4]), 0x7632);
+              w3 = (__float_as_uint(f[5]) >> 16) | 0x3f800000u;
+            }
+          } else {
+            // bf16_rn(fma(v, 2/255, -1)) == bf16_rn((v/255)*2 - 1) for all 256 byte values (tests/test_abi_cpu.py)
+            const float kk = 2.0f / 255.0f;
+            if (va) {
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaf(f[0], kk, -1.0f), fmaf(f[1], kk, -1.0f));
+              const __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaf(f[2], kk, -1.0f), 0.0f);        // channel 3 is zero padding
+              w0 = *reinterpret_cast<const uint32_t*>(&h0);
+              w1 = *reinterpret_cast<const uint32_t*>(&h1);
+            }
+            if (vb) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaf(f[3], kk, -1.0f), fmaf(f[4], kk, -1.0f));
+              const __nv_bfloat162 h3 = __floats2bfloat162_rn(fmaf(f[5], kk, -1.0f), 0.0f);
+              w2 = *reinterpret_cast<const uint32_t*>(&h2);
+              w3 = *reinterpret_cast<const uint32_t*>(&h3);
+            }
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dstA + pr * C1_PITCH + jj * 16), "r"(w0), "r"(w1), "r"(w2),
+                       "r"(w3)
+                       : "memory");
+        }
       }
       fence_proxy_async_smem();                       // patch is consumed by tcgen05.mma (async proxy)
       __syncwarp();
