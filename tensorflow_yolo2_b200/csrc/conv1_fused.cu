@@ -83,7 +83,8 @@ struct Conv1Args {
   uint32_t fd_img_mul, fd_img_shr, fd_w_mul, fd_w_shr;   // magic-number division by tiles_per_img / tiles_w
   float alpha;
   int tma_store;         // the pooled tile leaves as one TMA box store from swizzled smem (0: 16-byte global stores per lane)
-  int debug;             // ablation knobs (env Y2_CONV1_DEBUG): 1 no raw loads, 2 no conversion, 4 no TMEM drain/stores, 8 no MMA
+  int debug;             // ablation knobs (env Y2_CONV1_DEBUG): 1 no raw loads, 2 no conversion, 4 no TMEM drain/stores, 8 no MMA,
+                         // 16 TMEM drain without the pooling math / output
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
@@ -332,6 +333,7 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         }
+        if (a.debug & 16) continue;                       // ablation: TMEM drain only (no pooling math, no output)
         const float4 sa = *reinterpret_cast<const float4*>(&s_shift[ch * 8]);
         const float4 sb = *reinterpret_cast<const float4*>(&s_shift[ch * 8 + 4]);
         const float shv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
