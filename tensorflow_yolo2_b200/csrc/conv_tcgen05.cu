@@ -763,7 +763,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // lines: ncu (layer 3 vs the pooled layer 5, identical MMA work) showed the LSU/MIO pipe congested by them -- LDS of
     // scale/shift stalling (short scoreboard), the MMA warp's own LDS delayed, tensor pipe 48 % vs 71 %.
     constexpr bool tma_store = TMAST;
-    static_assert(!TMAST || (A_MODE == 2 && !FIRST), "TMA-store epilogue: halo-patch mode only");
+    static_assert(!TMAST || A_MODE == 2, "TMA-store epilogue: halo-patch mode only");
     const uint32_t stg_group = smem_b_stat + a.stg_offset + (uint32_t)gi * 16384u;
     uint32_t nstore = 0;
     for (int it = tp;; it += TP) {
@@ -820,6 +820,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int c0 = nbase + cc;
         if constexpr (tma_store) {
+         if (out_f32) {
+          // float32 rows (the training forward pass: conv + bias): the 32-column chunk leaves as TWO boxes of 16 columns -- 64 bytes
+          // per row, the staging geometry of the bf16 case.  The direct path issues eight 16-byte stores per lane and chunk, each
+          // instruction touching 32 different lines.
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            const uint32_t stg = stg_group + (nstore & 1u) * 8192u;
+            if (r == 0) bulk_wait_group_read<1>();
+            asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = 16 * part + 4 * j;
+              const float4 sc = *reinterpret_cast<const float4*>(&my_scale[cc + i]);
+              const float4 sh = *reinterpret_cast<const float4*>(&my_shift[cc + i]);
+              float f0 = fmaf(__uint_as_float(v[i + 0]), sc.x, sh.x), f1 = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
+              float f2 = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z), f3 = fmaf(__uint_as_float(v[i + 3]), sc.w, sh.w);
+              if (leaky_on) {
+                f0 = fmaxf(f0, a.alpha * f0); f1 = fmaxf(f1, a.alpha * f1);
+                f2 = fmaxf(f2, a.alpha * f2); f3 = fmaxf(f3, a.alpha * f3);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4)),
+                           "r"(__float_as_uint(f0)), "r"(__float_as_uint(f1)), "r"(__float_as_uint(f2)), "r"(__float_as_uint(f3))
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
+            if (r == 0) {
+              tma_store_4d(&tmY, stg, c0 + 16 * part, t.w0, t.h0, t.n0);
+              bulk_commit_group();
+            }
+            ++nstore;
+          }
+         } else {
           // bf16x3 output: the chunk leaves as TWO boxes, the hi halves at channel c0 and the lo halves at lo_off + c0 (the affine
           // is evaluated again for the second box -- cheaper than keeping 32 more packed registers live)
           const int nparts = a.split_out ? 2 : 1;
@@ -869,6 +902,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             ++nstore;
           }
+         }
         } else if (A_MODE != 0 && pool && !out_f32 && c0 + 32 <= a.Cout && (a.ldy & 7) == 0 && (a.lo_off & 7) == 0) {
           epilogue_chunk_pooled_bf16(a, v, my_scale, my_shift, cc, c0, valid_px, orow, leaky_on, lane);
         } else if (c0 < (a.split_out ? a.Cout : a.ldy)) {
@@ -1213,8 +1247,11 @@ static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     case 0: return launch_conv3<BLOCK_N, 0, KIND>(tmA, tmB, tmY, a, smem, st);
     case 1: return launch_conv3<BLOCK_N, 1, KIND>(tmA, tmB, tmY, a, smem, st);
     default:
+      if constexpr (KIND == 0) {
+        if (a.tma_store) return launch_conv3<BLOCK_N, 2, KIND, false, true>(tmA, tmB, tmY, a, smem, st);
+      }
       if constexpr (KIND != 0 && BLOCK_N <= 128) {
-        if constexpr (KIND == 2 && BLOCK_N == 128) {
+        if constexpr ((KIND == 2 && BLOCK_N == 128) || (KIND == 1 && BLOCK_N == 64)) {
           if (a.cta2 && a.tma_store) return launch_conv3<BLOCK_N, 2, KIND, true, true>(tmA, tmB, tmY, a, smem, st);
         }
         if (a.cta2) return launch_conv3<BLOCK_N, 2, KIND, true>(tmA, tmB, tmY, a, smem, st);
@@ -1565,11 +1602,18 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   // leaves 3 instead of 5 operand stages next to the streamed filters and layer 3 got SLOWER, 308 -> 325 us.)
   const size_t STG_BYTES = 4 * 2 * 8192;
   a.tma_store = 0;
-  if (a.a_mode == 2 && !a.first_layer && !pool && !out_f32 && (!split_out || (a.lo_off % 8 == 0 && env().conv_tma_store_split)) &&
-      p->Cout % 32 == 0 && a.ldy % 8 == 0 &&
-      (reinterpret_cast<uintptr_t>(p->y) & 15) == 0 && EPI_GROUPS == 4 && block_n == 128 && a.row_bytes == 128 && a.cta2 &&
-      b_region + 3 * (size_t)stage_bytes + STG_BYTES <= SMEM_BUDGET && !env().conv_no_tma_store)
-    a.tma_store = 1;
+  {
+    const bool common = a.a_mode == 2 && !pool && p->Cout % 32 == 0 && a.ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(p->y) & 15) == 0 &&
+                        EPI_GROUPS == 4 && b_region + 3 * (size_t)stage_bytes + STG_BYTES <= SMEM_BUDGET && !env().conv_no_tma_store;
+    // bf16 rows: the 128-channel pair kernel (layer 3); float32 rows (training forward): also the first layer and the 64-channel
+    // pair kernel (layer 2), whose 16-byte per-lane stores cost far more than the bf16 ones
+    const bool shape_bf16 = !a.first_layer && block_n == 128 && a.row_bytes == 128 && a.cta2;
+    const bool shape_f32 = shape_bf16 || (a.first_layer && block_n == 32 && p->Cout == 32) ||
+                           (!a.first_layer && block_n == 64 && a.row_bytes == 64 && a.cta2 && p->Cout == 64);
+    // (64 columns on 128-byte operand rows -- layer 4 without the input-stationary kernel: 131 -> 141 us, not enabled)
+    if (common && !out_f32 && shape_bf16 && (!split_out || (a.lo_off % 8 == 0 && env().conv_tma_store_split))) a.tma_store = 1;
+    if (common && out_f32 && shape_f32 && !env().conv_no_tma_store_f32) a.tma_store = 1;
+  }
   const size_t stg_bytes = a.tma_store ? STG_BYTES : 0;
   int stages = (int)((SMEM_BUDGET - b_region - stg_bytes) / stage_bytes);
   if (stages > 12) stages = 12;
@@ -1661,11 +1705,13 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
   memset(&tmY, 0, sizeof(tmY));
   if (a.tma_store) {
     // output [N, H, W, Cout] with row stride ldy: boxes of 32 channels x the 8 x 16 pixel tile, 64-byte swizzled rows
+    // (float32 rows: boxes of 16 channels -- the same 64 bytes per row)
+    const cuuint64_t es = out_f32 ? 4 : 2;
     cuuint64_t dims[4] = {(cuuint64_t)(split_out ? a.lo_off + p->Cout : p->Cout), (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
-    cuuint64_t strides[3] = {(cuuint64_t)a.ldy * 2, (cuuint64_t)p->W * a.ldy * 2, (cuuint64_t)p->H * p->W * a.ldy * 2};
-    cuuint32_t box[4] = {32, 8, 16, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)a.ldy * es, (cuuint64_t)p->W * a.ldy * es, (cuuint64_t)p->H * p->W * a.ldy * es};
+    cuuint32_t box[4] = {out_f32 ? 16u : 32u, 8, 16, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encodeTiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p->y, dims, strides, box, estr,
+    CUresult r = g_encodeTiled(&tmY, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p->y, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

@@ -112,6 +112,42 @@ def test_conv_halo_pair_vs_single_cta_and_oracle(ops, monkeypatch, N, H, W, Cin,
     assert np.linalg.norm(g - want) / np.linalg.norm(want) < 4e-3
 
 
+@pytest.mark.parametrize('N,H,W,Cin,Cout,ld', [(2, 64, 80, 64, 128, 128),     # layer 3 / 5 shape of the training forward pass
+                                               (2, 70, 68, 64, 128, 160),     # tiles clipped at the right / bottom edge, padded rows
+                                               (1, 104, 104, 32, 64, 64),     # layer 2: 64-byte operand rows, 64 columns
+                                               (2, 96, 64, 3, 32, 32)])       # first layer (8-channel padded input)
+def test_conv_f32_rows_tma_store_equals_direct_stores(ops, monkeypatch, N, H, W, Cin, Cout, ld):
+    """Training forward: conv + bias as float32 rows [N*H*W, ld].  On the halo-patch path the rows leave through swizzled smem
+    and TMA box stores of 16 columns; Y2_CONV_NO_TMA_STORE_F32=1 selects the per-lane 16-byte stores: same bits, and both
+    within bf16-operand tolerance of the oracle."""
+    rs = np.random.RandomState(H + Cout)
+    x = rs.randn(N, H, W, Cin).astype(np.float32)
+    w = (rs.randn(3, 3, Cin, Cout) * 0.05).astype(np.float32)
+    b = rs.randn(Cout).astype(np.float32)
+    if Cin == 3:
+        xb = torch.zeros((N, H, W, 8), dtype=torch.bfloat16, device='cuda')
+        xb[..., :3] = cu(x, torch.bfloat16)
+    else:
+        xb = cu(x, torch.bfloat16)
+    wp = ops.pack_weights_bf16(cu(w))
+    monkeypatch.setenv('Y2_CONV_NO_IS', '1')
+    ops.reload_env()
+    outs = []
+    for direct in (False, True):
+        if direct:
+            monkeypatch.setenv('Y2_CONV_NO_TMA_STORE_F32', '1')
+            ops.reload_env()
+        y = torch.full((N * H * W, ld), -7.0, dtype=torch.float32, device='cuda')
+        ops.conv_fwd_bf16(xb, wp, 3, Cin, Cout, scale=None, shift=cu(b), leaky=False, pool=False, out_f32=True, ldy=ld, out=y)
+        torch.cuda.synchronize()
+        outs.append(y)
+    assert torch.equal(outs[0][:, :Cout], outs[1][:, :Cout])
+    want = O.conv2d_same(O.bf16_round(torch.tensor(x)).double(), O.bf16_round(torch.tensor(w)).double(), torch.float64) \
+        + torch.tensor(b).double()
+    g = outs[0][:, :Cout].cpu().numpy().reshape(N, H, W, Cout)
+    assert np.linalg.norm(g - want.numpy()) / np.linalg.norm(want.numpy()) < 1e-5
+
+
 @pytest.mark.parametrize('N,H,W,Cin,pool,out_f32,x3', [(3, 72, 72, 32, True, False, False),     # layer 2 shape: 64-byte rows, pooled epilogue
                                                          (1, 104, 104, 128, False, False, False),  # layer 4 shape: two chunks, odd tile count
                                                          (2, 70, 66, 64, False, False, False),     # ragged: W % 14 != 0, H % 8 != 0
