@@ -35,7 +35,8 @@ static void env_read() {
   e.conv_no_bstat = on("Y2_CONV_NO_BSTAT");
   e.conv_no_kwmerge = on("Y2_CONV_NO_KWMERGE");
   e.conv_no_tma_store = on("Y2_CONV_NO_TMA_STORE");
-  e.conv_tma_store_split = on("Y2_CONV_TMA_STORE_SPLIT");
+  e.conv_tma_store_split = num("Y2_CONV_TMA_STORE_SPLIT", 0);
+  e.conv_is_no_tma_store = on("Y2_CONV_IS_NO_TMA_STORE");
   e.conv_no_tma_store_f32 = on("Y2_CONV_NO_TMA_STORE_F32");
   e.conv1_no_tma_store = on("Y2_CONV1_NO_TMA_STORE");
   e.bn_stats_unr4 = on("Y2_BN_STATS_UNR4");

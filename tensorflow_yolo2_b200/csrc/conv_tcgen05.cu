@@ -764,7 +764,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // scale/shift stalling (short scoreboard), the MMA warp's own LDS delayed, tensor pipe 48 % vs 71 %.
     constexpr bool tma_store = TMAST;
     static_assert(!TMAST || A_MODE == 2, "TMA-store epilogue: halo-patch mode only");
-    const uint32_t stg_group = smem_b_stat + a.stg_offset + (uint32_t)gi * 16384u;
+    // a.tma_store == 2: ONE 8 KB buffer per group (32 KB instead of 64 KB of staging, one more operand stage for the bf16x3 layer
+    // 3); every box store then waits for the previous one's smem read
+    const bool stg_single = a.tma_store == 2;
+    const uint32_t stg_group = smem_b_stat + a.stg_offset + (uint32_t)gi * (stg_single ? 8192u : 16384u);
     uint32_t nstore = 0;
     for (int it = tp;; it += TP) {
       const int tile = sched_first + it * sched_step;
@@ -858,8 +861,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int nparts = a.split_out ? 2 : 1;
 #pragma unroll 1
           for (int part = 0; part < nparts; ++part) {
-            const uint32_t stg = stg_group + (nstore & 1u) * 8192u;
-            if (r == 0) bulk_wait_group_read<1>();              // the store that last used this buffer has read it
+            const uint32_t stg = stg_group + (stg_single ? 0u : (nstore & 1u) * 8192u);
+            if (r == 0) {                                        // the store that last used this buffer has read it
+              if (stg_single) bulk_wait_group_read<0>();
+              else bulk_wait_group_read<1>();
+            }
             asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
             // row r = h * 8 + w of the box, 64 B per row; 16-byte unit j (8 channels) at j ^ ((r >> 1) & 3)  (SWIZZLE_64B);
             // one unit at a time: affine + leaky + pack + store, so that only the 32 accumulators stay live
@@ -950,7 +956,8 @@ constexpr int IS_N = 192, IS_COUT = 64, IS_OUT_W = 14, IS_TW = 16, IS_TH = 8, IS
 
 template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-conv_is_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+conv_is_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
+               const ConvArgs a) {
   constexpr uint32_t ROW_BYTES = KIND == 1 ? 64u : 128u;
   constexpr int KSTEPS = ROW_BYTES / 32;
   constexpr int NBUF = 2;
@@ -1107,6 +1114,14 @@ conv_is_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool out_f32 = (a.flags & Y2_CONV_OUT_F32) != 0;
     const int Ho = pool ? a.H >> 1 : a.H, Wo = pool ? a.W >> 1 : a.W;
     const int cc0 = cp * 32;
+    // TMA-store epilogue (un-pooled outputs): the group's 8 x 14 output pixels x 32 channels are staged as 64-byte rows in
+    // 64B-swizzled smem (box row = h * 14 + w) and leave as one box store -- float32 rows as two boxes of 16 channels, bf16x3 as
+    // a hi and a lo box; one 8 KB buffer per group (a group stores once per two tiles).
+    const bool tma_st = a.tma_store != 0 && !pool;
+    const uint32_t stg = smem_a + (uint32_t)a.stages * stage_bytes + (uint32_t)gi * 8192u;
+    const int brow = r_th * IS_OUT_W + r_tw;
+    const uint32_t stg_row = stg + (uint32_t)brow * 64u;
+    const uint32_t swz = (uint32_t)((brow >> 1) & 3);
     int it = tp;
     for (int sg = pair + tp * npairs; sg < m_groups; sg += 2 * npairs, it += 2) {
       int n, h0, w0;
@@ -1137,12 +1152,57 @@ conv_is_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[buf]) & PEER_BIT_MASK);
-      if (pool && !out_f32 && (a.ldy & 7) == 0 && (a.lo_off & 7) == 0)
+      if (tma_st) {
+        const int nparts = (out_f32 || a.split_out) ? 2 : 1;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          if (part >= nparts) break;
+          if (r == 0) bulk_wait_group_read<0>();              // the group's previous box store has read the buffer
+          asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
+          if (r_tw < IS_OUT_W) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              if (out_f32) {
+                float f[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int i = 16 * part + 4 * j + e;
+                  f[e] = fmaf(__uint_as_float(sum[i]), s_scale[cc0 + i], s_shift[cc0 + i]);
+                  if (leaky_on) f[e] = fmaxf(f[e], a.alpha * f[e]);
+                }
+                pk = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+              } else {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int i = 8 * j + e;
+                  f[e] = fmaf(__uint_as_float(sum[i]), s_scale[cc0 + i], s_shift[cc0 + i]);
+                  if (leaky_on) f[e] = fmaxf(f[e], a.alpha * f[e]);
+                }
+                uint4 hi, lo;
+                split8_bf16(f, hi, lo);
+                pk = part ? lo : hi;
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + (((uint32_t)j ^ swz) << 4)), "r"(pk.x), "r"(pk.y),
+                           "r"(pk.z), "r"(pk.w)
+                           : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(8 + gi) : "memory");
+          if (r == 0) {
+            tma_store_4d(&tmY, stg, cc0 + (out_f32 ? 16 * part : part * a.lo_off), w0, h0, n);   // clipped at the image border
+            bulk_commit_group();
+          }
+        }
+      } else if (pool && !out_f32 && (a.ldy & 7) == 0 && (a.lo_off & 7) == 0)
         epilogue_chunk_pooled_bf16(a, sum, s_scale, s_shift, cc0, cc0, valid_px, orow, leaky_on, lane);
       else
         epilogue_chunk<32>(a, sum, s_scale, s_shift, cc0, cc0, valid, orow, pool, leaky_on, out_f32);
       __syncwarp();
     }
+    if (tma_st && r == 0) bulk_wait_group_read<0>();      // smem must outlive the last box store's read
   }
 
   tc_fence_before();
@@ -1323,13 +1383,20 @@ static int conv_is_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
     b_region = 0;
     stage_bytes += 3 * (size_t)a.b_sub_bytes;
   }
-  int stages = (int)((SMEM_BUDGET - b_region) / stage_bytes);
+  // un-pooled outputs leave through 32 KB of staging + TMA box stores when at least three ring stages remain next to it
+  const size_t IS_STG = 4 * 8192;
+  a.tma_store = 0;
+  if (!pool && !env().conv_is_no_tma_store && a.ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(p->y) & 15) == 0 &&
+      (!split_out || a.lo_off % 8 == 0) && (SMEM_BUDGET - b_region - IS_STG) / stage_bytes >= 3)
+    a.tma_store = 1;
+  const size_t stg_bytes = a.tma_store ? IS_STG : 0;
+  int stages = (int)((SMEM_BUDGET - b_region - stg_bytes) / stage_bytes);
   if (stages < 3) return Y2_OK;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   a.stages = stages;
   fastdiv_init((uint32_t)a.tiles_w, &a.fd_w_mul, &a.fd_w_shr);
   fastdiv_init((uint32_t)a.tiles_h, &a.fd_h_mul, &a.fd_h_shr);
-  const size_t smem = b_region + (size_t)stages * stage_bytes + 1024;
+  const size_t smem = b_region + (size_t)stages * stage_bytes + stg_bytes + 1024;
   int rc = load_driver_entry_points();
   if (rc != Y2_OK) return rc;
   CUtensorMap tmA, tmB;
@@ -1351,7 +1418,19 @@ static int conv_is_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
                       CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("y2_conv_fwd_bf16 (input-stationary): tensor map B encode failed (CUresult %d)", (int)r); return Y2_ERR_DRIVER; }
   }
-  (void)pool;
+  CUtensorMap tmY;
+  memset(&tmY, 0, sizeof(tmY));
+  if (a.tma_store) {
+    const cuuint64_t es = out_f32 ? 4 : 2;
+    cuuint64_t dims[4] = {(cuuint64_t)(split_out ? a.lo_off + p->Cout : p->Cout), (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t strides[3] = {(cuuint64_t)a.ldy * es, (cuuint64_t)p->W * a.ldy * es, (cuuint64_t)p->H * p->W * a.ldy * es};
+    cuuint32_t box[4] = {out_f32 ? 16u : 32u, (cuuint32_t)IS_OUT_W, (cuuint32_t)IS_TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encodeTiled(&tmY, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p->y, dims, strides,
+                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("y2_conv_fwd_bf16 (input-stationary): tensor map Y encode failed (CUresult %d)", (int)r); return Y2_ERR_DRIVER; }
+  }
   const int groups = (a.m_tiles + 1) / 2;
   const int npairs = groups < g_num_sms / 2 ? groups : g_num_sms / 2;
   cudaLaunchConfig_t cfg;
@@ -1365,10 +1444,10 @@ static int conv_is_try(const y2_conv_params* p, cudaStream_t st, int* handled) {
   cfg.numAttrs = fill_launch_attrs(attr, 2u);
   if (a.row_bytes == 64) {
     Y2_CUDA(cudaFuncSetAttribute(conv_is_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_is_kernel<1>, tmA, tmB, a));
+    Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_is_kernel<1>, tmA, tmB, tmY, a));
   } else {
     Y2_CUDA(cudaFuncSetAttribute(conv_is_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_is_kernel<2>, tmA, tmB, a));
+    Y2_CUDA(cudaLaunchKernelEx(&cfg, conv_is_kernel<2>, tmA, tmB, tmY, a));
   }
   Y2_LAUNCHED();
   *handled = 1;
@@ -1611,10 +1690,16 @@ extern "C" int y2_conv_fwd_bf16(const y2_conv_params* p, y2_stream_t stream) {
     const bool shape_f32 = shape_bf16 || (a.first_layer && block_n == 32 && p->Cout == 32) ||
                            (!a.first_layer && block_n == 64 && a.row_bytes == 64 && a.cta2 && p->Cout == 64);
     // (64 columns on 128-byte operand rows -- layer 4 without the input-stationary kernel: 131 -> 141 us, not enabled)
-    if (common && !out_f32 && shape_bf16 && (!split_out || (a.lo_off % 8 == 0 && env().conv_tma_store_split))) a.tma_store = 1;
+    if (common && !out_f32 && shape_bf16 && !split_out) a.tma_store = 1;
+    if (!out_f32 && split_out && shape_bf16 && a.lo_off % 8 == 0 && env().conv_tma_store_split) {
+      const size_t stg = env().conv_tma_store_split == 2 ? STG_BYTES / 2 : STG_BYTES;
+      if (a.a_mode == 2 && !pool && p->Cout % 32 == 0 && a.ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(p->y) & 15) == 0 &&
+          EPI_GROUPS == 4 && b_region + 3 * (size_t)stage_bytes + stg <= SMEM_BUDGET && !env().conv_no_tma_store)
+        a.tma_store = env().conv_tma_store_split == 2 ? 2 : 1;
+    }
     if (common && out_f32 && shape_f32 && !env().conv_no_tma_store_f32) a.tma_store = 1;
   }
-  const size_t stg_bytes = a.tma_store ? STG_BYTES : 0;
+  const size_t stg_bytes = a.tma_store == 2 ? STG_BYTES / 2 : (a.tma_store ? STG_BYTES : 0);
   int stages = (int)((SMEM_BUDGET - b_region - stg_bytes) / stage_bytes);
   if (stages > 12) stages = 12;
   if (stages < 2) {
