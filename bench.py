@@ -596,6 +596,7 @@ def run_train(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    graphed = tr.graph is not None or tr.seg_graphs is not None
     peaks = load_peaks()
     flops_img, _ = conv_flops_per_image(IS, of)
     alg = 3.0 * N * flops_img                                   # forward + data gradient + weight gradient
@@ -619,9 +620,10 @@ def run_train(args):
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='bf16', data='synthetic', config=train_config(world, args.loss),
                 e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=20),
-                gpu_launches=int(tr.launches_per_step * args.steps if tr.graph is not None else launches),
-                launches_per_step=int(tr.launches_per_step if tr.graph is not None else launches // max(args.steps, 1)),
-                cuda_graph=tr.graph is not None, roofline=roofline, cpu_baseline=cpu, clocks=clocks, phases_ms=phases,
+                gpu_launches=int(tr.launches_per_step * args.steps if graphed else launches),
+                launches_per_step=int(tr.launches_per_step if graphed else launches // max(args.steps, 1)),
+                cuda_graph=('one graph' if tr.graph is not None else '%d graphs (one per stretch between bucket launches) + update'
+                            % len(tr.seg_graphs[0])) if graphed else False, roofline=roofline, cpu_baseline=cpu, clocks=clocks, phases_ms=phases,
                 allreduce=dict(bytes_per_step=int(tr.arena_elems * 4) if world > 1 else 0, buckets=len(tr.buckets) if world > 1 else 0,
                                exposed_ms=phases.get('allreduce_exposed')),
                 final_loss=final_loss)

@@ -5,7 +5,7 @@ defaults, all layers in training mode, a log line every 10 iterations, a snapsho
 the reference's `sess.run([merged, loss, train_op, ious, object_mask], ...)` is `Yolo2Trainer.step` (forward,
 get_loss, backward, BN moving-average updates, Adam) on libyolo2_b200.so.
 
-    python tensorflow_yolo2_b200/pascal/pascal_train_darknet.py [--iters N] [--synthetic]
+    python tensorflow_yolo2_b200/pascal/pascal_train_darknet.py [--iters N] [--synthetic] [--no-graph]
     torchrun --nproc-per-node 8 ... pascal_train_darknet.py      # data parallel: NCCL gradient all-reduce
 
 --synthetic feeds random images/labels when VOCdevkit is not on disk (the reference asserts in that case,
@@ -88,7 +88,7 @@ def main(argv):
     store = default_store()
     trainer = Yolo2Trainer(BATCH_SIZE, IMAGE_SIZE, 5 * B + NUM_CLASS, store=store, loss='v1', num_class=NUM_CLASS, B=B,
                            lambda_coord=float(cfg.LAMBDA_COORD), lambda_noobj=float(cfg.LAMBDA_NOOBJ),
-                           device=torch.device('cuda', local))
+                           device=torch.device('cuda', local), use_cuda_graph='--no-graph' not in argv)
     last_iter_num = restore_darknet19_variables(None, imdb, net_name='darknet19', save_epoch=False)
     if last_iter_num > 0:
         # tf.train.Saver() restores every global variable (:54,83): Adam's slots and beta powers come back with the weights

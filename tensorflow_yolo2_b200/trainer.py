@@ -85,14 +85,16 @@ class Yolo2Trainer:
         self.layers = (create_classifier_variables(self.store, self.OF) if loss == 'softmax'
                        else create_variables(self.store, self.OF))
         self.iteration = 0
-        # the whole step (forward, loss, backward, Adam: ~290 launches) replayed as ONE CUDA graph; single-process only --
-        # with world > 1 the NCCL buckets are issued eagerly on NCCL's stream so that they overlap the backward kernels
-        # (capturing the NCCL buckets into the graph as well was tried on 2 GPUs: the capture dead-locks -- not offered)
+        # the whole step (forward, loss, backward, Adam: ~245 launches) replayed as ONE CUDA graph.  With world > 1 the NCCL
+        # buckets stay eager launches on NCCL's stream (capturing them too dead-locked in a 2-GPU trial) and the step is cut
+        # into one graph per stretch between two bucket launches: [forward, loss, backward down to the first bucket's last
+        # layer], [... to the second bucket], ..., [update] -- see _enqueue_segment / step.
         import os as _os
-        self.use_cuda_graph = bool(use_cuda_graph) and self.world == 1
+        self.use_cuda_graph = bool(use_cuda_graph)
         if _os.environ.get('Y2_BUCKET_MB'):
             bucket_bytes = int(float(_os.environ['Y2_BUCKET_MB']) * (1 << 20))
         self.graph = None
+        self.seg_graphs = None
         self.launches_per_step = 0
         self._grads_clean = True                    # the gradient arena is all zero (fresh, or cleared by the last update)
         dev = self.device
@@ -271,30 +273,38 @@ class Yolo2Trainer:
         if not self._grads_clean:                   # (only when backward runs twice without an update in between: the
             self.grads.zero_()                      #  update kernel leaves the arena cleared)
         self._grads_clean = False
-        nl = len(self.layers)
-        dy = self.dnet
         self.reducer.begin()
-        for li in reversed(range(nl)):
-            L, g, s, P, G = self.layers[li], self.geom[li], self.stats[li], self.P[li], self.G[li]
-            H, M, cout, cin, k = g['H'], g['M'], L['cout'], L['cin'], L['k']
-            if capture is not None:
-                capture[li] = dy.clone()
-            dh = self.dh[:M * g['ld_dh']].view(M, g['ld_dh'])
-            ops.bn_leaky_pool_bwd(self.raw[li], dy, s['mean'], s['var'], P['gamma'], P['beta'], self.N, H, H, cout,
-                                  ldh=g['ldh'], leaky=True, pool=L['pool'], ld_dh=g['ld_dh'], dgamma=G['gamma'],
-                                  dbeta=G['beta'], dh=dh, workspace=self.ws)
-            xin = self.x0 if li == 0 else self.acts[li - 1]
-            if li == 0:
-                ops.conv_wgrad_c3(xin, dh, cout, G['W'])
-            else:
-                ops.conv_wgrad_bf16(xin, dh, k, cin, cout, G['W'])
-                ops.pack_weights_dgrad_bf16(P['W'], g['ld_dh'], out=self.packed_dgrad[li])
-                dx = self.dx[li & 1][:M * cin].view(self.N, H, H, cin)
-                ops.conv_fwd_bf16(dh.view(self.N, H, H, g['ld_dh']), self.packed_dgrad[li], k, g['ld_dh'], cin, scale=None,
-                                  shift=None, leaky=False, pool=False, out=dx)
-                dy = dx
+        for li in reversed(range(len(self.layers))):
+            self._backward_layer(li, capture)
             self.reducer.layer_done(li)
         self.reducer.finish(scale=False)            # sums; the 1/world of the mean is applied inside the update kernel
+
+    def _dy_of(self, li):
+        """Gradient w.r.t. layer li's output: the loss gradient for the last layer, else the data gradient layer li + 1 wrote."""
+        if li == len(self.layers) - 1:
+            return self.dnet
+        g, L = self.geom[li + 1], self.layers[li + 1]
+        return self.dx[(li + 1) & 1][:g['M'] * L['cin']].view(self.N, g['H'], g['H'], L['cin'])
+
+    def _backward_layer(self, li, capture=None):
+        L, g, s, P, G = self.layers[li], self.geom[li], self.stats[li], self.P[li], self.G[li]
+        H, M, cout, cin, k = g['H'], g['M'], L['cout'], L['cin'], L['k']
+        dy = self._dy_of(li)
+        if capture is not None:
+            capture[li] = dy.clone()
+        dh = self.dh[:M * g['ld_dh']].view(M, g['ld_dh'])
+        ops.bn_leaky_pool_bwd(self.raw[li], dy, s['mean'], s['var'], P['gamma'], P['beta'], self.N, H, H, cout,
+                              ldh=g['ldh'], leaky=True, pool=L['pool'], ld_dh=g['ld_dh'], dgamma=G['gamma'],
+                              dbeta=G['beta'], dh=dh, workspace=self.ws)
+        xin = self.x0 if li == 0 else self.acts[li - 1]
+        if li == 0:
+            ops.conv_wgrad_c3(xin, dh, cout, G['W'])
+        else:
+            ops.conv_wgrad_bf16(xin, dh, k, cin, cout, G['W'])
+            ops.pack_weights_dgrad_bf16(P['W'], g['ld_dh'], out=self.packed_dgrad[li])
+            dx = self.dx[li & 1][:M * cin].view(self.N, H, H, cin)
+            ops.conv_fwd_bf16(dh.view(self.N, H, H, g['ld_dh']), self.packed_dgrad[li], k, g['ld_dh'], cin, scale=None,
+                              shift=None, leaky=False, pool=False, out=dx)
 
     def _set_lr(self):
         """TF's bias-corrected step size of iteration self.iteration -> device scalar (a 4-byte async copy, outside the graph)."""
@@ -322,16 +332,76 @@ class Yolo2Trainer:
         self.backward()
         self.update(_lr_set=True)
 
+    # ---- data parallel: one graph per stretch between two bucket launches ----
+    def _segments(self):
+        """[(first layer, last layer)] of the backward stretches, in execution (descending layer) order; stretch i ends with
+        the layer after which bucket i is complete."""
+        segs, hi = [], len(self.layers) - 1
+        for b in self.buckets:
+            segs.append((hi, b['ready_after']))
+            hi = b['ready_after'] - 1
+        assert hi == -1, 'the last bucket must close at layer 0'
+        return segs
+
+    def _enqueue_segment(self, i, seg):
+        if i == 0:
+            self.forward()
+            self.loss()
+        for li in range(seg[0], seg[1] - 1, -1):
+            self._backward_layer(li)
+
+    def _step_segmented(self):
+        """world > 1 with CUDA graphs: replay stretch i, launch bucket i's all-reduce (eager, NCCL's stream, overlapping the
+        next stretch), ..., wait for the buckets, replay the update."""
+        segs = self._segments()
+        if self.seg_graphs is None:
+            if not self._grads_clean:
+                self.grads.zero_()
+                self._grads_clean = True
+            # warm-up outside the capture (every rank runs it, collectives included), then restore what it changed
+            snap = [t.clone() for t in self._graph_state()]
+            self._enqueue_step()
+            torch.cuda.synchronize(self.device)
+            for t, c in zip(self._graph_state(), snap):
+                t.copy_(c)
+            self.grads.zero_()
+            n0 = ops.launch_count()
+            pool = torch.cuda.graph_pool_handle()
+            graphs = []
+            for i, seg in enumerate(segs):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    self._enqueue_segment(i, seg)
+                graphs.append(g)
+            gu = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gu, pool=pool):
+                self.update(_lr_set=True)
+            self.launches_per_step = ops.launch_count() - n0
+            for t, c in zip(self._graph_state(), snap):       # (capture does not execute, but keep the invariant explicit)
+                t.copy_(c)
+            self.seg_graphs = (graphs, gu)
+        graphs, gu = self.seg_graphs
+        self.reducer.begin()
+        for g, seg in zip(graphs, segs):
+            g.replay()
+            self.reducer.layer_done(seg[1])
+        self.reducer.finish(scale=False)
+        gu.replay()
+        self._grads_clean = True
+        self.store.version += 1
+
     def step(self, images=None, capture=None):
         """One training iteration on the current stream.  images: uint8 [N,IS,IS,3] BGR (host or device) or None
         to reuse self.in_u8.  Returns the device tensor terms[5] (the loss is terms[4])."""
         if images is not None:
             t = torch.as_tensor(images)
             if t.dtype == torch.uint8:
-                self.in_f32 = None
+                if self.in_f32 is not None:                 # the input kind is baked into a captured step
+                    self.in_f32, self.graph, self.seg_graphs = None, None, None
                 self.in_u8.copy_(t, non_blocking=True)
             else:       # float images as produced by pascal_voc.get() (float64 in the reference, cast at the feed)
                 if self.in_f32 is None:
+                    self.graph, self.seg_graphs = None, None
                     self.in_f32 = torch.empty((self.N, self.IS, self.IS, 3), dtype=torch.float32, device=self.device)
                 self.in_f32.copy_(t.to(torch.float32), non_blocking=True)
         self.iteration += 1
@@ -342,6 +412,9 @@ class Yolo2Trainer:
                 self.loss()
                 self.backward(capture)
                 self.update(_lr_set=True, zero_grad=capture is None)      # (a capturing caller reads the gradients afterwards)
+                return self.terms
+            if self.world > 1:
+                self._step_segmented()
                 return self.terms
             if self.graph is None:
                 if not self._grads_clean:

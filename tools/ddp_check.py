@@ -60,11 +60,29 @@ def main():
     pmax = p.clone()
     dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
     same = bool(torch.equal(p, pmax)) or float((p - pmax).abs().max()) < 1e-6
+    # (c) the data-parallel step as CUDA graphs (one per stretch between two bucket launches, NCCL eager in between) against
+    #     eager launches: three iterations each from the same initial weights
+    res = []
+    for graph in (False, True):
+        st_c, _ = make_store(45, tame=True)
+        tr = Yolo2Trainer(N, IS, 45, store=st_c, loss='v1', B=5, device=dev, bucket_bytes=8 << 20, use_cuda_graph=graph)
+        tr.set_labels(lab)
+        losses = [float(tr.step(img)[4]) for _ in range(3)]
+        torch.cuda.synchronize()
+        assert (tr.seg_graphs is not None) == graph and tr.iteration == 3
+        res.append((losses, tr.params.clone()))
+    (l0, p0), (l1, p1) = res
+    graph_ok = bool(np.allclose(l0, l1, rtol=2e-2)) and float((p0 - p1).abs().mean()) < 3e-4 and float((p0 - p1).abs().max()) < 1e-2
+    pg = p1.clone()
+    dist.all_reduce(pg, op=dist.ReduceOp.MAX)
+    graph_ok = graph_ok and (bool(torch.equal(p1, pg)) or float((p1 - pg).abs().max()) < 1e-6)
+    ok = ok and graph_ok
     flag = torch.tensor([1.0 if (ok and same) else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print('ddp_check world=%d buckets=%d grad rel err %.3g weights identical %s -> %s' %
-              (world, len(ddp.buckets), err, same, 'OK' if flag.item() == 1.0 else 'FAIL'), flush=True)
+        print('ddp_check world=%d buckets=%d grad rel err %.3g weights identical %s, segmented graphs == eager %s (losses %s vs %s) -> %s' %
+              (world, len(ddp.buckets), err, same, graph_ok, np.round(l0, 4).tolist(), np.round(l1, 4).tolist(),
+               'OK' if flag.item() == 1.0 else 'FAIL'), flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 
