@@ -38,6 +38,21 @@ def make_buckets(layer_ranges, bucket_bytes, elem_bytes=4):
     return buckets
 
 
+def bucket_segments(buckets, n_layers):
+    """The backward pass cut at the bucket launches: [(first layer, last layer)] in execution (descending layer) order, stretch i
+    ending with the layer after which bucket i is complete.  Each stretch is one CUDA graph of the data-parallel step
+    (Yolo2Trainer._step_segmented); the all-reduce of bucket i is launched between stretch i and stretch i + 1."""
+    segs, hi = [], int(n_layers) - 1
+    for b in buckets:
+        if not 0 <= b['ready_after'] <= hi:
+            raise ValueError('buckets must be ordered by descending ready_after layer')
+        segs.append((hi, b['ready_after']))
+        hi = b['ready_after'] - 1
+    if hi != -1:
+        raise ValueError('the last bucket must close at layer 0')
+    return segs
+
+
 class BucketedAllReduce:
     def __init__(self, flat, buckets, group=None, world=None):
         self.flat, self.buckets, self.group = flat, buckets, group

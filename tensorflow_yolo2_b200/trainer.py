@@ -30,7 +30,7 @@ import torch
 
 from . import ops
 from .engine import create_classifier_variables, create_variables
-from .parallel import BucketedAllReduce, make_buckets
+from .parallel import BucketedAllReduce, bucket_segments, make_buckets
 from .variables import VariableStore
 from .yolo2_nets.net_utils import VOC_ANCHORS
 
@@ -334,14 +334,7 @@ class Yolo2Trainer:
 
     # ---- data parallel: one graph per stretch between two bucket launches ----
     def _segments(self):
-        """[(first layer, last layer)] of the backward stretches, in execution (descending layer) order; stretch i ends with
-        the layer after which bucket i is complete."""
-        segs, hi = [], len(self.layers) - 1
-        for b in self.buckets:
-            segs.append((hi, b['ready_after']))
-            hi = b['ready_after'] - 1
-        assert hi == -1, 'the last bucket must close at layer 0'
-        return segs
+        return bucket_segments(self.buckets, len(self.layers))
 
     def _enqueue_segment(self, i, seg):
         if i == 0:

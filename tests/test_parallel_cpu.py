@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from tensorflow_yolo2_b200.parallel import BucketedAllReduce, make_buckets, shard_range
+from tensorflow_yolo2_b200.parallel import BucketedAllReduce, bucket_segments, make_buckets, shard_range
 
 
 def _free_port():
@@ -42,6 +42,26 @@ def test_make_buckets_contiguous_and_ordered():
     assert all((x['end'] - x['start']) * 4 >= 4 * 3000 for x in b[:-1])
 
 
+def test_bucket_segments_cover_the_backward_pass():
+    """The data-parallel step replays one CUDA graph per stretch between two bucket launches: the stretches tile layers
+    n-1 .. 0 in order and stretch i ends exactly where bucket i becomes complete."""
+    ranges, off = [], 0
+    for layer, n in zip(range(9, -1, -1), [1000, 50, 4000, 10, 10, 10, 7000, 64, 64, 128]):
+        ranges.append((layer, off, off + n))
+        off += n
+    b = make_buckets(ranges, bucket_bytes=4 * 3000)
+    segs = bucket_segments(b, 10)
+    assert len(segs) == len(b) and segs[0][0] == 9 and segs[-1][1] == 0
+    assert [s[1] for s in segs] == [x['ready_after'] for x in b]
+    for (h0, l0), (h1, l1) in zip(segs, segs[1:]):
+        assert h0 >= l0 and h1 == l0 - 1
+    assert bucket_segments(make_buckets(ranges, bucket_bytes=1 << 40), 10) == [(9, 0)]          # one bucket: one stretch
+    with pytest.raises(ValueError):
+        bucket_segments(b[:-1], 10)                                                           # does not reach layer 0
+    with pytest.raises(ValueError):
+        bucket_segments(list(reversed(b)), 10)
+
+
 def _worker(rank, world, port, q):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -62,6 +82,14 @@ def _worker(rank, world, port, q):
         dist.all_gather(gathered, mine)
         want = sum(gathered) / world
         ok = torch.allclose(flat, want, rtol=1e-6, atol=1e-7)
+        # the graphed data-parallel step calls layer_done only at the END of each stretch: every bucket must still be launched
+        flat2 = mine.clone()
+        red2 = BucketedAllReduce(flat2, buckets, None, world)
+        red2.begin()
+        for hi, lo in bucket_segments(buckets, 5):
+            red2.layer_done(lo)
+        red2.finish()
+        ok = ok and torch.allclose(flat2, want, rtol=1e-6, atol=1e-7)
         # batch sharding: the ranks' shards tile the global batch
         lo, hi = shard_range(13, rank, world)
         idx = torch.zeros(13)
