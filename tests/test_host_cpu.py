@@ -146,3 +146,27 @@ def test_checkpoint_discovery_resume_and_warm_start(cfg_scratch):
         np.testing.assert_array_equal(np.asarray(st[n]), want[n])
     assert [os.path.basename(p) for p in nu.get_ordered_ckpts(None, imdb, 'darknet19', save_epoch=False)] == \
         [cfg.TRAIN_SNAPSHOT_PREFIX + '_iter_40000.ckpt', cfg.TRAIN_SNAPSHOT_PREFIX + '_iter_80000.ckpt']
+
+
+def test_ilsvrc_cls_synthetic_loader_matches_reference_read_path():
+    """ilsvrc_cls (the ImageNet scripts' database, ilsvrc2017_cls_multithread.py:95-117,320-323,408-415) on its in-memory
+    synthetic set: batches are cv2.resize((IS, IS)) -> float32 -> x/255*2-1 of the records in cursor order, labels 1-D, the
+    epoch counter advances and the list is reshuffled when the cursor wraps; augmentation / prefetch options raise."""
+    import cv2
+    from tensorflow_yolo2_b200.img_dataset.ilsvrc2017_cls import ilsvrc_cls
+    db = ilsvrc_cls('val', batch_size=6, image_size=64, synthetic=10)
+    assert db.name == 'ilsvrc_2017_cls' and db.num_class == 1000 and db.image_num == 10 and db.total_batch == 2 and db.epoch == 1
+    recs = [dict(r) for r in db.gt_labels[:6]]
+    images, labels = db.get()
+    assert images.shape == (6, 64, 64, 3) and labels.shape == (6,)
+    for k, r in enumerate(recs):
+        want = cv2.resize(db._synthetic[r['imname']], (64, 64)).astype(np.float32) / 255.0 * 2.0 - 1.0
+        np.testing.assert_array_equal(images[k].astype(np.float32), want)
+        assert labels[k] == r['label']
+    assert images.min() >= -1.0 and images.max() <= 1.0
+    db.get()                                           # records 6..9, wraps: epoch 2, cursor back at 2
+    assert db.epoch == 2 and db.cursor == 2
+    with pytest.raises(NotImplementedError):
+        ilsvrc_cls('train', data_aug=True, synthetic=4)
+    with pytest.raises(NotImplementedError):
+        ilsvrc_cls('train', multithread=True, synthetic=4)
