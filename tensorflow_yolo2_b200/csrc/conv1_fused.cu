@@ -94,6 +94,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "memory");
 }
 
+// packed float32 pairs (sm_100 FADD2 / FMUL2: one issue slot for two lanes of arithmetic; IEEE results identical to the scalar ops)
+__device__ __forceinline__ void c1_add2(float& a0, float& a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb, rc;\n mov.b64 ra, {%0, %1};\n mov.b64 rb, {%2, %3};\n add.rn.f32x2 rc, ra, rb;\n mov.b64 {%0, %1}, rc; }"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void c1_mul2(float& d0, float& d1, float a0, float a1, float b) {
+  asm("{ .reg .b64 ra, rb, rc;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %4};\n mul.rn.f32x2 rc, ra, rb;\n mov.b64 {%0, %1}, rc; }"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b));
+}
+
 struct C1Tile {
   int n, ph0, pw0;
 };
@@ -339,11 +351,16 @@ conv1_u8_pool_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
         const float shv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
         float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float m = fmaxf(fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])),
-                          fmaxf(__uint_as_float(v2[e]), __uint_as_float(v3[e])));
-          m += shv[e];
-          f[e] = fmaxf(m, alpha * m);
+        for (int e = 0; e < 8; e += 2) {
+          float m0 = fmaxf(fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])),
+                           fmaxf(__uint_as_float(v2[e]), __uint_as_float(v3[e])));
+          float m1 = fmaxf(fmaxf(__uint_as_float(v0[e + 1]), __uint_as_float(v1[e + 1])),
+                           fmaxf(__uint_as_float(v2[e + 1]), __uint_as_float(v3[e + 1])));
+          float t0, t1;
+          c1_add2(m0, m1, shv[e], shv[e + 1]);            // m += shift      (two channels per instruction)
+          c1_mul2(t0, t1, m0, m1, alpha);                 // alpha * m
+          f[e] = fmaxf(m0, t0);
+          f[e + 1] = fmaxf(m1, t1);
         }
         uint32_t o[4];
 #pragma unroll
